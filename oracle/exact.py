@@ -1,0 +1,64 @@
+"""ORACLE (test infrastructure only).  Brute-force enumeration of the joint distribution,
+restating /root/reference/src/exact.jl:5-41 (exact_prob), :43-75 (site marginals) and the
+pair marginals used by every small-tree test of the reference (test/glauber_small_tree.jl:40-72).
+Vectorised over the q^{N(T+1)} configurations with numpy; usable up to ~2e6 configurations."""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+
+def exact_prob(bp):
+    g, w, phi, psi, q = bp.g, bp.w, bp.phi, bp.psi, bp.q
+    N, L = g.N, bp.T + 1
+    dims = [q[i] for i in range(N) for _ in range(L)]  # variable (i,t) -> axis i*L+t
+    Q = int(np.prod(dims))
+    assert Q <= 4_000_000, f"{Q} configurations"
+    grids = np.indices(dims).reshape(len(dims), -1)  # [var, config] 0-based
+    X = lambda i, t: grids[i * L + t]
+    logp = np.zeros(Q)
+    neigh = [[g.dst[e] for e in g.out_edges[i]] for i in range(N)]
+    with np.errstate(divide="ignore"):
+        for i in range(N):
+            logp += np.log(np.asarray(phi[i][0])[X(i, 0)])
+            for t in range(L - 1):
+                # tabulate w over (x', x_neigh..., x)
+                qn = [q[k] for k in neigh[i]]
+                tab = np.zeros([q[i]] + qn + [q[i]])
+                for idx in np.ndindex(*tab.shape):
+                    tab[idx] = w[i][t](idx[0] + 1, [v + 1 for v in idx[1:-1]], idx[-1] + 1)
+                sel = (X(i, t + 1),) + tuple(X(k, t) for k in neigh[i]) + (X(i, t),)
+                logp += np.log(tab[sel])
+                logp += np.log(np.asarray(phi[i][t + 1])[X(i, t + 1)])
+        for e in range(g.ne):
+            i, j = g.src[e], g.dst[e]
+            for t in range(L):
+                logp += 0.5 * np.log(np.asarray(psi[e][t])[X(i, t), X(j, t)])
+    mx = logp.max()
+    logZ = mx + np.log(np.exp(logp - mx).sum())
+    p = np.exp(logp - logZ)
+    return p.reshape(dims), float(np.exp(logZ)), float(logZ)
+
+
+def exact_marginals(bp, p):
+    N, L = bp.g.N, bp.T + 1
+    out = []
+    for i in range(N):
+        out.append([p.sum(axis=tuple(a for a in range(N * L) if a != i * L + t)) for t in range(L)])
+    return out
+
+
+def exact_pair_marginals(bp, p):
+    g = bp.g
+    N, L = g.N, bp.T + 1
+    out = []
+    for e in range(g.ne):
+        i, j = g.src[e], g.dst[e]
+        row = []
+        for t in range(L):
+            a, b = i * L + t, j * L + t
+            m = p.sum(axis=tuple(c for c in range(N * L) if c not in (a, b)))
+            row.append(m if a < b else m.T)
+        out.append(row)
+    return out

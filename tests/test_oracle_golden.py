@@ -1,0 +1,142 @@
+"""Pins the oracle (CPU restatement) against the reference's own known-answer test and against
+brute-force enumeration, mirroring the reference's test strategy."""
+import numpy as np
+import pytest
+
+from oracle import exact, factors as F, mpbp as O, tt
+
+
+# /root/reference/test/sis_infinite_graph.jl:21-29 -- the only numeric literals in the reference test-suite
+SIS_INFINITE_GOLDEN = np.array([
+    [0.9000000001671186, 0.0999999998328814],
+    [0.8932690998131098, 0.10673090018689023],
+    [0.8899420329322244, 0.11005796706777556],
+    [0.8884643888492034, 0.11153561115079656],
+    [0.8880305235706524, 0.1119694764293476],
+    [0.8882121515614524, 0.11178784843854758],
+    [0.8887717202217936, 0.1112282797782064],
+])
+
+
+def test_sis_infinite_graph_golden():
+    # inputs: /root/reference/test/sis_infinite_graph.jl:3-18
+    T, k, gamma, lam, rho = 6, 3, 0.1, 0.1, 0.2
+    w = [F.SISFactor(lam, rho) for _ in range(T + 1)]
+    phi = [np.array([1 - gamma, gamma]) if t == 0 else np.ones(2) for t in range(T + 1)]
+    bp = O.mpbp_infinite_graph(k, w, 2, phi)
+    iters, _ = O.iterate(bp, maxiter=200, trunc=tt.TruncBond(10), tol=1e-14)
+    b = np.array(O.beliefs(bp)[0])
+    assert iters < 200
+    # reference asserts isapprox with rtol = sqrt(eps); we are ~4e-11 away
+    assert np.max(np.abs(b - SIS_INFINITE_GOLDEN)) < 1e-9
+
+
+def test_glauber_infinite_vs_complete_graph():
+    # /root/reference/test/glauber_infinite_graph.jl:7-45 (deterministic inputs, run without damping)
+    T, k, m0 = 3, 3, 0.5
+    w = [F.HomogeneousGlauberFactor(1.0, 0.0, 1.0) for _ in range(T + 1)]
+    phi = [np.array([(1 + m0) / 2, (1 - m0) / 2]) if t == 0 else np.ones(2) for t in range(T + 1)]
+    phi[1] = np.array([0.4, 0.6])
+    phi[-1] = np.array([0.95, 0.05])
+    bp = O.mpbp_infinite_graph(k, w, 2, phi)
+    O.iterate(bp, maxiter=150, trunc=tt.TruncThresh(0.0), tol=1e-15)
+    f_inf = O.bethe_free_energy(bp)
+    N = k + 1
+    g = O.BiDiGraph(N, [(a, b) for a in range(N) for b in range(a + 1, N)])
+    bpx = O.MPBP(g, [w] * N, [2] * N, T, phi=[phi] * N)
+    O.iterate(bpx, maxiter=150, trunc=tt.TruncThresh(0.0), tol=1e-15)
+    f_k4 = O.bethe_free_energy(bpx) / N
+    assert abs(f_inf - 0.98812749675847) < 1e-10  # derived known answer (SURVEY.md header fact 3(ii))
+    assert abs(f_inf - f_k4) < 1e-10
+    assert np.allclose(np.array(O.beliefs(bp)[0]), np.array(O.beliefs(bpx)[0]), atol=1e-10)
+
+
+def _small_tree(rng, T=2):
+    # /root/reference/test/glauber_small_tree.jl:6-24 (own RNG stream: Julia's cannot be replayed)
+    und = [(0, 1), (1, 2), (1, 3)]
+    N = 5
+    g = O.BiDiGraph(N, und)
+    h = rng.standard_normal(N)
+    w = [[F.HomogeneousGlauberFactor(1.0, h[i], 1.0) for _ in range(T + 1)] for i in range(N)]
+    phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(N)]
+    for i in range(N):
+        phi[i][0] = np.array([0.75, 0.25])
+    # N random (soft-ish) one-hot observations
+    for _ in range(N):
+        i, t = rng.integers(N), rng.integers(1, T + 1)
+        o = np.full(2, 1e-3)
+        o[rng.integers(2)] = 1.0
+        phi[i][t] = phi[i][t] * o
+    return g, w, phi
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_glauber_small_tree_vs_exact(generic):
+    rng = np.random.default_rng(111)
+    T = 2
+    g, w, phi = _small_tree(rng, T)
+    if generic:
+        w = [[F.GenericFactor(x) for x in wi] for wi in w]
+    bp = O.MPBP(g, w, [2] * g.N, T, phi=phi)
+    trunc = tt.TruncThresh(0.0) if generic else tt.TruncBondThresh(10)
+    O.iterate(bp, maxiter=20, trunc=trunc, tol=0.0)
+    p, Z, logZ = exact.exact_prob(bp)
+    assert abs(np.exp(-O.bethe_free_energy(bp)) - Z) < 1e-9 * Z
+    be = exact.exact_marginals(bp, p)
+    assert np.allclose(np.array(O.beliefs(bp)), np.array(be), atol=1e-10)
+    pb, _ = O.pair_beliefs(bp)
+    pe = exact.exact_pair_marginals(bp, p)
+    assert np.allclose(np.array(pb), np.array(pe), atol=1e-10)
+    for A in bp.mu:  # test/normalizations.jl:48-52
+        assert abs(tt.lognormalization(A)) < 1e-10
+
+
+def test_sis_small_tree_vs_exact():
+    # /root/reference/test/sis_small_tree.jl:2-51 structure: star graph, T=3, bond cap 4 is exact
+    T = 3
+    g = O.BiDiGraph(4, [(0, 1), (0, 2), (0, 3)])
+    lam, rho, gamma, alpha = 0.5, 0.4, 0.5, 0.1
+    w = [[F.SISFactor(lam, rho, alpha) for _ in range(T + 1)] for _ in range(4)]
+    phi = [[np.array([1 - gamma, gamma]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(4)]
+    rng = np.random.default_rng(5)
+    for i in range(4):
+        o = np.full(2, 0.2)
+        o[rng.integers(2)] = 1.0
+        phi[i][T] = phi[i][T] * o
+    bp = O.MPBP(g, w, [2] * 4, T, phi=phi)
+    O.iterate(bp, maxiter=10, trunc=tt.TruncBondMax(4), tol=0.0)
+    p, Z, _ = exact.exact_prob(bp)
+    assert abs(np.exp(-O.bethe_free_energy(bp)) - Z) < 1e-9 * Z
+    assert np.allclose(np.array(O.beliefs(bp)), np.array(exact.exact_marginals(bp, p)), atol=1e-10)
+    pb, _ = O.pair_beliefs(bp)
+    assert np.allclose(np.array(pb), np.array(exact.exact_pair_marginals(bp, p)), atol=1e-10)
+
+
+def test_sirs_small_tree_vs_exact():
+    # /root/reference/test/sirs_small_tree.jl structure (q=3, TruncThresh(0.0))
+    T = 2
+    g = O.BiDiGraph(3, [(0, 1), (1, 2)])
+    w = [[F.SIRSFactor(0.4, 0.15, 0.2, 0.05) for _ in range(T + 1)] for _ in range(3)]
+    gamma = 0.3
+    phi = [[np.array([1 - gamma, gamma, 0.0]) if t == 0 else np.ones(3) for t in range(T + 1)] for _ in range(3)]
+    phi[0][2] = np.array([0.1, 1.0, 0.3])
+    bp = O.MPBP(g, w, [3] * 3, T, phi=phi)
+    O.iterate(bp, maxiter=6, trunc=tt.TruncThresh(0.0), tol=0.0)
+    p, Z, _ = exact.exact_prob(bp)
+    assert abs(np.exp(-O.bethe_free_energy(bp)) - Z) < 1e-9 * Z
+    assert np.allclose(np.array(O.beliefs(bp)), np.array(exact.exact_marginals(bp, p)), atol=1e-10)
+
+
+def test_schedules_share_fixed_point():
+    # test/sis_heterogeneous_compare_homogeneous.jl:5-35 graph: loopy, TruncBond(3)
+    T = 3
+    und = [(0, 1), (0, 2), (1, 2), (2, 3), (3, 4)]
+    g = O.BiDiGraph(5, und)
+    w = [[F.SISFactor(0.15, 0.12) for _ in range(T + 1)] for _ in range(5)]
+    phi = [[np.array([0.87, 0.13]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(5)]
+    res = []
+    for sched in ("sequential", "parallel"):
+        bp = O.MPBP(g, w, [2] * 5, T, phi=phi)
+        O.iterate(bp, maxiter=200, trunc=tt.TruncBond(3), tol=1e-13, schedule=sched)
+        res.append(np.array(O.beliefs(bp)))
+    assert np.allclose(res[0], res[1], atol=1e-7)
