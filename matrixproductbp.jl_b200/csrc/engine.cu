@@ -1,0 +1,1145 @@
+// engine.cu -- host runtime of the MPBP engine: device state, arena, cavity-DAG planner, launch sequencing,
+// and the extern "C" boundary declared in include/mpbp.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mpbp.h"
+#include "kernels.cuh"
+
+using namespace mpbp;
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CUDA_OK(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) return fail("CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+struct NodeClass {
+  int z = 0, q = 0, nt = 1;
+  bool generic = false;
+  std::vector<int> qn, ny;
+  double* d_pxy = nullptr;
+  std::vector<size_t> pxy_off;
+  size_t pxy_ts = 0;
+  double* d_pyy = nullptr;
+  std::map<std::pair<int, int>, std::pair<size_t, size_t>> pyy;  // (d1,d2) -> (offset, tstride)
+  double* d_w = nullptr;
+  std::vector<size_t> w_off;
+  size_t w_ts = 0;
+  double* d_wd = nullptr;
+  size_t wd_ts = 0;
+  double* d_minit = nullptr;
+  size_t minit_ts = 0;
+};
+
+struct MsgStore {
+  double* data = nullptr;
+  int* bonds = nullptr;
+  double* ls = nullptr;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  void* take(size_t bytes) {
+    size_t a = (used + 255) & ~size_t(255);
+    if (a + bytes > cap) return nullptr;
+    used = a + bytes;
+    return base + a;
+  }
+};
+
+}  // namespace
+
+struct mpbp_state {
+  int device = 0;
+  int64_t N = 0, E2 = 0;
+  int T = 0, L = 1, dmax = 1, qmax = 1;
+  int inf_k = 0;  // > 0: InfiniteRegularGraph(k)
+  std::vector<int> q;
+  std::vector<int64_t> colptr, dst, rev, src;
+  std::vector<int64_t> phi_off, psi_off, marg_off;
+  double *d_phi = nullptr, *d_psi = nullptr;
+  MsgStore msg[2];
+  int cur = 0;
+  int64_t slot = 0;  // doubles per message slot
+  int sstride = 0;   // doubles per message site
+  int* d_qprod = nullptr;
+  double *d_marg = nullptr, *d_logzi = nullptr, *d_logzij = nullptr, *d_f = nullptr, *d_means = nullptr;
+  int64_t* d_marg_off = nullptr;
+  int* d_q = nullptr;
+  double* d_delta = nullptr;
+  int* d_err = nullptr;
+  double* d_flops = nullptr;
+  std::vector<NodeClass> classes;
+  std::vector<int> class_of_node;
+  Arena arena;
+  cudaStream_t st = nullptr;
+  // options
+  double arena_gb = 0;       // 0 = auto
+  double max_group_ops = 1e9;
+  int profile = 0;
+  // counters
+  double n_launch = 0, qr_ms = 0, n_ops = 0, n_edge_updates = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  size_t ev_used = 0;
+  int max_smem = 0;
+};
+
+namespace {
+
+template <class T>
+int upload(T** dptr, const T* host, size_t n) {
+  if (n == 0) n = 1;
+  CUDA_OK(cudaMalloc((void**)dptr, n * sizeof(T)));
+  if (host) CUDA_OK(cudaMemcpy(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int alloc_msg_store(mpbp_state* h, MsgStore& m) {
+  CUDA_OK(cudaMalloc((void**)&m.data, sizeof(double) * h->slot * h->E2));
+  CUDA_OK(cudaMalloc((void**)&m.bonds, sizeof(int) * (h->L + 1) * h->E2));
+  CUDA_OK(cudaMalloc((void**)&m.ls, sizeof(double) * h->E2));
+  return 0;
+}
+
+TTRef msg_ref(const mpbp_state* h, const MsgStore& m, int64_t e, int P) {
+  TTRef r;
+  r.data = m.data + e * h->slot;
+  r.bonds = m.bonds + e * (h->L + 1);
+  r.ls = m.ls + e;
+  r.stride = h->sstride;
+  r.P = P;
+  return r;
+}
+
+int flat_messages(mpbp_state* h, MsgStore& m) {
+  k_flat_messages<<<(unsigned)h->E2, 128, 0, h->st>>>(m.data, m.bonds, m.ls, h->d_qprod, h->slot, h->L, h->E2, h->sstride);
+  h->n_launch++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int common_init(mpbp_state* h) {
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamCreate(&h->st));
+  CUDA_OK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  {
+    const int ms = h->max_smem;
+    CUDA_OK(cudaFuncSetAttribute(k_kron_carry, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_kron_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_small, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_jacobi_project, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 1024));
+    CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 1024));
+    CUDA_OK(cudaFuncSetAttribute(k_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 1024));
+    CUDA_OK(cudaFuncSetAttribute(k_pair_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 2048));
+  }
+  const int L = h->L;
+  h->qmax = *std::max_element(h->q.begin(), h->q.end());
+  h->sstride = h->dmax * h->dmax * h->qmax * h->qmax;
+  h->slot = (int64_t)L * h->sstride;
+  h->phi_off.resize(h->N + 1);
+  h->marg_off.resize(h->N + 1);
+  h->phi_off[0] = 0;
+  for (int64_t i = 0; i < h->N; ++i) h->phi_off[i + 1] = h->phi_off[i] + (int64_t)L * h->q[i];
+  h->marg_off = h->phi_off;
+  h->psi_off.resize(h->E2 + 1);
+  h->psi_off[0] = 0;
+  std::vector<int> qprod(h->E2);
+  for (int64_t e = 0; e < h->E2; ++e) {
+    qprod[e] = h->q[h->src[e]] * h->q[h->dst[e]];
+    h->psi_off[e + 1] = h->psi_off[e] + (int64_t)L * qprod[e];
+  }
+  std::vector<double> ones(std::max(h->phi_off[h->N], h->psi_off[h->E2]), 1.0);
+  if (upload(&h->d_phi, ones.data(), h->phi_off[h->N])) return 1;
+  if (upload(&h->d_psi, ones.data(), h->psi_off[h->E2])) return 1;
+  if (upload(&h->d_qprod, qprod.data(), h->E2)) return 1;
+  if (upload(&h->d_q, h->q.data(), h->N)) return 1;
+  if (upload(&h->d_marg_off, h->marg_off.data(), h->N + 1)) return 1;
+  // beliefs start uniform (flat_mpem1), means accordingly
+  std::vector<double> marg(h->marg_off[h->N]);
+  std::vector<double> means(h->N * L);
+  for (int64_t i = 0; i < h->N; ++i) {
+    for (int64_t k = h->marg_off[i]; k < h->marg_off[i + 1]; ++k) marg[k] = 1.0 / h->q[i];
+    for (int t = 0; t < L; ++t) means[i * L + t] = 0.5 * (h->q[i] + 1);
+  }
+  if (upload(&h->d_marg, marg.data(), marg.size())) return 1;
+  if (upload(&h->d_means, means.data(), means.size())) return 1;
+  const int64_t nzij = h->inf_k > 0 ? h->inf_k : h->E2;
+  std::vector<double> zeros(std::max<int64_t>(std::max<int64_t>(h->N, nzij), 8), 0.0);
+  if (upload(&h->d_logzi, zeros.data(), h->N)) return 1;
+  if (upload(&h->d_logzij, zeros.data(), nzij)) return 1;
+  if (upload(&h->d_f, zeros.data(), h->N)) return 1;
+  if (upload(&h->d_delta, zeros.data(), 1)) return 1;
+  if (upload(&h->d_flops, zeros.data(), 1)) return 1;
+  int zero = 0;
+  if (upload(&h->d_err, &zero, 1)) return 1;
+  if (alloc_msg_store(h, h->msg[0])) return 1;
+  if (flat_messages(h, h->msg[0])) return 1;
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int ensure_arena(mpbp_state* h) {
+  if (h->arena.base) return 0;
+  size_t freeb = 0, total = 0;
+  CUDA_OK(cudaMemGetInfo(&freeb, &total));
+  size_t want = h->arena_gb > 0 ? (size_t)(h->arena_gb * 1e9) : (size_t)(freeb * 0.80);
+  if (h->arena_gb <= 0) {
+    // leave room for a second message buffer (Jacobi schedule)
+    size_t msgb = sizeof(double) * h->slot * h->E2;
+    if (want > msgb + (size_t(1) << 30)) want -= msgb;
+  }
+  CUDA_OK(cudaMalloc((void**)&h->arena.base, want));
+  h->arena.cap = want;
+  return 0;
+}
+
+struct Plan {
+  std::vector<BtJob> bt;
+  std::vector<InitJob> init;
+  std::vector<std::vector<OpDesc>> levels;  // ops by level (scratch pointers filled per group)
+  std::vector<std::vector<int>> capA, capB;  // bond capacities of the operands per op (1 or dmax)
+  std::vector<FinJob> fin;
+  std::vector<BelJob> bel;
+  std::vector<FJob> fj;
+};
+
+TTRef arena_tt(mpbp_state* h, int cap, int P, bool& ok) {
+  TTRef r;
+  r.stride = cap * cap * P;
+  r.P = P;
+  r.data = (double*)h->arena.take(sizeof(double) * (size_t)h->L * r.stride);
+  r.bonds = (int*)h->arena.take(sizeof(int) * (h->L + 1));
+  r.ls = (double*)h->arena.take(sizeof(double));
+  ok = ok && r.data && r.bonds && r.ls;
+  return r;
+}
+
+// bytes of persistent (per-node) arena storage needed by one node update
+size_t node_bytes(const mpbp_state* h, int64_t i) {
+  const NodeClass& c = h->classes[h->class_of_node[i]];
+  const int z = c.z, q = c.q, d = h->dmax, L = h->L;
+  auto tt = [&](int cap, int ny) { return (size_t)L * cap * cap * ny * q * 8 + 4 * (L + 1) + 8 + 3 * 256; };
+  size_t b = 0;
+  b += (size_t)z * tt(d, c.ny[1]);
+  b += tt(1, c.ny[0]);
+  for (int k = 1; k < z; ++k) b += tt(d, c.ny[k + 1]) + tt(d, c.ny[z - k]) + tt(d, c.ny[z - 1]);
+  b += tt(d, c.ny[z]);
+  // finalize + belief scratch
+  const int qjm = h->qmax;
+  size_t fin = (size_t)(L + 1) * (d * q) * (d * q) + (size_t)d * d * q * q * q * qjm + (size_t)d * d * q * q * qjm +
+               (size_t)d * d * q * qjm + 2 * (size_t)d * d * q + (L + 1) + (size_t)(d * q * qjm) * (d * q * qjm);
+  b += (size_t)z * (fin * 8 + 8 * 256);
+  b += ((size_t)L * d * q + (size_t)d * d * q * q) * 8 + 2 * 256;
+  if (h->inf_k > 0) b += (size_t)z * (h->slot * 8 + 4 * (L + 1) + 8 + 3 * 256);
+  return b;
+}
+
+size_t op_scratch_bytes(const mpbp_state* h, int capA, int capB, int X) {
+  const size_t D = (size_t)capA * capB, d = h->dmax, L = h->L;
+  const size_t mrows = D * X;
+  const size_t nch = (mrows + QR_MAX_M - 1) / QR_MAX_M;
+  size_t dbl = L * D * D + mrows * D + (nch > 1 ? nch * D * D : 0) + d * D * X + D * d * X + (d * X) * (d * X) + 2 * d * D;
+  return dbl * 8 + 4 * (L + 1) + 10 * 256;
+}
+
+int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, Plan& P) {
+  const int L = h->L, d = h->dmax;
+  bool ok = true;
+  for (int64_t i : nodes) {
+    const int ci = h->class_of_node[i];
+    if (ci < 0 || ci >= (int)h->classes.size()) return fail("node %lld has no factor class", (long long)i);
+    const NodeClass& c = h->classes[ci];
+    if (c.generic) return fail("generic BPFactor classes are not supported by the device path yet");
+    const int z = c.z, q = c.q;
+    const int64_t e0 = h->inf_k > 0 ? 0 : h->colptr[i];
+    const int deg = h->inf_k > 0 ? h->inf_k : (int)(h->colptr[i + 1] - h->colptr[i]);
+    if (deg != z) return fail("node %lld has degree %d but its class has z=%d", (long long)i, deg, z);
+    if (q != h->q[i]) return fail("node %lld: class q mismatch", (long long)i);
+    // B~_k
+    std::vector<TTRef> src(z);
+    for (int k = 0; k < z; ++k) {
+      const int64_t eout = h->inf_k > 0 ? 0 : e0 + k;
+      const int64_t ein = h->inf_k > 0 ? 0 : h->rev[eout];
+      const int qk = h->inf_k > 0 ? q : h->q[h->dst[eout]];
+      if (qk != c.qn[k]) return fail("node %lld neighbour %d: class qn mismatch", (long long)i, k);
+      BtJob jb;
+      jb.msg = msg_ref(h, h->msg[rb], ein, qk * q);
+      jb.out = arena_tt(h, d, c.ny[1] * q, ok);
+      jb.psi = h->d_psi + h->psi_off[eout];
+      jb.pxy = c.d_pxy + c.pxy_off[k];
+      jb.pxy_tstride = (int)c.pxy_ts;
+      jb.qk = qk;
+      jb.qi = q;
+      jb.ny1 = c.ny[1];
+      src[k] = jb.out;
+      P.bt.push_back(jb);
+    }
+    // init
+    InitJob ij;
+    ij.out = arena_tt(h, 1, c.ny[0] * q, ok);
+    ij.minit = c.d_minit;
+    ij.tstride = (int)c.minit_ts;
+    ij.n = c.ny[0] * q;
+    P.init.push_back(ij);
+    const TTRef init = ij.out;
+    auto add_op = [&](int level, const TTRef& a, int da, const TTRef& b, int db, int ca, int cb, TTRef& out) -> int {
+      auto it = c.pyy.find({da, db});
+      if (it == c.pyy.end()) return fail("class %d lacks the prob_yy table for (d1,d2)=(%d,%d)", ci, da, db);
+      OpDesc op;
+      memset(&op, 0, sizeof op);
+      op.a = a;
+      op.b = b;
+      op.ny1 = c.ny[da];
+      op.ny2 = c.ny[db];
+      op.nyo = c.ny[da + db];
+      op.q = q;
+      out = arena_tt(h, d, op.nyo * q, ok);
+      op.o = out;
+      op.pyy = c.d_pyy + it->second.first;
+      op.pyy_tstride = (int)it->second.second;
+      if ((int)P.levels.size() <= level) {
+        P.levels.resize(level + 1);
+        P.capA.resize(level + 1);
+        P.capB.resize(level + 1);
+      }
+      P.levels[level].push_back(op);
+      P.capA[level].push_back(ca);
+      P.capB[level].push_back(cb);
+      return 0;
+    };
+    std::vector<TTRef> dest(z);
+    TTRef full;
+    if (z == 1) {
+      dest[0] = init;
+      if (add_op(1, src[0], 1, init, 0, d, 1, full)) return 1;
+    } else {
+      std::vector<TTRef> p(z), s(z + 1);
+      p[0] = src[0];
+      for (int k = 1; k < z; ++k)
+        if (add_op(k, p[k - 1], k, src[k], 1, d, d, p[k])) return 1;
+      if (add_op(z, p[z - 1], z, init, 0, d, 1, full)) return 1;
+      s[z] = init;
+      for (int k = z - 1; k >= 1; --k)
+        if (add_op(z - k, src[k], 1, s[k + 1], z - 1 - k, d, k == z - 1 ? 1 : d, s[k])) return 1;
+      for (int k = 1; k < z; ++k)
+        if (add_op(std::max(k - 1, z - k - 1) + 1, p[k - 1], k, s[k + 1], z - 1 - k, d, k == z - 1 ? 1 : d, dest[k]))
+          return 1;
+      dest[0] = s[1];
+    }
+    // outgoing messages
+    for (int j = 0; j < z; ++j) {
+      const int64_t eout = h->inf_k > 0 ? 0 : e0 + j;
+      const int qj = c.qn[j];
+      FinJob fj;
+      memset(&fj, 0, sizeof fj);
+      fj.c = dest[j];
+      if (h->inf_k > 0 && j < z - 1) {
+        // only the last recomputation stays in bp.mu[1] (src/infinite_graph.jl + recursive_bp_factor.jl:154-158)
+        TTRef scratch;
+        scratch.stride = h->sstride;
+        scratch.P = q * qj;
+        scratch.data = (double*)h->arena.take(sizeof(double) * h->slot);
+        scratch.bonds = (int*)h->arena.take(sizeof(int) * (L + 1));
+        scratch.ls = (double*)h->arena.take(sizeof(double));
+        ok = ok && scratch.data && scratch.bonds && scratch.ls;
+        fj.out = scratch;
+      } else {
+        fj.out = msg_ref(h, h->msg[wb], eout, q * qj);
+      }
+      fj.nyc = c.ny[z - 1];
+      fj.q = q;
+      fj.qj = qj;
+      fj.W = c.d_w + c.w_off[j];
+      fj.w_tstride = (int)c.w_ts;
+      fj.phi = h->d_phi + h->phi_off[i];
+      fj.logz_out = h->d_logzij + (h->inf_k > 0 ? j : eout);
+      const size_t dq = (size_t)d * q;
+      fj.rstride = (int)(dq * dq);
+      fj.Rbuf = (double*)h->arena.take(8 * (size_t)(L + 1) * fj.rstride);
+      fj.kdim = (int*)h->arena.take(4 * (L + 1));
+      fj.Bt = (double*)h->arena.take(8 * (size_t)d * d * q * qj * q);
+      fj.S = (double*)h->arena.take(8 * (size_t)d * d * q * q * q * qj);
+      fj.H = (double*)h->arena.take(8 * (size_t)d * d * q * qj);
+      fj.R2 = (double*)h->arena.take(8 * (size_t)(d * q * qj) * (d * q * qj));
+      fj.Pr[0] = (double*)h->arena.take(8 * (size_t)d * d * q);
+      fj.Pr[1] = (double*)h->arena.take(8 * (size_t)d * d * q);
+      ok = ok && fj.Rbuf && fj.kdim && fj.Bt && fj.S && fj.H && fj.R2 && fj.Pr[0] && fj.Pr[1];
+      P.fin.push_back(fj);
+    }
+    BelJob bj;
+    memset(&bj, 0, sizeof bj);
+    bj.full = full;
+    bj.ny = c.ny[z];
+    bj.q = q;
+    bj.Wd = c.d_wd;
+    bj.w_tstride = (int)c.wd_ts;
+    bj.phi = h->d_phi + h->phi_off[i];
+    bj.marg = h->d_marg + h->marg_off[i];
+    bj.logz = h->d_logzi + i;
+    bj.bw = (double*)h->arena.take(8 * (size_t)L * d * q);
+    bj.Bt = (double*)h->arena.take(8 * (size_t)d * d * q * q);
+    ok = ok && bj.bw && bj.Bt;
+    P.bel.push_back(bj);
+    FJob f;
+    f.logzi = h->d_logzi + i;
+    f.logzij = h->d_logzij + (h->inf_k > 0 ? 0 : e0);
+    f.z = z;
+    f.f = h->d_f + i;
+    P.fj.push_back(f);
+  }
+  if (!ok) return fail("arena exhausted while planning %zu nodes (internal sizing error)", nodes.size());
+  return 0;
+}
+
+template <class J>
+int upload_jobs(mpbp_state* h, const std::vector<J>& v, J** d) {
+  *d = (J*)h->arena.take(sizeof(J) * std::max<size_t>(v.size(), 1));
+  if (!*d) return fail("arena exhausted (job descriptors)");
+  if (!v.empty()) CUDA_OK(cudaMemcpyAsync(*d, v.data(), sizeof(J) * v.size(), cudaMemcpyHostToDevice, h->st));
+  return 0;
+}
+
+void ev_begin(mpbp_state* h) {
+  if (!h->profile) return;
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    h->ev_pool.push_back({a, b});
+  }
+  cudaEventRecord(h->ev_pool[h->ev_used].first, h->st);
+}
+void ev_end(mpbp_state* h) {
+  if (!h->profile) return;
+  cudaEventRecord(h->ev_pool[h->ev_used].second, h->st);
+  h->ev_used++;
+}
+
+// run one group of ops of one level (scratch already assigned)
+int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int maxX, int maxNy, int maxq, const Trunc& tr) {
+  const int L = h->L, d = h->dmax;
+  cudaStream_t st = h->st;
+  k_op_setup<<<(nops + 127) / 128, 128, 0, st>>>(d_ops, nops, L);
+  h->n_launch++;
+  // shared-memory budgets
+  const int qr_vrows_big = std::min(QR_MAX_M, (int)((h->max_smem - 4096) / 8 / QB) - 64);
+  const size_t qr_smem_big = qr_shared_doubles(qr_vrows_big) * 8;
+  const size_t kc_smem = ((size_t)maxDcap + (size_t)d * d * maxNy) * 8;
+  const size_t kp_smem = (size_t)d * d * d * 8;
+  if (kc_smem > (size_t)h->max_smem || kp_smem > (size_t)h->max_smem)
+    return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, maxNy);
+  const int dXcap = d * maxX;
+  const int ccap = std::min(dXcap, maxDcap);
+  const size_t jac_fixed = (size_t)ccap + (ccap + 1) / 2 + 1;
+  size_t jac_doubles = (size_t)dXcap * ccap;
+  if ((jac_fixed + jac_doubles) * 8 > (size_t)h->max_smem - 2048) jac_doubles = ((size_t)h->max_smem - 2048) / 8 - jac_fixed;
+  const size_t jac_smem = (jac_fixed + jac_doubles) * 8;
+  const int mrows_cap = maxDcap * maxX;
+  // number of TSQR stages for the capacity
+  int nstages = 1;
+  {
+    long long m = mrows_cap;
+    while (m > QR_MAX_M) {
+      m = ((m + QR_MAX_M - 1) / QR_MAX_M) * maxDcap;
+      nstages++;
+      if (nstages > 6) return fail("TSQR does not converge for D=%d", maxDcap);
+    }
+  }
+  // ---- sweep 1 (R->L) ----
+  for (int t = L - 1; t >= 1; --t) {
+    dim3 g1(nops, maxq, (maxDcap + KC_RC - 1) / KC_RC);
+    k_kron_carry<<<g1, NT, kc_smem, st>>>(d_ops, t, L);
+    h->n_launch++;
+    long long m = mrows_cap;
+    ev_begin(h);
+    for (int s = 0; s < nstages; ++s) {
+      const int nch = (int)((m + QR_MAX_M - 1) / QR_MAX_M);
+      dim3 g2(nops, nch);
+      k_qr_stage<<<g2, NT, qr_smem_big, st>>>(d_ops, t, s, qr_vrows_big, h->d_flops);
+      h->n_launch++;
+      m = (long long)nch * maxDcap;
+    }
+    ev_end(h);
+  }
+  // ---- sweep 2 (L->R) ----
+  const int qr_vrows_small = std::min(qr_vrows_big, std::max(64, maxDcap));
+  const size_t qr_smem_small = qr_shared_doubles(qr_vrows_small) * 8;
+  for (int t = 0; t < L; ++t) {
+    dim3 g3(nops, maxq, maxNy);
+    k_kron_proj<<<g3, NT, kp_smem, st>>>(d_ops, t);
+    h->n_launch++;
+    if (t < L - 1) {
+      dim3 g4(nops, (dXcap + 31) / 32, (maxDcap + 31) / 32);
+      k_gemm_m2t<<<g4, NT, 0, st>>>(d_ops, t);
+      k_qr_small<<<nops, NT, qr_smem_small, st>>>(d_ops, t, qr_vrows_small);
+      k_jacobi_project<<<nops, NT, jac_smem, st>>>(d_ops, t, tr, d, (int)jac_doubles, h->d_err);
+      h->n_launch += 3;
+    } else {
+      k_op_last<<<nops, NT, 0, st>>>(d_ops, t);
+      h->n_launch++;
+    }
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, const Trunc& tr) {
+  const int L = h->L, d = h->dmax;
+  h->arena.used = 0;
+  Plan P;
+  if (build_plan(h, nodes, rb, wb, P)) return 1;
+  cudaStream_t st = h->st;
+  BtJob* d_bt;
+  InitJob* d_init;
+  FinJob* d_fin;
+  BelJob* d_bel;
+  FJob* d_fj;
+  if (upload_jobs(h, P.bt, &d_bt) || upload_jobs(h, P.init, &d_init) || upload_jobs(h, P.fin, &d_fin) ||
+      upload_jobs(h, P.bel, &d_bel) || upload_jobs(h, P.fj, &d_fj))
+    return 1;
+  if (!P.bt.empty()) {
+    dim3 g((unsigned)P.bt.size(), L);
+    k_btilde<<<g, NT, 0, st>>>(d_bt, L);
+    h->n_launch++;
+  }
+  k_init_tt<<<(unsigned)P.init.size(), 64, 0, st>>>(d_init, (int)P.init.size(), L);
+  h->n_launch++;
+  // ---- cavity levels ----
+  const size_t persistent = h->arena.used;
+  for (size_t lev = 1; lev < P.levels.size(); ++lev) {
+    auto& ops = P.levels[lev];
+    size_t i0 = 0;
+    while (i0 < ops.size()) {
+      h->arena.used = persistent;
+      size_t i1 = i0;
+      int maxD = 1, maxX = 1, maxNy = 1, maxq = 1;
+      // reserve room for the descriptor array first
+      OpDesc* d_ops = (OpDesc*)h->arena.take(sizeof(OpDesc) * (ops.size() - i0));
+      if (!d_ops) return fail("arena exhausted (op descriptors)");
+      while (i1 < ops.size() && (double)(i1 - i0) < h->max_group_ops) {
+        OpDesc& op = ops[i1];
+        const int ca = P.capA[lev][i1], cb = P.capB[lev][i1];
+        const int X = op.nyo * op.q;
+        const size_t need = op_scratch_bytes(h, ca, cb, X);
+        if (h->arena.used + need > h->arena.cap) break;
+        const size_t D = (size_t)ca * cb;
+        const size_t mrows = D * X;
+        const size_t nch = (mrows + QR_MAX_M - 1) / QR_MAX_M;
+        op.r = (int*)h->arena.take(4 * (L + 1));
+        op.Lstride = (long long)(D * D);
+        op.Lbuf = (double*)h->arena.take(8 * (size_t)L * D * D);
+        op.M = (double*)h->arena.take(8 * mrows * D);
+        op.Ms = nch > 1 ? (double*)h->arena.take(8 * nch * D * D) : nullptr;
+        op.G = (double*)h->arena.take(8 * (size_t)d * D * X);
+        op.M2T = (double*)h->arena.take(8 * D * (size_t)d * X);
+        op.R2 = (double*)h->arena.take(8 * (size_t)(d * X) * (d * X));
+        op.Pc[0] = (double*)h->arena.take(8 * (size_t)d * D);
+        op.Pc[1] = (double*)h->arena.take(8 * (size_t)d * D);
+        if (!op.r || !op.Lbuf || !op.M || (nch > 1 && !op.Ms) || !op.G || !op.M2T || !op.R2 || !op.Pc[0] || !op.Pc[1]) break;
+        maxD = std::max(maxD, (int)D);
+        maxX = std::max(maxX, X);
+        maxNy = std::max(maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
+        maxq = std::max(maxq, op.q);
+        ++i1;
+      }
+      if (i1 == i0) return fail("arena too small for a single op (need %.1f MB)", op_scratch_bytes(h, d, d, ops[i0].nyo * ops[i0].q) / 1e6);
+      const int nops = (int)(i1 - i0);
+      CUDA_OK(cudaMemcpyAsync(d_ops, ops.data() + i0, sizeof(OpDesc) * nops, cudaMemcpyHostToDevice, st));
+      if (run_op_group(h, d_ops, nops, maxD, maxX, maxNy, maxq, tr)) return 1;
+      // descriptors / scratch are reused by the next group: wait for the stream
+      CUDA_OK(cudaStreamSynchronize(st));
+      h->n_ops += nops;
+      i0 = i1;
+    }
+  }
+  h->arena.used = persistent;
+  // ---- outgoing messages, beliefs, free energy ----
+  {
+    int qm = h->qmax;
+    const int rows_cap = d * qm * qm * qm;
+    const int vrows = std::max(64, std::min(QR_MAX_M, rows_cap));
+    const int ccap = d * qm * qm;  // max(c, p) of the sweep-B matrices
+    const size_t jac_fixed = (size_t)ccap + (ccap + 1) / 2 + 1;
+    size_t jac_doubles = std::max<size_t>((size_t)d * qm * qm * d * qm, 2 * (size_t)(d + 1));
+    const size_t qrd = qr_shared_doubles(vrows);
+    if ((qrd + jac_fixed + jac_doubles) * 8 > (size_t)h->max_smem - 2048) {
+      if ((qrd + jac_fixed + 2 * (d + 1)) * 8 > (size_t)h->max_smem - 2048) return fail("finalize kernel: shared memory too small");
+      jac_doubles = ((size_t)h->max_smem - 2048) / 8 - qrd - jac_fixed;
+    }
+    const size_t smem = (qrd + jac_fixed + jac_doubles) * 8;
+    if (!P.fin.empty()) {
+      k_finalize<<<(unsigned)P.fin.size(), NT, smem, st>>>(d_fin, L, tr, d, vrows, (int)jac_doubles, h->d_err);
+      h->n_launch++;
+    }
+    const size_t bsm = 2 * (size_t)d * qm * 8;
+    k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
+    k_free_energy<<<(unsigned)(P.fj.size() + 127) / 128, 128, 0, st>>>(d_fj, (int)P.fj.size());
+    h->n_launch += 2;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(st));
+  h->n_edge_updates += (double)P.fin.size();
+  return 0;
+}
+
+// update a set of pairwise independent-or-double-buffered nodes, chunked by arena capacity
+int run_nodes(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, const Trunc& tr) {
+  if (ensure_arena(h)) return 1;
+  // fraction of the arena given to persistent per-node storage; the rest is op scratch
+  const size_t budget = (size_t)(h->arena.cap * 0.45);
+  size_t i0 = 0;
+  while (i0 < nodes.size()) {
+    size_t used = 0, i1 = i0;
+    while (i1 < nodes.size()) {
+      const size_t nb = node_bytes(h, nodes[i1]) + 4096;
+      if (used + nb > budget && i1 > i0) break;
+      used += nb;
+      ++i1;
+    }
+    std::vector<int64_t> chunk(nodes.begin() + i0, nodes.begin() + i1);
+    if (run_nodes_chunk(h, chunk, rb, wb, tr)) return 1;
+    i0 = i1;
+  }
+  return 0;
+}
+
+int check_err(mpbp_state* h) {
+  int e = 0;
+  CUDA_OK(cudaMemcpy(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) {
+    int zero = 0;
+    cudaMemcpy(h->d_err, &zero, sizeof(int), cudaMemcpyHostToDevice);
+    return fail("device error flags 0x%x:%s%s%s", e, (e & ERR_BOND_OVERFLOW) ? " bond dimension exceeds dmax" : "",
+                (e & ERR_NAN) ? " NaN/non-positive normalisation in tensor train" : "",
+                (e & ERR_JACOBI_NOCONV) ? " Jacobi SVD did not converge" : "");
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* mpbp_last_error(void) { return g_err.c_str(); }
+int mpbp_version(void) { return 100; }
+
+int mpbp_create(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* colptr, const int64_t* dst,
+                const int64_t* rev, int dmax, int device, mpbp_handle* out) {
+  if (!out) return fail("null out");
+  if (N <= 0 || E2 < 0 || T < 0 || dmax < 1) return fail("invalid sizes N=%lld E2=%lld T=%d dmax=%d", (long long)N, (long long)E2, T, dmax);
+  if (dmax > 32) return fail("dmax=%d exceeds the supported bond capacity 32", dmax);
+  mpbp_state* h = new mpbp_state();
+  h->device = device;
+  h->N = N;
+  h->E2 = E2;
+  h->T = T;
+  h->L = T + 1;
+  h->dmax = dmax;
+  h->q.assign(q, q + N);
+  h->colptr.assign(colptr, colptr + N + 1);
+  h->dst.assign(dst, dst + E2);
+  h->rev.assign(rev, rev + E2);
+  h->src.resize(E2);
+  for (int64_t i = 0; i < N; ++i) {
+    if (h->q[i] < 1 || h->q[i] > 8) { delete h; return fail("q[%lld]=%d out of range 1..8", (long long)i, q[i]); }
+    for (int64_t e = colptr[i]; e < colptr[i + 1]; ++e) h->src[e] = i;
+  }
+  if (h->colptr[0] != 0 || h->colptr[N] != E2) { delete h; return fail("colptr does not span the edges"); }
+  for (int64_t e = 0; e < E2; ++e) {
+    const int64_t r = rev[e];
+    if (r < 0 || r >= E2 || h->rev[r] != e || h->src[r] != h->dst[e] || h->dst[r] != h->src[e]) {
+      delete h;
+      return fail("rev[%lld] is not the reverse edge (graph must be symmetric, src/mpbp.jl:18)", (long long)e);
+    }
+  }
+  h->class_of_node.assign(N, -1);
+  if (common_init(h)) { delete h; return 1; }
+  *out = h;
+  return 0;
+}
+
+int mpbp_create_infinite(int k, int T, int q, int dmax, int device, mpbp_handle* out) {
+  if (!out) return fail("null out");
+  if (k < 1 || T < 0 || dmax < 1 || q < 1 || q > 8) return fail("invalid arguments");
+  if (dmax > 32) return fail("dmax=%d exceeds the supported bond capacity 32", dmax);
+  mpbp_state* h = new mpbp_state();
+  h->device = device;
+  h->N = 1;
+  h->E2 = 1;
+  h->T = T;
+  h->L = T + 1;
+  h->dmax = dmax;
+  h->inf_k = k;
+  h->q = {q};
+  h->colptr = {0, 1};
+  h->dst = {0};
+  h->rev = {0};
+  h->src = {0};
+  h->class_of_node.assign(1, -1);
+  if (common_init(h)) { delete h; return 1; }
+  *out = h;
+  return 0;
+}
+
+int mpbp_destroy(mpbp_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  for (auto& c : h->classes) {
+    cudaFree(c.d_pxy); cudaFree(c.d_pyy); cudaFree(c.d_w); cudaFree(c.d_wd); cudaFree(c.d_minit);
+  }
+  for (int b = 0; b < 2; ++b) { cudaFree(h->msg[b].data); cudaFree(h->msg[b].bonds); cudaFree(h->msg[b].ls); }
+  cudaFree(h->d_phi); cudaFree(h->d_psi); cudaFree(h->d_qprod); cudaFree(h->d_marg); cudaFree(h->d_logzi);
+  cudaFree(h->d_logzij); cudaFree(h->d_f); cudaFree(h->d_means); cudaFree(h->d_marg_off); cudaFree(h->d_q);
+  cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->arena.base);
+  for (auto& e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+int mpbp_add_node_class(mpbp_handle h, int z, int q, const int32_t* qn, int nt, const int32_t* ny, const double* pxy,
+                        int npairs, const int32_t* pair_d1, const int32_t* pair_d2, const double* pyy,
+                        const double* w, const double* wd, const double* minit, int32_t* class_id) {
+  if (!h) return fail("null handle");
+  if (z < 1) return fail("degree-0 nodes have no messages: z must be >= 1");
+  if (nt != 1 && nt != h->L) return fail("nt must be 1 or T+1");
+  CUDA_OK(cudaSetDevice(h->device));
+  NodeClass c;
+  c.z = z;
+  c.q = q;
+  c.nt = nt;
+  c.qn.assign(qn, qn + z);
+  c.ny.assign(ny, ny + z + 1);
+  for (int l = 0; l <= z; ++l)
+    if (c.ny[l] < 1 || c.ny[l] > 64) return fail("nstates(w,%d)=%d out of range", l, c.ny[l]);
+  const bool td = nt > 1;
+  // pxy
+  size_t tot = 0;
+  c.pxy_off.resize(z);
+  for (int k = 0; k < z; ++k) { c.pxy_off[k] = tot; tot += (size_t)c.ny[1] * qn[k] * q; }
+  c.pxy_ts = td ? tot : 0;
+  if (upload(&c.d_pxy, pxy, tot * nt)) return 1;
+  // pyy
+  size_t off = 0;
+  for (int p = 0; p < npairs; ++p) {
+    const int d1 = pair_d1[p], d2 = pair_d2[p];
+    if (d1 < 0 || d2 < 0 || d1 + d2 > z) return fail("invalid (d1,d2)=(%d,%d)", d1, d2);
+    const size_t sz = (size_t)c.ny[d1 + d2] * c.ny[d1] * c.ny[d2] * q;
+    c.pyy[{d1, d2}] = {off, td ? sz : 0};
+    off += sz * nt;
+  }
+  if (upload(&c.d_pyy, pyy, off)) return 1;
+  // w
+  tot = 0;
+  c.w_off.resize(z);
+  for (int j = 0; j < z; ++j) { c.w_off[j] = tot; tot += (size_t)q * q * qn[j] * c.ny[z - 1]; }
+  c.w_ts = td ? tot : 0;
+  if (upload(&c.d_w, w, tot * nt)) return 1;
+  const size_t wds = (size_t)q * q * c.ny[z];
+  c.wd_ts = td ? wds : 0;
+  if (upload(&c.d_wd, wd, wds * nt)) return 1;
+  const size_t mis = (size_t)c.ny[0] * q;
+  c.minit_ts = td ? mis : 0;
+  // Minit must cover all L sites even when time-independent: expand on the host
+  std::vector<double> mi((size_t)h->L * mis);
+  for (int t = 0; t < h->L; ++t) memcpy(mi.data() + t * mis, minit + (td ? t * mis : 0), mis * 8);
+  c.minit_ts = mis;
+  if (upload(&c.d_minit, mi.data(), mi.size())) return 1;
+  h->classes.push_back(c);
+  if (class_id) *class_id = (int)h->classes.size() - 1;
+  return 0;
+}
+
+int mpbp_add_generic_class(mpbp_handle, int, int, const int32_t*, int, const double*, int32_t*) {
+  return fail("generic BPFactor classes (exhaustive trace, src/bp_core.jl:18-57) are not implemented on the device yet");
+}
+
+int mpbp_set_node_classes(mpbp_handle h, const int32_t* cls) {
+  if (!h) return fail("null handle");
+  for (int64_t i = 0; i < h->N; ++i) {
+    if (cls[i] < 0 || cls[i] >= (int)h->classes.size()) return fail("class_of_node[%lld]=%d unknown", (long long)i, cls[i]);
+    h->class_of_node[i] = cls[i];
+  }
+  return 0;
+}
+
+int mpbp_set_phi(mpbp_handle h, const double* phi) {
+  if (!h || !phi) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpyAsync(h->d_phi, phi, sizeof(double) * h->phi_off[h->N], cudaMemcpyHostToDevice, h->st));
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+int mpbp_set_psi(mpbp_handle h, const double* psi) {
+  if (!h || !psi) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpyAsync(h->d_psi, psi, sizeof(double) * h->psi_off[h->E2], cudaMemcpyHostToDevice, h->st));
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int mpbp_get_message(mpbp_handle h, int64_t e, int32_t* bonds, double* data, int64_t cap, int64_t* needed) {
+  if (!h || e < 0 || e >= h->E2) return fail("bad edge index");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int L = h->L;
+  const MsgStore& m = h->msg[h->cur];
+  std::vector<int> b(L + 1);
+  CUDA_OK(cudaMemcpy(b.data(), m.bonds + e * (L + 1), sizeof(int) * (L + 1), cudaMemcpyDeviceToHost));
+  const int P = h->q[h->src[e]] * h->q[h->dst[e]];
+  int64_t tot = 0;
+  for (int t = 0; t < L; ++t) tot += (int64_t)b[t] * b[t + 1] * P;
+  if (needed) *needed = tot;
+  if (bonds) memcpy(bonds, b.data(), sizeof(int) * (L + 1));
+  if (!data) return 0;
+  if (cap < tot) return fail("buffer too small: need %lld doubles", (long long)tot);
+  double ls;
+  CUDA_OK(cudaMemcpy(&ls, m.ls + e, sizeof(double), cudaMemcpyDeviceToHost));
+  const double f = std::exp(ls / L);
+  int64_t off = 0;
+  for (int t = 0; t < L; ++t) {
+    const int64_t n = (int64_t)b[t] * b[t + 1] * P;
+    CUDA_OK(cudaMemcpy(data + off, m.data + e * h->slot + (int64_t)t * h->sstride, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < n; ++k) data[off + k] *= f;
+    off += n;
+  }
+  return 0;
+}
+
+int mpbp_set_message(mpbp_handle h, int64_t e, const int32_t* bonds, const double* data) {
+  if (!h || e < 0 || e >= h->E2 || !bonds || !data) return fail("bad argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int L = h->L;
+  if (bonds[0] != 1 || bonds[L] != 1) return fail("first/last bond must be 1 (src/mpems.jl:41)");
+  for (int t = 0; t <= L; ++t)
+    if (bonds[t] < 1 || bonds[t] > h->dmax) return fail("bond %d exceeds dmax=%d", bonds[t], h->dmax);
+  MsgStore& m = h->msg[h->cur];
+  const int P = h->q[h->src[e]] * h->q[h->dst[e]];
+  int64_t off = 0;
+  for (int t = 0; t < L; ++t) {
+    const int64_t n = (int64_t)bonds[t] * bonds[t + 1] * P;
+    CUDA_OK(cudaMemcpy(m.data + e * h->slot + (int64_t)t * h->sstride, data + off, sizeof(double) * n, cudaMemcpyHostToDevice));
+    off += n;
+  }
+  std::vector<int> b(bonds, bonds + L + 1);
+  CUDA_OK(cudaMemcpy(m.bonds + e * (L + 1), b.data(), sizeof(int) * (L + 1), cudaMemcpyHostToDevice));
+  const double zero = 0.0;
+  CUDA_OK(cudaMemcpy(m.ls + e, &zero, sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int mpbp_reset_messages(mpbp_handle h) {
+  if (!h) return fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (flat_messages(h, h->msg[h->cur])) return 1;
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int mpbp_iterate(mpbp_handle h, int maxiter, int trunc_kind, int trunc_d, double trunc_eps, double tol, double damp,
+                 int schedule, const int64_t* nodes_in, int64_t n_nodes, const int64_t* order, const double* obs,
+                 int* iters, double* deltas) {
+  if (!h) return fail("null handle");
+  if (damp != 0.0) return fail("damp > 0 (set_msg! damping, src/recursive_bp_factor.jl:172-176) is not implemented on the device yet");
+  if (trunc_kind < 0 || trunc_kind > 2) return fail("unknown truncation kind %d", trunc_kind);
+  if ((trunc_kind == MPBP_TRUNC_BOND || trunc_kind == MPBP_TRUNC_BOND_THRESH) && trunc_d > h->dmax)
+    return fail("TruncBond(%d) exceeds the device bond capacity dmax=%d", trunc_d, h->dmax);
+  if (trunc_d < 1 && trunc_kind != MPBP_TRUNC_THRESH) return fail("TruncBond(d) needs d >= 1");
+  CUDA_OK(cudaSetDevice(h->device));
+  Trunc tr{trunc_kind, trunc_d, trunc_eps};
+  std::vector<int64_t> base;
+  if (nodes_in) base.assign(nodes_in, nodes_in + n_nodes);
+  else { base.resize(h->N); for (int64_t i = 0; i < h->N; ++i) base[i] = i; n_nodes = h->N; }
+  for (int64_t i : base) if (i < 0 || i >= h->N) return fail("node index %lld out of range", (long long)i);
+  double* d_obs = nullptr;
+  if (obs) { if (upload(&d_obs, obs, (size_t)h->N * h->qmax)) return 1; }
+  int64_t* d_nodes = nullptr;
+  if (upload(&d_nodes, base.data(), base.size())) return 1;
+  if (schedule == MPBP_SCHEDULE_PARALLEL && !h->msg[1].data) {
+    if (alloc_msg_store(h, h->msg[1])) return 1;
+  }
+  int done = 0;
+  for (int it = 0; it < maxiter; ++it) {
+    std::vector<int64_t> ord = order ? std::vector<int64_t>(order + (size_t)it * n_nodes, order + (size_t)(it + 1) * n_nodes) : base;
+    if (schedule == MPBP_SCHEDULE_PARALLEL) {
+      const int rb = h->cur, wb = 1 - h->cur;
+      // messages of nodes outside `nodes` are carried over unchanged
+      CUDA_OK(cudaMemcpyAsync(h->msg[wb].data, h->msg[rb].data, sizeof(double) * h->slot * h->E2, cudaMemcpyDeviceToDevice, h->st));
+      CUDA_OK(cudaMemcpyAsync(h->msg[wb].bonds, h->msg[rb].bonds, sizeof(int) * (h->L + 1) * h->E2, cudaMemcpyDeviceToDevice, h->st));
+      CUDA_OK(cudaMemcpyAsync(h->msg[wb].ls, h->msg[rb].ls, sizeof(double) * h->E2, cudaMemcpyDeviceToDevice, h->st));
+      if (run_nodes(h, ord, rb, wb, tr)) return 1;
+      h->cur = wb;
+    } else {
+      // level scheduling of the in-place sweep: level(i) = 1 + max level of earlier-visited neighbours
+      std::vector<int> pos(h->N, -1), level(h->N, 0);
+      for (size_t k = 0; k < ord.size(); ++k) pos[ord[k]] = (int)k;
+      int nlev = 0;
+      std::vector<std::vector<int64_t>> levels;
+      for (size_t k = 0; k < ord.size(); ++k) {
+        const int64_t i = ord[k];
+        int lv = 0;
+        if (h->inf_k == 0)
+          for (int64_t e = h->colptr[i]; e < h->colptr[i + 1]; ++e) {
+            const int64_t j = h->dst[e];
+            if (pos[j] >= 0 && pos[j] < (int)k) lv = std::max(lv, level[j] + 1);
+          }
+        level[i] = lv;
+        if (lv >= nlev) { nlev = lv + 1; levels.resize(nlev); }
+        levels[lv].push_back(i);
+      }
+      for (auto& lvn : levels)
+        if (run_nodes(h, lvn, h->cur, h->cur, tr)) return 1;
+    }
+    if (check_err(h)) return 1;
+    // CB_BP: Delta = max |means_new - means_old| (src/mpbp.jl:174-183)
+    CUDA_OK(cudaMemsetAsync(h->d_delta, 0, sizeof(double), h->st));
+    k_means_delta<<<(unsigned)base.size(), 64, 0, h->st>>>(h->d_marg, h->d_marg_off, h->d_q, d_obs, h->qmax, d_nodes,
+                                                           (long long)base.size(), h->L, h->d_means, h->d_delta);
+    h->n_launch++;
+    double delta = 0;
+    CUDA_OK(cudaMemcpyAsync(&delta, h->d_delta, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CUDA_OK(cudaStreamSynchronize(h->st));
+    if (deltas) deltas[it] = delta;
+    done = it + 1;
+    if (delta < tol) break;
+  }
+  if (h->profile) {
+    for (size_t k = 0; k < h->ev_used; ++k) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev_pool[k].first, h->ev_pool[k].second);
+      h->qr_ms += ms;
+    }
+    h->ev_used = 0;
+  }
+  cudaFree(d_obs);
+  cudaFree(d_nodes);
+  if (iters) *iters = done;
+  return 0;
+}
+
+int mpbp_beliefs(mpbp_handle h, double* out) {
+  if (!h || !out) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpy(out, h->d_marg, sizeof(double) * h->marg_off[h->N], cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int mpbp_free_energy(mpbp_handle h, double* f) {
+  if (!h || !f) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpy(f, h->d_f, sizeof(double) * h->N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int mpbp_pair_beliefs(mpbp_handle h, double* out, double* logz) {
+  if (!h || !out || !logz) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (ensure_arena(h)) return 1;
+  const int L = h->L, d = h->dmax;
+  const MsgStore& m = h->msg[h->cur];
+  double* d_out;
+  double* d_lz;
+  CUDA_OK(cudaMalloc((void**)&d_out, sizeof(double) * h->psi_off[h->E2]));
+  CUDA_OK(cudaMalloc((void**)&d_lz, sizeof(double) * h->E2));
+  const size_t per = 8 * (size_t)(L + 1) * d * d + 512;
+  int64_t e0 = 0;
+  while (e0 < h->E2) {
+    h->arena.used = 0;
+    const int64_t maxn = std::max<int64_t>(1, (int64_t)((h->arena.cap / 2) / (per + sizeof(PairJob))));
+    const int64_t e1 = std::min(h->E2, e0 + maxn);
+    std::vector<PairJob> jobs;
+    for (int64_t e = e0; e < e1; ++e) {
+      PairJob jb;
+      const int qs = h->q[h->src[e]], qd = h->q[h->dst[e]];
+      jb.A = msg_ref(h, m, e, qs * qd);
+      jb.B = msg_ref(h, m, h->rev[e], qs * qd);
+      jb.psi = h->d_psi + h->psi_off[e];
+      jb.qs = qs;
+      jb.qd = qd;
+      jb.out = d_out + h->psi_off[e];
+      jb.logz = d_lz + e;
+      jb.Renv = (double*)h->arena.take(8 * (size_t)(L + 1) * d * d);
+      if (!jb.Renv) return fail("arena exhausted (pair beliefs)");
+      jobs.push_back(jb);
+    }
+    PairJob* d_jobs;
+    if (upload_jobs(h, jobs, &d_jobs)) return 1;
+    k_pair_belief<<<(unsigned)jobs.size(), NT, 3 * (size_t)d * d * 8, h->st>>>(d_jobs, L, d);
+    h->n_launch++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->st));
+    e0 = e1;
+  }
+  CUDA_OK(cudaMemcpy(out, d_out, sizeof(double) * h->psi_off[h->E2], cudaMemcpyDeviceToHost));
+  std::vector<double> lz(h->E2);
+  CUDA_OK(cudaMemcpy(lz.data(), d_lz, sizeof(double) * h->E2, cudaMemcpyDeviceToHost));
+  cudaFree(d_out);
+  cudaFree(d_lz);
+  // logz[j] += (1/d_j - 1/2) log z_ij   (src/mpbp.jl:230 ; infinite graph: src/infinite_graph.jl:40)
+  for (int64_t i = 0; i < h->N; ++i) logz[i] = 0.0;
+  if (h->inf_k > 0) {
+    logz[0] = (1.0 / (h->inf_k - 1) - 0.5) * lz[0];
+  } else {
+    for (int64_t e = 0; e < h->E2; ++e) {
+      const int64_t j = h->src[e];
+      const double dj = (double)(h->colptr[j + 1] - h->colptr[j]);
+      logz[j] += (1.0 / dj - 0.5) * lz[e];
+    }
+  }
+  return 0;
+}
+
+int64_t mpbp_message_slot_bytes(mpbp_handle h) {
+  if (!h) return 0;
+  // data + bonds + ls, padded to 8 bytes
+  return (int64_t)(sizeof(double) * h->slot + sizeof(double) * ((h->L + 1 + 1) / 2) + sizeof(double));
+}
+
+int mpbp_pack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, void* dev_buf) {
+  if (!h || (!edges && n) || (!dev_buf && n)) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int64_t sb = mpbp_message_slot_bytes(h);
+  const MsgStore& m = h->msg[h->cur];
+  const int L = h->L;
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t e = edges[k];
+    if (e < 0 || e >= h->E2) return fail("bad edge index");
+    char* p = (char*)dev_buf + k * sb;
+    CUDA_OK(cudaMemcpyAsync(p, m.data + e * h->slot, sizeof(double) * h->slot, cudaMemcpyDeviceToDevice, h->st));
+    CUDA_OK(cudaMemcpyAsync(p + sizeof(double) * h->slot, m.bonds + e * (L + 1), sizeof(int) * (L + 1), cudaMemcpyDeviceToDevice, h->st));
+    CUDA_OK(cudaMemcpyAsync(p + sb - sizeof(double), m.ls + e, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, const void* dev_buf) {
+  if (!h || (!edges && n) || (!dev_buf && n)) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int64_t sb = mpbp_message_slot_bytes(h);
+  MsgStore& m = h->msg[h->cur];
+  const int L = h->L;
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t e = edges[k];
+    if (e < 0 || e >= h->E2) return fail("bad edge index");
+    const char* p = (const char*)dev_buf + k * sb;
+    CUDA_OK(cudaMemcpyAsync(m.data + e * h->slot, p, sizeof(double) * h->slot, cudaMemcpyDeviceToDevice, h->st));
+    CUDA_OK(cudaMemcpyAsync(m.bonds + e * (L + 1), p + sizeof(double) * h->slot, sizeof(int) * (L + 1), cudaMemcpyDeviceToDevice, h->st));
+    CUDA_OK(cudaMemcpyAsync(m.ls + e, p + sb - sizeof(double), sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int mpbp_counters(mpbp_handle h, double* out8, int reset) {
+  if (!h || !out8) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  double fl = 0;
+  CUDA_OK(cudaMemcpy(&fl, h->d_flops, sizeof(double), cudaMemcpyDeviceToHost));
+  out8[0] = h->n_launch;
+  out8[1] = fl;
+  out8[2] = 0;
+  out8[3] = h->qr_ms;
+  out8[4] = h->n_ops;
+  out8[5] = h->n_edge_updates;
+  out8[6] = (double)h->arena.cap;
+  out8[7] = 0;
+  if (reset) {
+    h->n_launch = h->qr_ms = h->n_ops = h->n_edge_updates = 0;
+    CUDA_OK(cudaMemset(h->d_flops, 0, sizeof(double)));
+  }
+  return 0;
+}
+
+int mpbp_set_option(mpbp_handle h, const char* name, double value) {
+  if (!h || !name) return fail("null argument");
+  std::string n(name);
+  if (n == "arena_gb") {
+    if (h->arena.base) return fail("arena already allocated");
+    h->arena_gb = value;
+  } else if (n == "max_group_ops") h->max_group_ops = value;
+  else if (n == "profile") h->profile = (int)value;
+  else return fail("unknown option %s", name);
+  return 0;
+}
+
+// ---- test hooks (unit tests of the two numerical kernels through the C ABI) ----
+__global__ void __launch_bounds__(NT) k_test_qr(double* A, int m, int n, double* R, int vrows) {
+  extern __shared__ double smem[];
+  qr_r_cta(A + (size_t)blockIdx.x * m * n, m, n, n, R + (size_t)blockIdx.x * min(m, n) * n, n, false, smem, vrows);
+}
+int mpbp_test_qr(const double* A, int batch, int m, int n, double* R) {
+  if (m > QR_MAX_M || n > NT * QR_MAX_CPT + QB) return fail("test_qr: size out of range");
+  double *dA, *dR;
+  const int k = std::min(m, n);
+  CUDA_OK(cudaMalloc((void**)&dA, sizeof(double) * batch * m * n));
+  CUDA_OK(cudaMalloc((void**)&dR, sizeof(double) * batch * k * n));
+  CUDA_OK(cudaMemcpy(dA, A, sizeof(double) * batch * m * n, cudaMemcpyHostToDevice));
+  const int vrows = std::min(2048, std::max(64, m));
+  const size_t sm = qr_shared_doubles(vrows) * 8;
+  CUDA_OK(cudaFuncSetAttribute(k_test_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_test_qr<<<batch, NT, sm>>>(dA, m, n, dR, vrows);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(R, dR, sizeof(double) * batch * k * n, cudaMemcpyDeviceToHost));
+  cudaFree(dA);
+  cudaFree(dR);
+  return 0;
+}
+__global__ void __launch_bounds__(NT) k_test_jacobi(double* A, int p, int c, double* sig, int* order) {
+  __shared__ int flag;
+  extern __shared__ double smem[];
+  double* a = A + (size_t)blockIdx.x * p * c;
+  jacobi_cols(a, p, c, p, &flag);
+  double* s = smem;
+  int* o = reinterpret_cast<int*>(smem + c);
+  jacobi_sort(a, p, c, p, s, o);
+  for (int i = threadIdx.x; i < c; i += NT) {
+    sig[(size_t)blockIdx.x * c + i] = s[o[i]];
+    order[(size_t)blockIdx.x * c + i] = o[i];
+  }
+}
+int mpbp_test_jacobi(double* A, int batch, int p, int c, double* sig, int32_t* order) {
+  double *dA, *dS;
+  int* dO;
+  CUDA_OK(cudaMalloc((void**)&dA, sizeof(double) * batch * p * c));
+  CUDA_OK(cudaMalloc((void**)&dS, sizeof(double) * batch * c));
+  CUDA_OK(cudaMalloc((void**)&dO, sizeof(int) * batch * c));
+  CUDA_OK(cudaMemcpy(dA, A, sizeof(double) * batch * p * c, cudaMemcpyHostToDevice));
+  k_test_jacobi<<<batch, NT, (c + (c + 1) / 2 + 1) * 8>>>(dA, p, c, dS, dO);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(A, dA, sizeof(double) * batch * p * c, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(sig, dS, sizeof(double) * batch * c, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(order, dO, sizeof(int) * batch * c, cudaMemcpyDeviceToHost));
+  cudaFree(dA);
+  cudaFree(dS);
+  cudaFree(dO);
+  return 0;
+}
+
+}  // extern "C"

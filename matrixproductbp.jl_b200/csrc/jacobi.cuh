@@ -1,0 +1,139 @@
+// jacobi.cuh -- one-sided (Hestenes) Jacobi SVD on the columns of a small column-major matrix, one CTA.
+//
+// Role in the hot path: every truncating SVD of the reference (TensorTrains truncators inside compress!,
+// call sites src/recursive_bp_factor.jl:127,156) only needs the leading singular vectors on ONE side.
+// After convergence the columns of A are mutually orthogonal: their norms are the singular values and the
+// normalised columns the left singular vectors of the input.  High relative accuracy, warp-shuffle
+// reductions, round-robin (tournament) pair ordering so that c/2 rotations run concurrently.
+#pragma once
+#include <cstdio>
+#include "common.cuh"
+
+namespace mpbp {
+
+constexpr int JACOBI_MAX_SWEEPS = 60;
+constexpr double JACOBI_EPS = 1.1102230246251565e-16;  // tolerance = 2*sqrt(p)*eps (LAPACK dgesvj: sqrt(m)*eps)
+
+// A: p x c column-major (lda), in shared or global memory.  flag: one int in shared memory.
+// Returns the number of sweeps used (JACOBI_MAX_SWEEPS+1 if not converged).  All threads must call.
+// Columns whose norm is below JACOBI_ZERO x (largest column norm) are numerically zero: they are not rotated
+// (a column inside the span of the others would otherwise shrink by eps per sweep forever) and callers zero
+// them in U (jacobi_inv_sigma).  LAPACK resolves such directions only to eps*sigma_max as well.
+constexpr double JACOBI_ZERO = 1e-15;
+__device__ __forceinline__ double jacobi_inv_sigma(double s, double smax) {
+  return (s > 2.0 * JACOBI_ZERO * smax && s > 0.0) ? 1.0 / s : 0.0;
+}
+__device__ inline int jacobi_cols(double* A, const int p, const int c, const int lda, int* flag) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (c < 2) return 0;
+  const int ce = c + (c & 1);
+  const double tol = 2.0 * JACOBI_EPS * sqrt((double)max(p, 64));
+  __shared__ double s_scale[NW];
+  {
+    double mx = 0.0;
+    for (int j = w; j < c; j += NW) {
+      double s = 0.0;
+      for (int k = lane; k < p; k += 32) { const double x = A[k + (size_t)j * lda]; s += x * x; }
+      mx = fmax(mx, warp_sum(s));
+    }
+    __syncthreads();
+    if (lane == 0) s_scale[w] = mx;
+    __syncthreads();
+  }
+  double scale2 = 0.0;
+#pragma unroll
+  for (int ww = 0; ww < NW; ++ww) scale2 = fmax(scale2, s_scale[ww]);
+  const double thr2 = JACOBI_ZERO * JACOBI_ZERO * scale2;
+  int sweep = 0;
+  for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = 0;
+    __syncthreads();
+    for (int round = 0; round < ce - 1; ++round) {
+      for (int pr = w; pr < ce / 2; pr += NW) {
+        int i, j;
+        if (pr == 0) {
+          i = ce - 1;
+          j = round;
+        } else {
+          i = (round + pr) % (ce - 1);
+          j = (round - pr + (ce - 1)) % (ce - 1);
+        }
+        if (i >= c || j >= c) continue;
+        if (i > j) {
+          const int t = i;
+          i = j;
+          j = t;
+        }
+        double* ai = A + (size_t)i * lda;
+        double* aj = A + (size_t)j * lda;
+        double a = 0.0, b = 0.0, g = 0.0;
+        for (int k = lane; k < p; k += 32) {
+          const double x = ai[k], y = aj[k];
+          a += x * x;
+          b += y * y;
+          g += x * y;
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        g = warp_sum(g);
+        const double lim = tol * sqrt(a) * sqrt(b);
+        if (fabs(g) > lim && lim > 0.0 && a > thr2 && b > thr2) {
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          for (int k = lane; k < p; k += 32) {
+            const double x = ai[k], y = aj[k];
+            ai[k] = cs * x - sn * y;
+            aj[k] = sn * x + cs * y;
+          }
+          if (lane == 0) *flag = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (*flag == 0) break;
+  }
+  __syncthreads();
+  if (sweep >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) {
+    // diagnostics: worst remaining pair
+    double worst = 0.0; int wi = -1, wj = -1; bool nan = false;
+    for (int i = 0; i < c; ++i)
+      for (int j = i + 1; j < c; ++j) {
+        double a = 0, b = 0, g = 0;
+        for (int k = 0; k < p; ++k) { const double x = A[k + (size_t)i * lda], y = A[k + (size_t)j * lda]; a += x * x; b += y * y; g += x * y; }
+        if (!(g == g)) nan = true;
+        const double r = (a > 0 && b > 0) ? fabs(g) / (sqrt(a) * sqrt(b)) : 0.0;
+        if (r > worst) { worst = r; wi = i; wj = j; }
+      }
+    printf("[mpbp] jacobi not converged: p=%d c=%d worst |cos|=%.3e at (%d,%d) nan=%d tol=%.2e\n", p, c, worst, wi, wj, (int)nan, tol);
+  }
+  return sweep;
+}
+
+// After jacobi_cols: column norms -> sig[c]; order[r] = index of the r-th largest column (ties by index).
+// sig, order in shared memory (c entries each).
+__device__ inline void jacobi_sort(const double* A, const int p, const int c, const int lda, double* sig,
+                                   int* order) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int j = w; j < c; j += NW) {
+    const double* aj = A + (size_t)j * lda;
+    double s = 0.0;
+    for (int k = lane; k < p; k += 32) s += aj[k] * aj[k];
+    s = warp_sum(s);
+    if (lane == 0) sig[j] = sqrt(s);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < c; j += NT) {
+    const double sj = sig[j];
+    int rank = 0;
+    for (int i = 0; i < c; ++i) {
+      const double si = sig[i];
+      rank += (si > sj) || (si == sj && i < j);
+    }
+    order[rank] = j;
+  }
+  __syncthreads();
+}
+
+}  // namespace mpbp

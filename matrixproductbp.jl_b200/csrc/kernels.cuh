@@ -1,0 +1,978 @@
+// kernels.cuh -- batched FP64 kernels of the MPBP node update (sm_100a).  See DESIGN.md for the math.
+//
+// Reference code each kernel replaces:
+//   k_btilde          compute_prob_ys, first map      src/recursive_bp_factor.jl:108-115
+//   k_kron_carry      op(): Kronecker build + right-orthogonalisation carry   :118-127 (+ TensorTrains.compress! sweep 1)
+//   k_qr_stage        un-truncated R->L sweep of compress! (triangular factors only)
+//   k_kron_proj, k_gemm_m2t, k_qr_small, k_jacobi_project   truncating L->R sweep of compress! (:127)
+//   k_finalize        _f_bp_partial :73-87, mpem2 src/mpems.jl:67-94, compress!(..., is_orthogonal=:left),
+//                     normalize_eachmatrix!, normalize! / set_msg!   src/recursive_bp_factor.jl:154-158,168-179
+//   k_belief          f_bp_partial_i, mpem2, marginalize, normalize!, marginals  :160-163, src/mpbp.jl:237
+//   k_pair_belief     pair_belief_as_mpem / pair_belief  src/bp_core.jl:95-109, src/mpbp.jl:202-235
+#pragma once
+#include "common.cuh"
+#include "jacobi.cuh"
+#include "qr.cuh"
+
+namespace mpbp {
+
+// ------------------------------------------------------------------------------------------------
+// B~_k = sum_{x_k} Pxy[y,x_k,x_i] psi[x_i,x_k] mu_{k->i}[m,n,x_k,x_i]
+// ------------------------------------------------------------------------------------------------
+struct BtJob {
+  TTRef msg;  // [m,n,xk,xi]
+  TTRef out;  // [m,n,y,xi]
+  const double* psi;  // [t][xi + qi*xk]
+  const double* pxy;  // [y + ny1*(xk + qk*xi)] per t
+  int pxy_tstride;
+  int qk, qi, ny1;
+};
+
+__global__ void __launch_bounds__(NT) k_btilde(const BtJob* jobs, int L) {
+  const BtJob jb = jobs[blockIdx.x];
+  const int t = blockIdx.y;
+  const int bl = jb.msg.bonds[t], br = jb.msg.bonds[t + 1];
+  const double* A = jb.msg.data + (size_t)t * jb.msg.stride;
+  double* O = jb.out.data + (size_t)t * jb.out.stride;
+  const double* psi = jb.psi + (size_t)t * jb.qi * jb.qk;
+  const double* pxy = jb.pxy + (size_t)t * jb.pxy_tstride;
+  const int mn = bl * br;
+  const int tot = mn * jb.ny1 * jb.qi;
+  for (int idx = threadIdx.x; idx < tot; idx += NT) {
+    const int e = idx % mn, y = (idx / mn) % jb.ny1, x = idx / (mn * jb.ny1);
+    double acc = 0.0;
+    for (int xk = 0; xk < jb.qk; ++xk)
+      acc += pxy[y + jb.ny1 * (xk + jb.qk * x)] * psi[x + jb.qi * xk] * A[e + mn * (xk + jb.qk * x)];
+    O[idx] = acc;
+  }
+  if (t == 0) {
+    for (int i = threadIdx.x; i <= L; i += NT) jb.out.bonds[i] = jb.msg.bonds[i];
+    if (threadIdx.x == 0) *jb.out.ls = *jb.msg.ls;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// heavy op descriptor
+// ------------------------------------------------------------------------------------------------
+struct OpDesc {
+  TTRef a, b, o;
+  int ny1, ny2, nyo, q;
+  const double* pyy;  // [y + nyo*(y1 + ny1*(y2 + ny2*x))] per t
+  int pyy_tstride;
+  int* r;             // [L+1]  r[t] = #cols of the sweep-1 factor L_t ; r[L] = 1
+  double* Lbuf;       // L_t at Lbuf + t*Lstride, column-major D_l(t) x r[t]
+  long long Lstride;
+  double* M;          // tall scratch, row-major (r*X) x D_l
+  double* Ms;         // TSQR stack scratch
+  double* G;          // [mt, n, y, x]
+  double* M2T;        // row-major r x (dX)  == column-major (dX) x r
+  double* R2;         // (dX) x (dX)
+  double* Pc[2];      // carry [mt, (m1,m2)]
+};
+
+__global__ void k_op_setup(const OpDesc* ops, int nops, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nops) return;
+  const OpDesc& op = ops[i];
+  op.r[L] = 1;
+  op.o.bonds[0] = 1;
+  *op.o.ls = *op.a.ls + *op.b.ls;
+}
+
+constexpr int KC_RC = 8;  // right-bond columns per CTA in k_kron_carry
+
+// M_t[(m1,m2), rr, y, x] = sum_{y1,y2} Pyy sum_{n1,n2} B1[m1,n1,y1,x] B2[m2,n2,y2,x] L_{t+1}[(n1,n2), rr]
+// grid (nops, q, ceil(rcap/KC_RC)); dyn smem: (Dcap + d*d*nymax) doubles
+__global__ void __launch_bounds__(NT) k_kron_carry(const OpDesc* ops, int t, int L) {
+  extern __shared__ double smem[];
+  const OpDesc& op = ops[blockIdx.x];
+  const int x = blockIdx.y;
+  if (x >= op.q) return;
+  const int bl1 = op.a.bonds[t], br1 = op.a.bonds[t + 1], bl2 = op.b.bonds[t], br2 = op.b.bonds[t + 1];
+  const int Dl = bl1 * bl2, Dr = br1 * br2;
+  const int rn = op.r[t + 1];
+  const int rr0 = blockIdx.z * KC_RC;
+  if (rr0 >= rn) return;
+  const double* A1 = op.a.data + (size_t)t * op.a.stride;
+  const double* A2 = op.b.data + (size_t)t * op.b.stride;
+  const double* Lm = (t + 1 < L) ? op.Lbuf + (size_t)(t + 1) * op.Lstride : nullptr;
+  const double* pyy = op.pyy + (size_t)t * op.pyy_tstride;
+  const int ny1 = op.ny1, ny2 = op.ny2, nyo = op.nyo;
+  double* Lcol = smem;
+  double* Z = smem + Dr;
+  const int rr1 = min(rr0 + KC_RC, rn);
+  for (int rr = rr0; rr < rr1; ++rr) {
+    for (int i = threadIdx.x; i < Dr; i += NT) Lcol[i] = Lm ? Lm[i + (size_t)Dr * rr] : 1.0;
+    __syncthreads();
+    const int nz = bl2 * br1 * ny2;
+    for (int idx = threadIdx.x; idx < nz; idx += NT) {
+      const int m2 = idx % bl2, n1 = (idx / bl2) % br1, y2 = idx / (bl2 * br1);
+      const double* a2 = A2 + m2 + (size_t)bl2 * br2 * (y2 + ny2 * x);
+      double acc = 0.0;
+      for (int n2 = 0; n2 < br2; ++n2) acc += a2[bl2 * n2] * Lcol[n1 + br1 * n2];
+      Z[idx] = acc;
+    }
+    __syncthreads();
+    const int no = Dl * nyo;
+    for (int idx = threadIdx.x; idx < no; idx += NT) {
+      const int c = idx % Dl, y = idx / Dl;
+      const int m1 = c % bl1, m2 = c / bl1;
+      double acc = 0.0;
+      for (int y2 = 0; y2 < ny2; ++y2)
+        for (int y1 = 0; y1 < ny1; ++y1) {
+          const double pv = pyy[y + nyo * (y1 + ny1 * (y2 + ny2 * x))];
+          if (pv != 0.0) {
+            const double* a1 = A1 + m1 + (size_t)bl1 * br1 * (y1 + ny1 * x);
+            const double* z = Z + m2 + bl2 * br1 * y2;
+            double s = 0.0;
+            for (int n1 = 0; n1 < br1; ++n1) s += a1[bl1 * n1] * z[bl2 * n1];
+            acc += pv * s;
+          }
+        }
+      op.M[c + (size_t)Dl * (rr + (size_t)rn * (y + nyo * x))] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// Q-less QR of the sweep-1 matrix, TSQR over row chunks of QR_MAX_M rows.
+// stage 0 reads op.M ((rn*X) x Dl); chunk results are stacked (each block padded to Dl rows) into op.Ms;
+// a later stage reduces the stack.  The final stage writes L_t (= R^T, stored as row-major R) and r[t].
+// grid (nops, nchunks_cap).  `src_sel`: 0 = M, 1 = Ms ; dst: final ? Lbuf : the other buffer.
+__device__ __forceinline__ int qr_stage_rows(int m0, int n, int stage) {
+  int m = m0;
+  for (int s = 0; s < stage; ++s) m = ((m + QR_MAX_M - 1) / QR_MAX_M) * n;
+  return m;
+}
+__global__ void __launch_bounds__(NT) k_qr_stage(const OpDesc* ops, int t, int stage, int vrows, double* flops) {
+  extern __shared__ double smem[];
+  const OpDesc& op = ops[blockIdx.x];
+  const int Dl = op.a.bonds[t] * op.b.bonds[t];
+  const int rn = op.r[t + 1];
+  const int X = op.nyo * op.q;
+  const int m0 = rn * X;
+  if (stage > 0 && qr_stage_rows(m0, Dl, stage - 1) <= QR_MAX_M) return;  // already finished
+  const int m = qr_stage_rows(m0, Dl, stage);
+  const int ch = blockIdx.y;
+  const int row0 = ch * QR_MAX_M;
+  if (row0 >= m) return;
+  const int rows = min(QR_MAX_M, m - row0);
+  const bool single = (m <= QR_MAX_M);  // this stage finishes the factorisation
+  double* src = ((stage & 1) ? op.Ms : op.M) + (size_t)row0 * Dl;
+  if (flops && threadIdx.x == 0) {
+    const double mm = rows, nn = Dl;
+    atomicAdd(flops, mm >= nn ? 2.0 * mm * nn * nn - (2.0 / 3.0) * nn * nn * nn : 2.0 * nn * mm * mm - (2.0 / 3.0) * mm * mm * mm);
+  }
+  if (single) {
+    double* dst = op.Lbuf + (size_t)t * op.Lstride;
+    qr_r_cta(src, rows, Dl, Dl, dst, Dl, true, smem, vrows);
+    if (threadIdx.x == 0) op.r[t] = min(rows, Dl);
+  } else {
+    double* dst = ((stage & 1) ? op.M : op.Ms) + (size_t)ch * Dl * Dl;
+    qr_r_cta(src, rows, Dl, Dl, dst, Dl, true, smem, vrows);
+    const int k = min(rows, Dl);
+    for (int idx = threadIdx.x + k * Dl; idx < Dl * Dl; idx += NT) dst[idx] = 0.0;
+  }
+}
+
+// G_t[mt, (n1,n2), y, x] = sum_{y1,y2} Pyy sum_{m1,m2} Pc[mt,(m1,m2)] B1[m1,n1,y1,x] B2[m2,n2,y2,x]
+// grid (nops, q, nyo_max); dyn smem dcap*dcap*dcap doubles
+__global__ void __launch_bounds__(NT) k_kron_proj(const OpDesc* ops, int t) {
+  extern __shared__ double smem[];
+  const OpDesc& op = ops[blockIdx.x];
+  const int x = blockIdx.y, y = blockIdx.z;
+  if (x >= op.q || y >= op.nyo) return;
+  const int bl1 = op.a.bonds[t], br1 = op.a.bonds[t + 1], bl2 = op.b.bonds[t], br2 = op.b.bonds[t + 1];
+  const int Dr = br1 * br2;
+  const int dt = op.o.bonds[t];
+  const double* Pc = (t == 0) ? nullptr : op.Pc[(t - 1) & 1];
+  const double* A1 = op.a.data + (size_t)t * op.a.stride;
+  const double* A2 = op.b.data + (size_t)t * op.b.stride;
+  const double* pyy = op.pyy + (size_t)t * op.pyy_tstride;
+  const int ny1 = op.ny1, ny2 = op.ny2, nyo = op.nyo;
+  double* Y = smem;
+  double* Gs = op.G + (size_t)dt * Dr * (y + nyo * x);
+  bool first = true;
+  for (int y1 = 0; y1 < ny1; ++y1) {
+    bool any = false;
+    for (int y2 = 0; y2 < ny2; ++y2) any |= (pyy[y + nyo * (y1 + ny1 * (y2 + ny2 * x))] != 0.0);
+    if (!any) continue;
+    const int nyy = dt * bl2 * br1;
+    for (int idx = threadIdx.x; idx < nyy; idx += NT) {
+      const int mt = idx % dt, m2 = (idx / dt) % bl2, n1 = idx / (dt * bl2);
+      const double* a1 = A1 + (size_t)bl1 * (n1 + br1 * (y1 + ny1 * x));
+      double acc = 0.0;
+      if (Pc) {
+        const double* pc = Pc + mt + (size_t)dt * bl1 * m2;
+        for (int m1 = 0; m1 < bl1; ++m1) acc += pc[dt * m1] * a1[m1];
+      } else {
+        acc = a1[0];  // t == 0: bl1 = bl2 = dt = 1
+      }
+      Y[idx] = acc;
+    }
+    __syncthreads();
+    for (int y2 = 0; y2 < ny2; ++y2) {
+      const double pv = pyy[y + nyo * (y1 + ny1 * (y2 + ny2 * x))];
+      if (pv == 0.0) continue;
+      const double* a2 = A2 + (size_t)bl2 * br2 * (y2 + ny2 * x);
+      const int ng = dt * Dr;
+      for (int idx = threadIdx.x; idx < ng; idx += NT) {
+        const int mt = idx % dt, n = idx / dt, n1 = n % br1, n2 = n / br1;
+        const double* yy = Y + mt + (size_t)dt * bl2 * n1;
+        const double* aa = a2 + (size_t)bl2 * n2;
+        double s = 0.0;
+        for (int m2 = 0; m2 < bl2; ++m2) s += yy[dt * m2] * aa[m2];
+        Gs[idx] = first ? pv * s : Gs[idx] + pv * s;
+      }
+      first = false;
+    }
+    __syncthreads();
+  }
+  if (first) {
+    const int ng = dt * Dr;
+    for (int idx = threadIdx.x; idx < ng; idx += NT) Gs[idx] = 0.0;
+  }
+}
+
+// M2T[a + dX*rr] = sum_n G[mt + dt*(n + Dr*yx)] * L_{t+1}[n + Dr*rr],  a = mt + dt*yx
+// grid (nops, ceil(dXcap/32), ceil(rcap/32)), 32x32 tiles, 4 outputs per thread
+__global__ void __launch_bounds__(NT) k_gemm_m2t(const OpDesc* ops, int t) {
+  __shared__ double Gs[32][33];
+  __shared__ double Ls[32][33];
+  const OpDesc& op = ops[blockIdx.x];
+  const int br1 = op.a.bonds[t + 1], br2 = op.b.bonds[t + 1];
+  const int Dr = br1 * br2;
+  const int dt = op.o.bonds[t];
+  const int X = op.nyo * op.q;
+  const int dX = dt * X;
+  const int rn = op.r[t + 1];
+  const int a0 = blockIdx.y * 32, r0 = blockIdx.z * 32;
+  if (a0 >= dX || r0 >= rn) return;
+  const double* Lm = op.Lbuf + (size_t)(t + 1) * op.Lstride;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty 0..7
+  double acc[4] = {0, 0, 0, 0};
+  for (int n0 = 0; n0 < Dr; n0 += 32) {
+    // Gs[aa][nn], Ls[nn][rr]
+    for (int k = 0; k < 4; ++k) {
+      const int nn = ty + 8 * k;
+      const int a = a0 + tx, n = n0 + nn;
+      Gs[tx][nn] = (a < dX && n < Dr) ? op.G[(a % dt) + (size_t)dt * (n + (size_t)Dr * (a / dt))] : 0.0;
+      const int nl = n0 + tx, rr = r0 + nn;
+      Ls[tx][nn] = (nl < Dr && rr < rn) ? Lm[nl + (size_t)Dr * rr] : 0.0;  // Ls[n][rr]
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int nn = 0; nn < 32; ++nn) {
+      const double g = Gs[tx][nn];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += g * Ls[nn][ty + 8 * k];
+    }
+    __syncthreads();
+  }
+  for (int k = 0; k < 4; ++k) {
+    const int a = a0 + tx, rr = r0 + ty + 8 * k;
+    if (a < dX && rr < rn) op.M2T[a + (size_t)dX * rr] = acc[k];
+  }
+}
+
+// if r_{t+1} > dX: R2 = R-factor of M2T (r x dX); Jacobi then runs on R2^T (dX x dX)
+__global__ void __launch_bounds__(NT) k_qr_small(const OpDesc* ops, int t, int vrows) {
+  extern __shared__ double smem[];
+  const OpDesc& op = ops[blockIdx.x];
+  const int dX = op.o.bonds[t] * op.nyo * op.q;
+  const int rn = op.r[t + 1];
+  if (rn <= dX) return;
+  qr_r_cta(op.M2T, rn, dX, dX, op.R2, dX, true, smem, vrows);
+}
+
+// truncated SVD (left vectors) of M2 (dX x r), output site, new carry Pc_t = U^T G_t (rescaled).
+// dyn smem: jac_doubles (matrix cache) + scratch
+__global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t, Trunc tr, int dcap, int jac_doubles,
+                                                       int* err) {
+  extern __shared__ double smem[];
+  __shared__ int flag;
+  __shared__ int s_keep;
+  __shared__ double red[NW + 1];
+  const OpDesc& op = ops[blockIdx.x];
+  const int br1 = op.a.bonds[t + 1], br2 = op.b.bonds[t + 1];
+  const int Dr = br1 * br2;
+  const int dt = op.o.bonds[t];
+  const int X = op.nyo * op.q;
+  const int p = dt * X;
+  const int rn = op.r[t + 1];
+  const int c = min(p, rn);
+  double* Ag = (rn > p) ? op.R2 : op.M2T;  // column-major p x c, lda = p
+  double* sig = smem;                      // c
+  int* order = reinterpret_cast<int*>(smem + c);  // c ints
+  double* cache = smem + c + (c + 1) / 2 + 1;
+  double* A = Ag;
+  if ((long long)p * c <= jac_doubles) {
+    for (int i = threadIdx.x; i < p * c; i += NT) cache[i] = Ag[i];
+    A = cache;
+    __syncthreads();
+  }
+  const int sweeps = jacobi_cols(A, p, c, p, &flag);
+  if (sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
+  jacobi_sort(A, p, c, p, sig, order);
+  if (threadIdx.x == 0) {
+    // sorted view for the policy
+    double nrm2 = 0.0;
+    for (int i = 0; i < c; ++i) nrm2 += sig[i] * sig[i];
+    int k = c;
+    if (tr.kind == 1 || tr.kind == 2) {
+      const double lim = tr.eps * sqrt(nrm2);
+      int last = 0;
+      for (int i = 0; i < c; ++i)
+        if (sig[order[i]] > lim) last = i + 1;
+      k = last > 0 ? last : 1;
+    }
+    if (tr.kind == 0 || tr.kind == 2) k = min(k, tr.d);
+    if (k > dcap) {
+      atomicOr(err, ERR_BOND_OVERFLOW);
+      k = dcap;
+    }
+    if (!(nrm2 == nrm2)) atomicOr(err, ERR_NAN);
+    s_keep = k;
+    op.o.bonds[t + 1] = k;
+  }
+  __syncthreads();
+  const int keep = s_keep;
+  // normalise the kept columns in place -> U
+  for (int kk = threadIdx.x >> 5; kk < keep; kk += NW) {
+    const int col = order[kk];
+    const double s = sig[col];
+    const double f = jacobi_inv_sigma(s, sig[order[0]]);
+    for (int k = threadIdx.x & 31; k < p; k += 32) A[k + (size_t)col * p] *= f;
+  }
+  __syncthreads();
+  // output site A_t[mt, kk, yx] = U[mt + dt*yx, kk]
+  double* O = op.o.data + (size_t)t * op.o.stride;
+  for (int idx = threadIdx.x; idx < dt * keep * X; idx += NT) {
+    const int mt = idx % dt, kk = (idx / dt) % keep, yx = idx / (dt * keep);
+    O[idx] = A[(mt + dt * yx) + (size_t)order[kk] * p];
+  }
+  // carry Pc_t[kk + keep*n] = sum_a U[a,kk] G[a; n]
+  double* Pn = op.Pc[t & 1];
+  double mx = 0.0;
+  for (int idx = threadIdx.x; idx < keep * Dr; idx += NT) {
+    const int kk = idx % keep, n = idx / keep;
+    const double* u = A + (size_t)order[kk] * p;
+    double acc = 0.0;
+    for (int yx = 0; yx < X; ++yx) {
+      const double* g = op.G + (size_t)dt * (n + (size_t)Dr * yx);
+      const double* uu = u + dt * yx;
+      for (int mt = 0; mt < dt; ++mt) acc += uu[mt] * g[mt];
+    }
+    Pn[idx] = acc;
+    mx = fmax(mx, fabs(acc));
+  }
+  mx = block_max(mx, red);
+  if (mx > 0.0 && isfinite(mx)) {
+    const double f = 1.0 / mx;
+    for (int idx = threadIdx.x; idx < keep * Dr; idx += NT) Pn[idx] *= f;
+    if (threadIdx.x == 0) *op.o.ls += log(mx);
+  }
+}
+
+// last site: A_L[mt, 0, yx] = G_L (Dr = 1), max-abs rescaled
+__global__ void __launch_bounds__(NT) k_op_last(const OpDesc* ops, int t) {
+  __shared__ double red[NW + 1];
+  const OpDesc& op = ops[blockIdx.x];
+  const int dt = op.o.bonds[t];
+  const int X = op.nyo * op.q;
+  double* O = op.o.data + (size_t)t * op.o.stride;
+  double mx = 0.0;
+  for (int idx = threadIdx.x; idx < dt * X; idx += NT) mx = fmax(mx, fabs(op.G[idx]));
+  mx = block_max(mx, red);
+  const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+  for (int idx = threadIdx.x; idx < dt * X; idx += NT) O[idx] = op.G[idx] * f;
+  if (threadIdx.x == 0) {
+    op.o.bonds[t + 1] = 1;
+    if (f != 1.0) *op.o.ls += log(mx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// outgoing message: MPEM3 build + MPEM3->MPEM2 + truncating R->L sweep + normalisation, one CTA per edge
+// ------------------------------------------------------------------------------------------------
+struct FinJob {
+  TTRef c;    // C_j [m,n,y,x]
+  TTRef out;  // message slot [m,n,x,xj]
+  int nyc, q, qj;
+  const double* W;  // [x' + q*(x + q*(xj + qj*y))] per t
+  int w_tstride;
+  const double* phi;   // [t][x]
+  double* logz_out;
+  // scratch (global)
+  double* Rbuf;  // R index t at Rbuf + t*rstride : row-major k_t x (bl_t*q)
+  int rstride;
+  int* kdim;     // [L+1]
+  double* Bt;    // [m,n,x,xj,x'] current site
+  double* S;     // sweep-A matrix / sweep-B N^T
+  double* H;     // [m,x,xj,k']
+  double* R2;    // (d*q*qj)^2 : QR pre-reduction of a wide sweep-B matrix
+  double* Pr[2];
+};
+
+__device__ inline void fin_build_B(const FinJob& jb, int t, int L, double* Bt) {
+  const int bl = jb.c.bonds[t], br = jb.c.bonds[t + 1];
+  const int q = jb.q, qj = jb.qj, ny = jb.nyc;
+  const double* C = jb.c.data + (size_t)t * jb.c.stride;
+  const double* phi = jb.phi + (size_t)t * q;
+  const int mn = bl * br;
+  const int tot = mn * q * qj * q;
+  if (t < L - 1) {
+    const double* W = jb.W + (size_t)t * jb.w_tstride;
+    for (int idx = threadIdx.x; idx < tot; idx += NT) {
+      const int e = idx % mn, x = (idx / mn) % q, xj = (idx / (mn * q)) % qj, xn = idx / (mn * q * qj);
+      double acc = 0.0;
+      for (int y = 0; y < ny; ++y) acc += W[xn + q * (x + q * (xj + qj * y))] * C[e + mn * (y + ny * x)];
+      Bt[idx] = acc * phi[x];
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < tot; idx += NT) {
+      const int e = idx % mn, x = (idx / mn) % q;
+      double acc = 0.0;
+      for (int y = 0; y < ny; ++y) acc += C[e + mn * (y + ny * x)];
+      Bt[idx] = acc * phi[x];
+    }
+  }
+  __syncthreads();
+}
+
+// dyn smem: qr scratch (vrows) followed by jacobi cache (jac_doubles)
+__global__ void __launch_bounds__(NT) k_finalize(const FinJob* jobs, int L, Trunc tr, int dcap, int vrows,
+                                                 int jac_doubles, int* err) {
+  extern __shared__ double smem[];
+  __shared__ int flag;
+  __shared__ int s_keep;
+  __shared__ double red[NW + 1];
+  __shared__ double s_ls;
+  const FinJob& jb = jobs[blockIdx.x];
+  const int q = jb.q, qj = jb.qj;
+  double* qrs = smem;
+  double* jsm = smem + qr_shared_doubles(vrows);
+  if (threadIdx.x == 0) {
+    jb.kdim[0] = 1;
+    s_ls = *jb.c.ls;
+  }
+  __syncthreads();
+  // ---------------- sweep A (L->R): triangular factors of the left-orthonormalisation ----------------
+  for (int t = 0; t < L - 1; ++t) {
+    const int bl = jb.c.bonds[t], br = jb.c.bonds[t + 1];
+    fin_build_B(jb, t, L, jb.Bt);
+    const int kprev = jb.kdim[t];
+    const int nrows = kprev * q * qj, ncols = br * q;
+    const double* Rp = jb.Rbuf + (size_t)t * jb.rstride;  // kprev x (bl*q) row-major (unused for t==0)
+    for (int idx = threadIdx.x; idx < nrows * ncols; idx += NT) {
+      const int col = idx % ncols, row = idx / ncols;
+      const int n = col % br, xn = col / br;
+      const int mt = row % kprev, x = (row / kprev) % q, xj = row / (kprev * q);
+      const double* b = jb.Bt + (size_t)bl * (n + br * (x + q * (xj + qj * xn)));
+      double acc = 0.0;
+      if (t == 0) acc = b[0];
+      else {
+        const double* rp = Rp + (size_t)mt * (bl * q) + bl * x;
+        for (int m = 0; m < bl; ++m) acc += rp[m] * b[m];
+      }
+      jb.S[idx] = acc;
+    }
+    __syncthreads();
+    double* Rn = jb.Rbuf + (size_t)(t + 1) * jb.rstride;
+    qr_r_cta(jb.S, nrows, ncols, ncols, Rn, ncols, true, qrs, vrows);
+    if (threadIdx.x == 0) jb.kdim[t + 1] = min(nrows, ncols);
+    __syncthreads();
+  }
+  // ---------------- sweep B (R->L): truncating SVDs ----------------
+  if (threadIdx.x == 0) {
+    jb.out.bonds[L] = 1;
+    jb.out.bonds[0] = 1;
+  }
+  __syncthreads();
+  for (int t = L - 1; t >= 0; --t) {
+    const int bl = jb.c.bonds[t], br = jb.c.bonds[t + 1];
+    fin_build_B(jb, t, L, jb.Bt);
+    const int kn = jb.out.bonds[t + 1];  // k~_{t+1}
+    const double* Pr = (t == L - 1) ? nullptr : jb.Pr[(t + 1) & 1];  // [(n + br*x') + br*q*k']
+    // H[m + bl*(x + q*(xj + qj*k'))]
+    const int nh = bl * q * qj * kn;
+    for (int idx = threadIdx.x; idx < nh; idx += NT) {
+      const int m = idx % bl, x = (idx / bl) % q, xj = (idx / (bl * q)) % qj, kp = idx / (bl * q * qj);
+      double acc = 0.0;
+      if (!Pr) acc = jb.Bt[m + (size_t)bl * (0 + br * (x + q * (xj + qj * 0)))];
+      else {
+        const double* pr = Pr + (size_t)br * q * kp;
+        for (int xn = 0; xn < q; ++xn) {
+          const double* b = jb.Bt + m + (size_t)bl * br * (x + q * (xj + qj * xn));
+          for (int n = 0; n < br; ++n) acc += b[bl * n] * pr[n + br * xn];
+        }
+      }
+      jb.H[idx] = acc;
+    }
+    __syncthreads();
+    double* O = jb.out.data + (size_t)t * jb.out.stride;
+    if (t == 0) {
+      // first site: [1, k', x, xj] = H[0,x,xj,k'], rescaled
+      double mx = 0.0;
+      for (int idx = threadIdx.x; idx < nh; idx += NT) mx = fmax(mx, fabs(jb.H[idx]));
+      mx = block_max(mx, red);
+      const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+      for (int idx = threadIdx.x; idx < nh; idx += NT) {
+        const int x = idx % q, xj = (idx / q) % qj, kp = idx / (q * qj);
+        O[kp + kn * (x + q * xj)] = jb.H[idx] * f;
+      }
+      if (threadIdx.x == 0 && f != 1.0) s_ls += log(mx);
+      __syncthreads();
+      break;
+    }
+    // N^T column-major: rows rr = k' + kn*(x + q*xj), cols mt
+    const int kprev = jb.kdim[t];
+    const int p = kn * q * qj;
+    int c = kprev;
+    const double* Rp = jb.Rbuf + (size_t)t * jb.rstride;
+    const bool wide = c > p;  // more columns than rows: reduce with a Q-less QR first (right vectors of N = those of R)
+    const int cp = max(c, p);
+    double* jcache = jsm + cp + (cp + 1) / 2 + 1;
+    double* A = (!wide && (long long)p * c <= jac_doubles) ? jcache : jb.S;
+    double* sig = jsm;
+    int* order = reinterpret_cast<int*>(jsm + cp);
+    for (int idx = threadIdx.x; idx < p * c; idx += NT) {
+      const int rr = idx % p, mt = idx / p;
+      const int kp = rr % kn, x = (rr / kn) % q, xj = rr / (kn * q);
+      const double* rp = Rp + (size_t)mt * (bl * q) + bl * x;
+      const double* h = jb.H + (size_t)bl * (x + q * (xj + qj * kp));
+      double acc = 0.0;
+      for (int m = 0; m < bl; ++m) acc += rp[m] * h[m];
+      A[idx] = acc;
+    }
+    __syncthreads();
+    if (wide) {
+      // A is N row-major (c x p); R (p x p, row-major) == R^T column-major
+      qr_r_cta(A, c, p, p, jb.R2, p, false, qrs, vrows);
+      A = jb.R2;
+      c = p;
+      if ((long long)p * c <= jac_doubles) {
+        for (int idx = threadIdx.x; idx < p * c; idx += NT) jcache[idx] = A[idx];
+        A = jcache;
+      }
+      __syncthreads();
+    }
+    const int sweeps = jacobi_cols(A, p, c, p, &flag);
+    if (sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
+    jacobi_sort(A, p, c, p, sig, order);
+    if (threadIdx.x == 0) {
+      const int ns = min(p, c);
+      double nrm2 = 0.0;
+      for (int i = 0; i < ns; ++i) nrm2 += sig[order[i]] * sig[order[i]];
+      int k = ns;
+      if (tr.kind == 1 || tr.kind == 2) {
+        const double lim = tr.eps * sqrt(nrm2);
+        int last = 0;
+        for (int i = 0; i < ns; ++i)
+          if (sig[order[i]] > lim) last = i + 1;
+        k = last > 0 ? last : 1;
+      }
+      if (tr.kind == 0 || tr.kind == 2) k = min(k, tr.d);
+      if (k > dcap) {
+        atomicOr(err, ERR_BOND_OVERFLOW);
+        k = dcap;
+      }
+      if (!(nrm2 == nrm2)) atomicOr(err, ERR_NAN);
+      s_keep = k;
+      jb.out.bonds[t] = k;
+    }
+    __syncthreads();
+    const int keep = s_keep;
+    for (int kk = threadIdx.x >> 5; kk < keep; kk += NW) {
+      const int col = order[kk];
+      const double s = sig[col];
+      const double f = jacobi_inv_sigma(s, sig[order[0]]);
+      for (int k = threadIdx.x & 31; k < p; k += 32) A[k + (size_t)col * p] *= f;
+    }
+    __syncthreads();
+    // message site: O[kk + keep*rr] = V^T[kk, rr]
+    for (int idx = threadIdx.x; idx < keep * p; idx += NT) {
+      const int kk = idx % keep, rr = idx / keep;
+      O[idx] = A[rr + (size_t)order[kk] * p];
+    }
+    // Pr_t[(m + bl*a) + bl*q*kk] = sum_{xj,k'} H[m,a,xj,k'] V^T[kk,(k',a,xj)]
+    double* Pn = jb.Pr[t & 1];
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < bl * q * keep; idx += NT) {
+      const int m = idx % bl, a = (idx / bl) % q, kk = idx / (bl * q);
+      const double* v = A + (size_t)order[kk] * p;
+      double acc = 0.0;
+      for (int xj = 0; xj < qj; ++xj)
+        for (int kp = 0; kp < kn; ++kp)
+          acc += jb.H[m + (size_t)bl * (a + q * (xj + qj * kp))] * v[kp + kn * (a + q * xj)];
+      Pn[idx] = acc;
+      mx = fmax(mx, fabs(acc));
+    }
+    mx = block_max(mx, red);
+    if (mx > 0.0 && isfinite(mx)) {
+      const double f = 1.0 / mx;
+      for (int idx = threadIdx.x; idx < bl * q * keep; idx += NT) Pn[idx] *= f;
+      if (threadIdx.x == 0) s_ls += log(mx);
+    }
+    __syncthreads();
+  }
+  // ---------------- normalisation: Z = sum_x prod_t A_t ----------------
+  // l (1 x k) <- l * sum_{x,xj} A_t[:,:,x,xj]; vectors in jsm
+  {
+    double* l0 = jsm;
+    double* l1 = jsm + dcap + 1;
+    if (threadIdx.x == 0) l0[0] = 1.0;
+    __syncthreads();
+    double logZ = 0.0;
+    for (int t = 0; t < L; ++t) {
+      const int bl = jb.out.bonds[t], br = jb.out.bonds[t + 1];
+      const double* O = jb.out.data + (size_t)t * jb.out.stride;
+      const int P = q * qj;
+      double mx = 0.0;
+      for (int n = threadIdx.x; n < br; n += NT) {
+        double acc = 0.0;
+        for (int pp = 0; pp < P; ++pp)
+          for (int m = 0; m < bl; ++m) acc += l0[m] * O[m + (size_t)bl * (n + br * pp)];
+        l1[n] = acc;
+        mx = fmax(mx, fabs(acc));
+      }
+      mx = block_max(mx, red);
+      const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+      for (int n = threadIdx.x; n < br; n += NT) l1[n] *= f;
+      if (f != 1.0) logZ += log(mx);
+      __syncthreads();
+      double* tmp = l0;
+      l0 = l1;
+      l1 = tmp;
+    }
+    if (threadIdx.x == 0) {
+      const double z = l0[0];
+      logZ += log(fabs(z));
+      *jb.logz_out = s_ls + logZ;
+      *jb.out.ls = -logZ;
+      if (!(logZ == logZ) || !(z > 0.0)) atomicOr(err, ERR_NAN);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// belief of node i from `full`: marginals + log z_i, one CTA per node
+// ------------------------------------------------------------------------------------------------
+struct BelJob {
+  TTRef full;  // [m,n,y,x]
+  int ny, q;
+  const double* Wd;  // [x' + q*(x + q*y)] per t
+  int w_tstride;
+  const double* phi;
+  double* marg;   // [t][x] output (stride q)
+  double* logz;   // output scalar
+  double* bw;     // scratch [L][dcap*q]
+  double* Bt;     // scratch [m,n,x,x']
+};
+
+__global__ void __launch_bounds__(NT) k_belief(const BelJob* jobs, int L, int dcap, int* err) {
+  __shared__ double red[NW + 1];
+  extern __shared__ double smem[];  // fw0, fw1 : dcap*q each
+  const BelJob& jb = jobs[blockIdx.x];
+  const int q = jb.q, ny = jb.ny;
+  const int bwst = dcap * q;
+  double logZ = 0.0;
+  // backward pass
+  for (int t = L - 1; t >= 0; --t) {
+    const int bl = jb.full.bonds[t], br = jb.full.bonds[t + 1];
+    const double* C = jb.full.data + (size_t)t * jb.full.stride;
+    const double* phi = jb.phi + (size_t)t * q;
+    double* bw = jb.bw + (size_t)t * bwst;
+    const int mn = bl * br;
+    double mx = 0.0;
+    if (t == L - 1) {
+      for (int idx = threadIdx.x; idx < bl * q; idx += NT) {
+        const int m = idx % bl, x = idx / bl;
+        double acc = 0.0;
+        for (int y = 0; y < ny; ++y) acc += C[m + mn * (y + ny * x)];
+        acc *= phi[x];
+        bw[idx] = acc;
+        mx = fmax(mx, fabs(acc));
+      }
+    } else {
+      const double* W = jb.Wd + (size_t)t * jb.w_tstride;
+      const double* bn = jb.bw + (size_t)(t + 1) * bwst;  // [n + br*x']
+      // Bt[m,n,x,x'] then contract
+      for (int idx = threadIdx.x; idx < mn * q * q; idx += NT) {
+        const int e = idx % mn, x = (idx / mn) % q, xn = idx / (mn * q);
+        double acc = 0.0;
+        for (int y = 0; y < ny; ++y) acc += W[xn + q * (x + q * y)] * C[e + mn * (y + ny * x)];
+        jb.Bt[idx] = acc * phi[x];
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < bl * q; idx += NT) {
+        const int m = idx % bl, x = idx / bl;
+        double acc = 0.0;
+        for (int xn = 0; xn < q; ++xn)
+          for (int n = 0; n < br; ++n) acc += jb.Bt[m + bl * (n + br * (x + q * xn))] * bn[n + br * xn];
+        bw[idx] = acc;
+        mx = fmax(mx, fabs(acc));
+      }
+    }
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < bl * q; idx += NT) bw[idx] *= f;
+    if (f != 1.0) logZ += log(mx);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double z = 0.0;
+    for (int x = 0; x < q; ++x) z += jb.bw[x];  // bl = 1 at t = 0
+    const double lz = *jb.full.ls + logZ + log(z);
+    *jb.logz = lz;
+    if (!(lz == lz)) atomicOr(err, ERR_NAN);
+  }
+  // forward pass + marginals
+  double* fw0 = smem;
+  double* fw1 = smem + bwst;
+  for (int t = 0; t < L; ++t) {
+    const int bl = jb.full.bonds[t], br = jb.full.bonds[t + 1];
+    const double* bw = jb.bw + (size_t)t * bwst;
+    if (threadIdx.x < q) {
+      const int x = threadIdx.x;
+      double acc = 0.0;
+      if (t == 0) acc = bw[x];
+      else
+        for (int m = 0; m < bl; ++m) acc += fw0[m + bl * x] * bw[m + bl * x];
+      red[x] = acc;  // q <= NW+1 assumed (q <= 8)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int x = 0; x < q; ++x) s += red[x];
+      for (int x = 0; x < q; ++x) jb.marg[(size_t)t * q + x] = red[x] / s;
+    }
+    __syncthreads();
+    if (t == L - 1) break;
+    // fw_t[n,x'] = sum_{m,x} fw_{t-1}[m,x] B_t[m,n,x,x']
+    const double* C = jb.full.data + (size_t)t * jb.full.stride;
+    const double* phi = jb.phi + (size_t)t * q;
+    const double* W = jb.Wd + (size_t)t * jb.w_tstride;
+    const int mn = bl * br;
+    for (int idx = threadIdx.x; idx < mn * q * q; idx += NT) {
+      const int e = idx % mn, x = (idx / mn) % q, xn = idx / (mn * q);
+      double acc = 0.0;
+      for (int y = 0; y < ny; ++y) acc += W[xn + q * (x + q * y)] * C[e + mn * (y + ny * x)];
+      jb.Bt[idx] = acc * phi[x];
+    }
+    __syncthreads();
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < br * q; idx += NT) {
+      const int n = idx % br, xn = idx / br;
+      double acc = 0.0;
+      for (int x = 0; x < q; ++x)
+        for (int m = 0; m < bl; ++m)
+          acc += (t == 0 ? 1.0 : fw0[m + bl * x]) * jb.Bt[m + bl * (n + br * (x + q * xn))];
+      fw1[idx] = acc;
+      mx = fmax(mx, fabs(acc));
+    }
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < br * q; idx += NT) fw1[idx] *= f;
+    __syncthreads();
+    double* tmp = fw0;
+    fw0 = fw1;
+    fw1 = tmp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair beliefs: one CTA per directed edge.  env matrices [a + da*b]
+// ------------------------------------------------------------------------------------------------
+struct PairJob {
+  TTRef A;  // mu_e   [a,a',xs,xd]
+  TTRef B;  // mu_rev [b,b',xd,xs]
+  const double* psi;  // [t][xs + qs*xd]
+  int qs, qd;
+  double* out;   // [t][xs + qs*xd]
+  double* logz;  // scalar
+  double* Renv;  // scratch [L+1][dcap*dcap]
+};
+
+__global__ void __launch_bounds__(NT) k_pair_belief(const PairJob* jobs, int L, int dcap) {
+  extern __shared__ double smem[];  // tmp [dcap*dcap], Lenv0, Lenv1
+  __shared__ double red[NW + 1];
+  __shared__ double pm[64];
+  const PairJob& jb = jobs[blockIdx.x];
+  const int qs = jb.qs, qd = jb.qd;
+  const int est = dcap * dcap;
+  double* tmp = smem;
+  double* L0 = smem + est;
+  double* L1 = smem + 2 * est;
+  double logZ = 0.0;
+  if (threadIdx.x == 0) jb.Renv[(size_t)L * est] = 1.0;
+  __syncthreads();
+  for (int t = L - 1; t >= 0; --t) {
+    const int al = jb.A.bonds[t], ar = jb.A.bonds[t + 1], bl = jb.B.bonds[t], br = jb.B.bonds[t + 1];
+    const double* At = jb.A.data + (size_t)t * jb.A.stride;
+    const double* Bt = jb.B.data + (size_t)t * jb.B.stride;
+    const double* psi = jb.psi + (size_t)t * qs * qd;
+    const double* Rn = jb.Renv + (size_t)(t + 1) * est;  // [a' + ar*b']
+    double* Rt = jb.Renv + (size_t)t * est;              // [a + al*b]
+    for (int idx = threadIdx.x; idx < al * bl; idx += NT) Rt[idx] = 0.0;
+    __syncthreads();
+    for (int xs = 0; xs < qs; ++xs)
+      for (int xd = 0; xd < qd; ++xd) {
+        const double ps = psi[xs + qs * xd];
+        if (ps == 0.0) continue;
+        const double* Ax = At + (size_t)al * ar * (xs + qs * xd);
+        const double* Bx = Bt + (size_t)bl * br * (xd + qd * xs);
+        // tmp[a + al*b'] = sum_a' Ax[a,a'] Rn[a',b']
+        for (int idx = threadIdx.x; idx < al * br; idx += NT) {
+          const int a = idx % al, b2 = idx / al;
+          double acc = 0.0;
+          for (int a2 = 0; a2 < ar; ++a2) acc += Ax[a + al * a2] * Rn[a2 + ar * b2];
+          tmp[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < al * bl; idx += NT) {
+          const int a = idx % al, b = idx / al;
+          double acc = 0.0;
+          for (int b2 = 0; b2 < br; ++b2) acc += tmp[a + al * b2] * Bx[b + bl * b2];
+          Rt[idx] += ps * acc;
+        }
+        __syncthreads();
+      }
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < al * bl; idx += NT) mx = fmax(mx, fabs(Rt[idx]));
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < al * bl; idx += NT) Rt[idx] *= f;
+    if (f != 1.0) logZ += log(mx);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *jb.logz = *jb.A.ls + *jb.B.ls + logZ + log(jb.Renv[0]);
+  // forward: Lenv [a + al*b], marginals
+  if (threadIdx.x == 0) L0[0] = 1.0;
+  __syncthreads();
+  for (int t = 0; t < L; ++t) {
+    const int al = jb.A.bonds[t], ar = jb.A.bonds[t + 1], bl = jb.B.bonds[t], br = jb.B.bonds[t + 1];
+    const double* At = jb.A.data + (size_t)t * jb.A.stride;
+    const double* Bt = jb.B.data + (size_t)t * jb.B.stride;
+    const double* psi = jb.psi + (size_t)t * qs * qd;
+    const double* Rn = jb.Renv + (size_t)(t + 1) * est;
+    for (int idx = threadIdx.x; idx < ar * br; idx += NT) L1[idx] = 0.0;
+    __syncthreads();
+    for (int xs = 0; xs < qs; ++xs)
+      for (int xd = 0; xd < qd; ++xd) {
+        const double ps = psi[xs + qs * xd];
+        const double* Ax = At + (size_t)al * ar * (xs + qs * xd);
+        const double* Bx = Bt + (size_t)bl * br * (xd + qd * xs);
+        // tmp[a' + ar*b] = sum_a Ax[a,a'] L0[a,b]
+        for (int idx = threadIdx.x; idx < ar * bl; idx += NT) {
+          const int a2 = idx % ar, b = idx / ar;
+          double acc = 0.0;
+          for (int a = 0; a < al; ++a) acc += Ax[a + al * a2] * L0[a + al * b];
+          tmp[idx] = acc;
+        }
+        __syncthreads();
+        // new[a',b'] = sum_b tmp[a',b] Bx[b,b'] ; marginal weight = sum new .* Rn
+        double part = 0.0;
+        for (int idx = threadIdx.x; idx < ar * br; idx += NT) {
+          const int a2 = idx % ar, b2 = idx / ar;
+          double acc = 0.0;
+          for (int b = 0; b < bl; ++b) acc += tmp[a2 + ar * b] * Bx[b + bl * b2];
+          acc *= ps;
+          L1[idx] += acc;
+          part += acc * Rn[idx];
+        }
+        part = block_sum1(part, red);
+        if (threadIdx.x == 0) pm[xs + qs * xd] = part;
+        __syncthreads();
+      }
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < qs * qd; ++i) s += pm[i];
+      for (int i = 0; i < qs * qd; ++i) jb.out[(size_t)t * qs * qd + i] = pm[i] / s;
+    }
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < ar * br; idx += NT) mx = fmax(mx, fabs(L1[idx]));
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < ar * br; idx += NT) L1[idx] *= f;
+    __syncthreads();
+    double* sw = L0;
+    L0 = L1;
+    L1 = sw;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+// Minit TT: [1,1,y,x] = prob_y0 per t
+struct InitJob {
+  TTRef out;
+  const double* minit;  // [y + ny0*x] per t
+  int tstride, n;       // n = ny0*q
+};
+__global__ void k_init_tt(const InitJob* jobs, int njobs, int L) {
+  const int j = blockIdx.x;
+  if (j >= njobs) return;
+  const InitJob& jb = jobs[j];
+  for (int idx = threadIdx.x; idx < L * jb.n; idx += blockDim.x) {
+    const int t = idx / jb.n, e = idx % jb.n;
+    jb.out.data[(size_t)t * jb.out.stride + e] = jb.minit[(size_t)t * jb.tstride + e];
+  }
+  for (int i = threadIdx.x; i <= L; i += blockDim.x) jb.out.bonds[i] = 1;
+  if (threadIdx.x == 0) *jb.out.ls = 0.0;
+}
+
+// f_i = (z/2 - 1) logz_i - 1/2 sum_j logz_{i->j}      (src/recursive_bp_factor.jl:163)
+struct FJob {
+  const double* logzi;
+  const double* logzij;  // contiguous z entries
+  int z;
+  double* f;
+};
+__global__ void k_free_energy(const FJob* jobs, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const FJob jb = jobs[i];
+  double s = 0.0;
+  for (int j = 0; j < jb.z; ++j) s += jb.logzij[j];
+  *jb.f = (0.5 * jb.z - 1.0) * (*jb.logzi) - 0.5 * s;
+}
+
+// flat message: every site all-ones with bond 1, normalised: ls = -L*log(qs*qd)
+__global__ void k_flat_messages(double* data, int* bonds, double* ls, const int* qprod, long long slot, int L,
+                                long long E2, int sstride) {
+  const long long e = blockIdx.x;
+  if (e >= E2) return;
+  const int P = qprod[e];
+  for (int idx = threadIdx.x; idx < L * P; idx += blockDim.x) {
+    const int t = idx / P, k = idx % P;
+    data[e * slot + (size_t)t * sstride + k] = 1.0;
+  }
+  for (int i = threadIdx.x; i <= L; i += blockDim.x) bonds[e * (L + 1) + i] = 1;
+  if (threadIdx.x == 0) ls[e] = -(double)L * log((double)P);
+}
+
+// means and delta: mean[i,t] = sum_x obs[i,x] marg[i,t,x]; delta = max |new - old| over the listed nodes
+__global__ void k_means_delta(const double* marg, const int64_t* moff, const int* q, const double* obs, int qmax,
+                              const int64_t* nodes, long long nn, int L, double* means, double* delta) {
+  const long long k = blockIdx.x;
+  if (k >= nn) return;
+  const long long i = nodes ? (long long)nodes[k] : k;
+  const int qi = q[i];
+  double mx = 0.0;
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    double m = 0.0;
+    for (int x = 0; x < qi; ++x) m += (obs ? obs[i * qmax + x] : (double)(x + 1)) * marg[moff[i] + (size_t)t * qi + x];
+    const double old = means[i * L + t];
+    mx = fmax(mx, fabs(m - old));
+    means[i * L + t] = m;
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0 && mx > 0.0) {
+    // atomic max on non-negative doubles via long long compare
+    atomicMax(reinterpret_cast<unsigned long long*>(delta), (unsigned long long)__double_as_longlong(mx));
+  }
+}
+
+}  // namespace mpbp

@@ -1,0 +1,93 @@
+"""CPU-side checks of the boundary: the shared library loads and exports every symbol include/mpbp.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mpbp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpbp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    import __graft_entry__ as G
+    G.build()
+    from mpbp_b200 import _lib
+    lib = C.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mpbp.h but not exported"
+    for n in names:
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+
+
+def test_version_and_error_string_without_gpu():
+    from mpbp_b200 import _lib
+    L = _lib.lib()
+    assert L.mpbp_version() == 100
+    assert isinstance(L.mpbp_last_error(), bytes)
+    # argument validation happens before any CUDA call
+    assert L.mpbp_destroy(None) == 0
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    from mpbp_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.MPBPError):
+        _lib.lib()
+
+
+def test_host_tabulation_matches_oracle_factors():
+    """the product's host-side factor tables agree with the oracle's independent factor definitions"""
+    import numpy as np
+    import mpbp_b200 as M
+    from oracle import factors as OF
+    pairs = [
+        (OF.HomogeneousGlauberFactor(0.7, -0.2, 1.3), M.HomogeneousGlauberFactor(0.7, -0.2, 1.3), 2),
+        (OF.SISFactor(0.3, 0.2, 0.05), M.SISFactor(0.3, 0.2, 0.05), 2),
+        (OF.SIRSFactor(0.3, 0.2, 0.1, 0.05), M.SIRSFactor(0.3, 0.2, 0.1, 0.05), 3),
+        (OF.PMJGlauberFactor([1, -1, 1], 0.5, 0.1, 1.0), M.PMJGlauberFactor([1, -1, 1], 0.5, 0.1, 1.0), 2),
+        (OF.IntegerGlauberFactor([1, -2, 1], 0.1, 0.8), M.IntegerGlauberFactor([1, -2, 1], 0.1, 0.8), 2),
+    ]
+    for a, b, q in pairs:
+        z = 3
+        for l in range(z + 1):
+            assert a.nstates(l) == b.nstates(l)
+        for xn in range(1, q + 1):
+            for x in range(1, q + 1):
+                for y in range(1, a.nstates(z) + 1):
+                    assert abs(a.prob_y(xn, x, y, z) - b.prob_y(xn, x, y, z)) < 1e-15
+                for xk in range(1, q + 1):
+                    for y in range(1, a.nstates(z - 1) + 1):
+                        assert abs(a.prob_y_partial(xn, x, xk, y, z - 1, 2) - b.prob_y_partial(xn, x, xk, y, z - 1, 2)) < 1e-15
+        import itertools
+        for xs in itertools.product(range(1, q + 1), repeat=z):
+            for xn in range(1, q + 1):
+                for x in range(1, q + 1):
+                    assert abs(a(xn, list(xs), x) - b(xn, list(xs), x)) < 1e-14
+
+
+def test_cavity_pairs_cover_recursion():
+    from mpbp_b200.factors import cavity_pairs
+    for z in range(1, 8):
+        ps = set(cavity_pairs(z))
+        if z == 1:
+            assert ps == {(1, 0)}
+            continue
+        need = {(k, 1) for k in range(1, z)} | {(z, 0)} | {(1, l) for l in range(0, z - 1)} | {(k, z - 1 - k) for k in range(1, z)}
+        assert need <= ps
+
+
+def test_graph_edge_order_matches_reference_convention():
+    import mpbp_b200 as M
+    g = M.IndexedBiDiGraph(4, [(2, 0), (0, 1), (3, 0)])
+    assert list(zip(g.src, g.dst)) == [(0, 1), (0, 2), (0, 3), (1, 0), (2, 0), (3, 0)]
+    assert list(g.rev) == [3, 4, 5, 0, 1, 2]
+    assert list(g.colptr) == [0, 3, 4, 5, 6]

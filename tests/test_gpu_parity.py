@@ -1,0 +1,182 @@
+"""Parity of the CUDA hot path (through the C-ABI) against the oracle and the reference golden vector.
+Tolerance: 1e-8 absolute on beliefs, pair beliefs and per-node Bethe free energy (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import mpbp_b200 as M
+from mpbp_b200 import _lib
+from oracle import mpbp as O, tt as OT
+from tests.common import build_pair, compare, otrunc
+from tests.test_oracle_golden import SIS_INFINITE_GOLDEN
+
+TOL = 1e-8
+
+
+def _qr(A):
+    b, m, n = A.shape
+    k = min(m, n)
+    R = np.zeros((b, k, n))
+    Ac = np.ascontiguousarray(A)
+    _lib.check(_lib.lib().mpbp_test_qr(Ac.ctypes.data_as(_lib.c_dp), b, m, n, R.ctypes.data_as(_lib.c_dp)))
+    return R
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 3), (3, 5), (40, 8), (160, 40), (257, 17), (700, 100), (1600, 400), (2048, 33), (9, 9)])
+def test_qr_r_factor(m, n):
+    rng = np.random.default_rng(m * 1000 + n)
+    A = rng.standard_normal((3, m, n))
+    A[1, :, n // 2] = A[1, :, 0] * 2.0  # exactly dependent column
+    A[2] *= np.logspace(0, -12, n)[None, :]  # badly scaled
+    R = _qr(A)
+    for b in range(3):
+        Rn = np.linalg.qr(A[b], mode="r")
+        assert np.allclose(np.tril(R[b], -1), 0)
+        scale = np.abs(Rn).max()
+        assert np.max(np.abs(np.abs(R[b]) - np.abs(Rn))) < 1e-12 * max(scale, 1) * max(m, n) ** 0.5 or \
+            np.max(np.abs(R[b].T @ R[b] - A[b].T @ A[b])) < 1e-12 * np.abs(A[b].T @ A[b]).max()
+        assert np.max(np.abs(R[b].T @ R[b] - A[b].T @ A[b])) < 1e-11 * np.abs(A[b].T @ A[b]).max()
+
+
+@pytest.mark.parametrize("p,c", [(4, 2), (80, 40), (80, 80), (33, 7), (40, 60), (135, 45)])
+def test_jacobi_singular_values(p, c):
+    rng = np.random.default_rng(p * 100 + c)
+    A = rng.standard_normal((2, c, p)) * np.logspace(0, -9, c)[None, :, None]  # batch of col-major p x c
+    A0 = A.copy()
+    sig = np.zeros((2, c))
+    order = np.zeros((2, c), dtype=np.int32)
+    _lib.check(_lib.lib().mpbp_test_jacobi(A.ctypes.data_as(_lib.c_dp), 2, p, c, sig.ctypes.data_as(_lib.c_dp), order.ctypes.data_as(_lib.c_i32p)))
+    for b in range(2):
+        Mx = A0[b].T  # p x c
+        s = np.linalg.svd(Mx, compute_uv=False)
+        k = min(p, c)
+        assert np.allclose(sig[b][:k], s[:k], rtol=1e-10, atol=1e-13 * s[0])
+        U = A[b].T[:, order[b][:k]] / sig[b][:k]
+        G = U.T @ U
+        good = sig[b][:k] > 1e-13 * s[0]
+        assert np.max(np.abs(G[np.ix_(good, good)] - np.eye(good.sum()))) < 1e-10
+        # projector onto the leading left singular vectors matches numpy's
+        Un = np.linalg.svd(Mx, full_matrices=False)[0]
+        kk = max(1, min(k, 5))
+        assert np.max(np.abs(U[:, :kk] @ U[:, :kk].T - Un[:, :kk] @ Un[:, :kk].T)) < 1e-7
+
+
+def test_sis_infinite_graph_golden_device():
+    # /root/reference/test/sis_infinite_graph.jl:3-29 through the CUDA path
+    T, k, gamma, lam, rho = 6, 3, 0.1, 0.1, 0.2
+    w = [M.SISFactor(lam, rho)] * (T + 1)
+    phi = [np.array([1 - gamma, gamma]) if t == 0 else np.ones(2) for t in range(T + 1)]
+    bp = M.mpbp_infinite_graph(k, w, 2, phi, dmax=10)
+    iters, cb = M.iterate_(bp, maxiter=200, svd_trunc=M.TruncBond(10), tol=1e-14)
+    assert iters < 200
+    b = M.beliefs(bp)[0]
+    assert np.max(np.abs(b - SIS_INFINITE_GOLDEN)) < TOL
+
+
+def _tree_case(seed, T=2):
+    rng = np.random.default_rng(seed)
+    und = [(0, 1), (1, 2), (1, 3), (3, 4)]
+    N = 5
+    h = rng.standard_normal(N)
+    kinds = [("glauber", (1.0, float(h[i]), 1.0)) for i in range(N)]
+    phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(N)]
+    for i in range(N):
+        phi[i][0] = np.array([0.75, 0.25])
+        t = int(rng.integers(1, T + 1))
+        o = np.full(2, 0.05)
+        o[rng.integers(2)] = 1.0
+        phi[i][t] = phi[i][t] * o
+    return N, und, kinds, phi
+
+
+@pytest.mark.parametrize("schedule", ["sequential", "parallel"])
+def test_glauber_small_tree_vs_oracle(schedule):
+    T = 2
+    N, und, kinds, phi = _tree_case(111, T)
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=10)
+    tr = M.TruncBondThresh(10)
+    O.iterate(bo, maxiter=6, trunc=otrunc(tr), tol=0.0, schedule=schedule)
+    M.iterate_(bd, maxiter=6, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule=schedule)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+    # exactness on a tree: Z_bp == Z_exact (reference test/glauber_small_tree.jl:63)
+    from oracle import exact
+    p, Z, logZ = exact.exact_prob(bo)
+    assert abs(-M.bethe_free_energy(bd) - logZ) < 1e-8
+
+
+@pytest.mark.parametrize("schedule", ["sequential", "parallel"])
+def test_sis_loopy_truncated_vs_oracle(schedule):
+    # graph of test/sis_heterogeneous_compare_homogeneous.jl:5-10, truncation active (TruncBond(3))
+    T = 4
+    und = [(0, 1), (0, 2), (1, 2), (2, 3), (3, 4)]
+    N = 5
+    kinds = [("sis", (0.15 + 0.02 * i, 0.12, 0.01)) for i in range(N)]
+    phi = [[np.array([0.87, 0.13]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][3] = np.array([0.2, 1.0])
+    rng = np.random.default_rng(3)
+    go = O.BiDiGraph(N, und)
+    psi = []
+    for e in range(go.ne):
+        psi.append(None)
+    for e in range(go.ne):
+        if psi[e] is None:
+            ps = [0.5 + rng.random((2, 2)) for _ in range(T + 1)]
+            psi[e] = ps
+            psi[go.rev[e]] = [p.T.copy() for p in ps]
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, psi=psi, dmax=4)
+    tr = M.TruncBond(3)
+    O.iterate(bo, maxiter=4, trunc=otrunc(tr), tol=0.0, schedule=schedule)
+    M.iterate_(bd, maxiter=4, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule=schedule)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+    for e in range(bd.E2):  # test/normalizations.jl:48-52
+        msg = bd.get_message(e)
+        l = np.ones((1, 1))
+        for a in msg:
+            l = l @ a.sum(axis=(2, 3))
+        assert abs(l[0, 0] - 1) < 1e-10
+
+
+def test_sirs_chain_vs_oracle():
+    T = 3
+    und = [(0, 1), (1, 2), (2, 3)]
+    N = 4
+    kinds = [("sirs", (0.4, 0.15, 0.2, 0.05))] * N
+    phi = [[np.array([0.7, 0.3, 0.0]) if t == 0 else np.ones(3) for t in range(T + 1)] for _ in range(N)]
+    phi[0][2] = np.array([0.1, 1.0, 0.3])
+    bo, bd = build_pair(N, und, T, kinds, [3] * N, phi, dmax=9)
+    tr = M.TruncThresh(1e-9)
+    O.iterate(bo, maxiter=5, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=5, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_glauber_degree5_star_truncated_vs_oracle():
+    # exercises nstates growth (l+1), all cavity levels of a z=5 node and a TSQR-free heavy op
+    T = 3
+    und = [(0, k) for k in range(1, 6)] + [(1, 2)]
+    N = 6
+    kinds = [("glauber", (0.4, 0.1 * (i - 2), 1.0)) for i in range(N)]
+    phi = [[np.array([0.2, 0.8]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=4)
+    tr = M.TruncBond(4)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_errors_are_loud():
+    T = 1
+    g = M.IndexedBiDiGraph(2, [(0, 1)])
+    w = [[M.SISFactor(0.1, 0.1)] * (T + 1)] * 2
+    bp = M.mpbp(g, w, [2, 2], T, dmax=2)
+    with pytest.raises(M.MPBPError):
+        M.iterate_(bp, maxiter=1, svd_trunc=M.TruncBond(5))  # exceeds dmax
+    with pytest.raises(M.MPBPError):
+        M.iterate_(bp, maxiter=1, svd_trunc=M.TruncBond(2), damp=0.5)  # not implemented -> loud
