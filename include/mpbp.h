@@ -115,12 +115,21 @@ int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, con
  * profiling is on), [4] heavy ops run, [5] edge updates. */
 int mpbp_counters(mpbp_handle h, double* out8, int reset);
 int mpbp_set_option(mpbp_handle h, const char* name, double value);
+/* device ms per kernel family since the last reset (option "profile" = 1): [0] sweep-1 QR, [1] kron_carry,
+ * [2] kron_proj, [3] gemm_m2t, [4] qr_small, [5] jacobi_project, [6] finalize, [7] belief */
+int mpbp_kernel_times(mpbp_handle h, double* out, int n, int reset);
+/* run all engine work on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream */
+int mpbp_set_stream(mpbp_handle h, void* cuda_stream);
+/* FP64 tensor-pipe (DMMA) peak of `device` in TFLOP/s, measured live (roofline denominator) */
+int mpbp_measure_fp64_peak(int device, double* tflops);
 
 /* ---- test hooks: the two numerical building blocks, callable on raw host matrices ----
  * mpbp_test_qr: `batch` row-major m x n matrices -> R factors (min(m,n) x n, row-major) of the Q-less QR.
  * mpbp_test_jacobi: `batch` column-major p x c matrices, orthogonalised in place by one-sided Jacobi;
  *   sig = column norms sorted descending, order = the matching column indices. */
 int mpbp_test_qr(const double* A, int batch, int m, int n, double* R);
+/* flat-tree DMMA QR (the sweep-1 kernel): R is n x n per matrix; H = 32 or 16; *ms = best device time of 3 launches */
+int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, double* ms);
 int mpbp_test_jacobi(double* A, int batch, int p, int c, double* sig, int32_t* order);
 
 #ifdef __cplusplus

@@ -36,7 +36,11 @@ SIGNATURES = {
     "mpbp_unpack_messages_dev": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, C.c_void_p]),
     "mpbp_counters": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
     "mpbp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "mpbp_kernel_times": (C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int]),
+    "mpbp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mpbp_measure_fp64_peak": (C.c_int, [C.c_int, c_dp]),
     "mpbp_test_qr": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, c_dp]),
+    "mpbp_test_qr_ft": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]),
     "mpbp_test_jacobi": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_i32p]),
 }
 

@@ -208,15 +208,22 @@ class MPBP:
         psi = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).ravel(order="F") for ps in self.psi for p in ps]))
         _lib.check(L.mpbp_set_psi(self._h, _p(psi, _lib.c_dp)))
 
-    def sync_factors(self):
+    def upload_phi(self, flat):
+        """upload phi from one contiguous float64 host buffer laid out [i][t][x] (e.g. pinned memory), no staging copy"""
+        flat = np.asarray(flat)
+        assert flat.dtype == np.float64 and flat.flags.c_contiguous and flat.size == int(np.sum(self.q)) * (self.T + 1)
+        _lib.check(_lib.lib().mpbp_set_phi(self._h, _p(flat, _lib.c_dp)))
+
+    def sync_factors(self, active=None):
         """tabulate the factors (host) and upload one class per distinct (factor, degree, neighbour states)."""
         L = _lib.lib()
         cache = {}
         cls = np.zeros(self.N, dtype=np.int32)
         for i in range(self.N):
             z = self.g.degree(i)
-            if z == 0:
-                raise MPBPError(f"node {i} has degree 0: isolated nodes carry no messages")
+            if active is not None and not active[i]:
+                cls[i] = -1
+                continue
             qn = np.array([self.q[0]] * z if self.infinite else [self.q[j] for j in self.g.neighbors(i)], dtype=np.int32)
             wi = self.w[i]
             if not isinstance(wi[0], RecursiveBPFactor):
@@ -270,6 +277,15 @@ class MPBP:
         out = np.zeros(8)
         _lib.check(_lib.lib().mpbp_counters(self._h, _p(out, _lib.c_dp), int(reset)))
         return dict(launches=out[0], qr_flops=out[1], qr_ms=out[3], ops=out[4], edge_updates=out[5], arena_bytes=out[6])
+
+    def kernel_times(self, reset=False):
+        out = np.zeros(9)
+        _lib.check(_lib.lib().mpbp_kernel_times(self._h, _p(out, _lib.c_dp), 9, int(reset)))
+        names = ["qr_sweep1", "kron_carry", "kron_proj", "gemm_m2t", "qr_small", "jacobi_project", "finalize", "belief", "btilde"]
+        return dict(zip(names, out.tolist()))
+
+    def set_stream(self, cuda_stream_ptr):
+        _lib.check(_lib.lib().mpbp_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
     def set_option(self, name, value):
         _lib.check(_lib.lib().mpbp_set_option(self._h, name.encode(), float(value)))

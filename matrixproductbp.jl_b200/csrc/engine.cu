@@ -93,6 +93,7 @@ struct mpbp_state {
   std::vector<int> class_of_node;
   Arena arena;
   cudaStream_t st = nullptr;
+  bool own_stream = true;
   // options
   double arena_gb = 0;       // 0 = auto
   double max_group_ops = 1e9;
@@ -100,7 +101,9 @@ struct mpbp_state {
   // counters
   double n_launch = 0, qr_ms = 0, n_ops = 0, n_edge_updates = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<int> ev_tag;
   size_t ev_used = 0;
+  double fam_ms[16] = {0};
   int max_smem = 0;
 };
 
@@ -142,16 +145,20 @@ int common_init(mpbp_state* h) {
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaStreamCreate(&h->st));
   CUDA_OK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  h->max_smem -= 2048;  // head-room for the kernels' static shared memory
   {
     const int ms = h->max_smem;
     CUDA_OK(cudaFuncSetAttribute(k_kron_carry, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_ft<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_ft<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_kron_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
-    CUDA_OK(cudaFuncSetAttribute(k_qr_small, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
-    CUDA_OK(cudaFuncSetAttribute(k_jacobi_project, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 1024));
-    CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 1024));
-    CUDA_OK(cudaFuncSetAttribute(k_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 1024));
-    CUDA_OK(cudaFuncSetAttribute(k_pair_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms - 2048));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_jacobi_project, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_pair_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
   }
   const int L = h->L;
   h->qmax = *std::max_element(h->q.begin(), h->q.end());
@@ -241,10 +248,11 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
   const int z = c.z, q = c.q, d = h->dmax, L = h->L;
   auto tt = [&](int cap, int ny) { return (size_t)L * cap * cap * ny * q * 8 + 4 * (L + 1) + 8 + 3 * 256; };
   size_t b = 0;
-  b += (size_t)z * tt(d, c.ny[1]);
+  if (z > 0) b += (size_t)z * tt(d, c.ny[1]);
   b += tt(1, c.ny[0]);
   for (int k = 1; k < z; ++k) b += tt(d, c.ny[k + 1]) + tt(d, c.ny[z - k]) + tt(d, c.ny[z - 1]);
   b += tt(d, c.ny[z]);
+  if (z == 0) return b + ((size_t)L * d * q + (size_t)d * d * q * q) * 8 + 4 * 256;
   // finalize + belief scratch
   const int qjm = h->qmax;
   size_t fin = (size_t)(L + 1) * (d * q) * (d * q) + (size_t)d * d * q * q * q * qjm + (size_t)d * d * q * q * qjm +
@@ -330,7 +338,9 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
     };
     std::vector<TTRef> dest(z);
     TTRef full;
-    if (z == 1) {
+    if (z == 0) {
+      full = init;  // cavity of an empty neighbourhood: (∅, init)
+    } else if (z == 1) {
       dest[0] = init;
       if (add_op(1, src[0], 1, init, 0, d, 1, full)) return 1;
     } else {
@@ -420,15 +430,29 @@ int upload_jobs(mpbp_state* h, const std::vector<J>& v, J** d) {
   return 0;
 }
 
-void ev_begin(mpbp_state* h) {
+enum { F_QR = 0, F_KC = 1, F_KP = 2, F_GEMM = 3, F_QRS = 4, F_JAC = 5, F_FIN = 6, F_BEL = 7, F_BT = 8, F_NFAM = 9 };
+void ev_begin(mpbp_state* h, int tag = F_QR) {
   if (!h->profile) return;
   if (h->ev_used == h->ev_pool.size()) {
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     h->ev_pool.push_back({a, b});
+    h->ev_tag.push_back(0);
   }
+  h->ev_tag[h->ev_used] = tag;
   cudaEventRecord(h->ev_pool[h->ev_used].first, h->st);
+}
+void ev_flush(mpbp_state* h) {
+  if (!h->profile || h->ev_used == 0) return;
+  cudaStreamSynchronize(h->st);
+  for (size_t k = 0; k < h->ev_used; ++k) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev_pool[k].first, h->ev_pool[k].second);
+    h->fam_ms[h->ev_tag[k]] += ms;
+    if (h->ev_tag[k] == F_QR) h->qr_ms += ms;
+  }
+  h->ev_used = 0;
 }
 void ev_end(mpbp_state* h) {
   if (!h->profile) return;
@@ -450,10 +474,8 @@ int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int 
   if (kc_smem > (size_t)h->max_smem || kp_smem > (size_t)h->max_smem)
     return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, maxNy);
   const int dXcap = d * maxX;
-  const int ccap = std::min(dXcap, maxDcap);
-  const size_t jac_fixed = (size_t)ccap + (ccap + 1) / 2 + 1;
-  size_t jac_doubles = (size_t)dXcap * ccap;
-  if ((jac_fixed + jac_doubles) * 8 > (size_t)h->max_smem - 2048) jac_doubles = ((size_t)h->max_smem - 2048) / 8 - jac_fixed;
+  const size_t jac_fixed = 3 * SUB_BMAX;
+  const size_t jac_doubles = (size_t)h->max_smem / 8 - jac_fixed;
   const size_t jac_smem = (jac_fixed + jac_doubles) * 8;
   const int mrows_cap = maxDcap * maxX;
   // number of TSQR stages for the capacity
@@ -466,20 +488,21 @@ int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int 
       if (nstages > 6) return fail("TSQR does not converge for D=%d", maxDcap);
     }
   }
+  const size_t ft32_big = ft_smem_doubles<32>(maxDcap) * 8, ft16_big = ft_smem_doubles<16>(maxDcap) * 8;
+  const size_t ft32_small = ft_smem_doubles<32>(dXcap) * 8, ft16_small = ft_smem_doubles<16>(dXcap) * 8;
+  if (ft16_big > (size_t)h->max_smem || ft16_small > (size_t)h->max_smem)
+    return fail("bond capacity %d (D=%d, d*X=%d) exceeds the shared-memory row block of the QR kernel", d, maxDcap, dXcap);
   // ---- sweep 1 (R->L) ----
   for (int t = L - 1; t >= 1; --t) {
     dim3 g1(nops, maxq, (maxDcap + KC_RC - 1) / KC_RC);
+    ev_begin(h, F_KC);
     k_kron_carry<<<g1, NT, kc_smem, st>>>(d_ops, t, L);
+    ev_end(h);
     h->n_launch++;
-    long long m = mrows_cap;
-    ev_begin(h);
-    for (int s = 0; s < nstages; ++s) {
-      const int nch = (int)((m + QR_MAX_M - 1) / QR_MAX_M);
-      dim3 g2(nops, nch);
-      k_qr_stage<<<g2, NT, qr_smem_big, st>>>(d_ops, t, s, qr_vrows_big, h->d_flops);
-      h->n_launch++;
-      m = (long long)nch * maxDcap;
-    }
+    ev_begin(h, F_QR);
+    if (ft32_big <= (size_t)h->max_smem) k_qr_ft<32><<<nops, NT, ft32_big, st>>>(d_ops, t, h->d_flops);
+    else k_qr_ft<16><<<nops, NT, ft16_big, st>>>(d_ops, t, h->d_flops);
+    h->n_launch++;
     ev_end(h);
   }
   // ---- sweep 2 (L->R) ----
@@ -487,13 +510,22 @@ int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int 
   const size_t qr_smem_small = qr_shared_doubles(qr_vrows_small) * 8;
   for (int t = 0; t < L; ++t) {
     dim3 g3(nops, maxq, maxNy);
+    ev_begin(h, F_KP);
     k_kron_proj<<<g3, NT, kp_smem, st>>>(d_ops, t);
+    ev_end(h);
     h->n_launch++;
     if (t < L - 1) {
       dim3 g4(nops, (dXcap + 31) / 32, (maxDcap + 31) / 32);
+      ev_begin(h, F_GEMM);
       k_gemm_m2t<<<g4, NT, 0, st>>>(d_ops, t);
-      k_qr_small<<<nops, NT, qr_smem_small, st>>>(d_ops, t, qr_vrows_small);
+      ev_end(h);
+      ev_begin(h, F_QRS);
+      if (ft32_small <= (size_t)h->max_smem) k_qr_small<32><<<nops, NT, ft32_small, st>>>(d_ops, t, (int)jac_doubles);
+      else k_qr_small<16><<<nops, NT, ft16_small, st>>>(d_ops, t, (int)jac_doubles);
+      ev_end(h);
+      ev_begin(h, F_JAC);
       k_jacobi_project<<<nops, NT, jac_smem, st>>>(d_ops, t, tr, d, (int)jac_doubles, h->d_err);
+      ev_end(h);
       h->n_launch += 3;
     } else {
       k_op_last<<<nops, NT, 0, st>>>(d_ops, t);
@@ -569,6 +601,7 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
       if (run_op_group(h, d_ops, nops, maxD, maxX, maxNy, maxq, tr)) return 1;
       // descriptors / scratch are reused by the next group: wait for the stream
       CUDA_OK(cudaStreamSynchronize(st));
+      ev_flush(h);
       h->n_ops += nops;
       i0 = i1;
     }
@@ -589,16 +622,21 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     }
     const size_t smem = (qrd + jac_fixed + jac_doubles) * 8;
     if (!P.fin.empty()) {
+      ev_begin(h, F_FIN);
       k_finalize<<<(unsigned)P.fin.size(), NT, smem, st>>>(d_fin, L, tr, d, vrows, (int)jac_doubles, h->d_err);
+      ev_end(h);
       h->n_launch++;
     }
     const size_t bsm = 2 * (size_t)d * qm * 8;
+    ev_begin(h, F_BEL);
     k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
+    ev_end(h);
     k_free_energy<<<(unsigned)(P.fj.size() + 127) / 128, 128, 0, st>>>(d_fj, (int)P.fj.size());
     h->n_launch += 2;
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(st));
+  ev_flush(h);
   h->n_edge_updates += (double)P.fin.size();
   return 0;
 }
@@ -717,7 +755,7 @@ int mpbp_destroy(mpbp_handle h) {
   cudaFree(h->d_logzij); cudaFree(h->d_f); cudaFree(h->d_means); cudaFree(h->d_marg_off); cudaFree(h->d_q);
   cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->arena.base);
   for (auto& e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-  cudaStreamDestroy(h->st);
+  if (h->own_stream) cudaStreamDestroy(h->st);
   delete h;
   return 0;
 }
@@ -726,14 +764,14 @@ int mpbp_add_node_class(mpbp_handle h, int z, int q, const int32_t* qn, int nt, 
                         int npairs, const int32_t* pair_d1, const int32_t* pair_d2, const double* pyy,
                         const double* w, const double* wd, const double* minit, int32_t* class_id) {
   if (!h) return fail("null handle");
-  if (z < 1) return fail("degree-0 nodes have no messages: z must be >= 1");
+  if (z < 0) return fail("z must be >= 0");
   if (nt != 1 && nt != h->L) return fail("nt must be 1 or T+1");
   CUDA_OK(cudaSetDevice(h->device));
   NodeClass c;
   c.z = z;
   c.q = q;
   c.nt = nt;
-  c.qn.assign(qn, qn + z);
+  if (z > 0) c.qn.assign(qn, qn + z);
   c.ny.assign(ny, ny + z + 1);
   for (int l = 0; l <= z; ++l)
     if (c.ny[l] < 1 || c.ny[l] > 64) return fail("nstates(w,%d)=%d out of range", l, c.ny[l]);
@@ -782,7 +820,7 @@ int mpbp_add_generic_class(mpbp_handle, int, int, const int32_t*, int, const dou
 int mpbp_set_node_classes(mpbp_handle h, const int32_t* cls) {
   if (!h) return fail("null handle");
   for (int64_t i = 0; i < h->N; ++i) {
-    if (cls[i] < 0 || cls[i] >= (int)h->classes.size()) return fail("class_of_node[%lld]=%d unknown", (long long)i, cls[i]);
+    if (cls[i] < -1 || cls[i] >= (int)h->classes.size()) return fail("class_of_node[%lld]=%d unknown", (long long)i, cls[i]);
     h->class_of_node[i] = cls[i];
   }
   return 0;
@@ -927,14 +965,7 @@ int mpbp_iterate(mpbp_handle h, int maxiter, int trunc_kind, int trunc_d, double
     done = it + 1;
     if (delta < tol) break;
   }
-  if (h->profile) {
-    for (size_t k = 0; k < h->ev_used; ++k) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, h->ev_pool[k].first, h->ev_pool[k].second);
-      h->qr_ms += ms;
-    }
-    h->ev_used = 0;
-  }
+  ev_flush(h);
   cudaFree(d_obs);
   cudaFree(d_nodes);
   if (iters) *iters = done;
@@ -1075,6 +1106,70 @@ int mpbp_counters(mpbp_handle h, double* out8, int reset) {
   return 0;
 }
 
+int mpbp_set_stream(mpbp_handle h, void* cuda_stream) {
+  if (!h) return fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  if (h->own_stream) cudaStreamDestroy(h->st);
+  h->st = (cudaStream_t)cuda_stream;
+  h->own_stream = false;
+  return 0;
+}
+
+// FP64 tensor-pipe (DMMA m8n8k4) throughput of this device, measured live: the roofline denominator of the
+// QR/GEMM kernels (MEASURED_PEAKS.json carries no FP64 figure).  Returns TFLOP/s.
+__global__ void k_peak_dmma(double* out, int iters) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = 0.0;
+  const double a = threadIdx.x * 1e-9, b = 1.0000001;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[2 * j]), "+d"(c[2 * j + 1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+int mpbp_measure_fp64_peak(int device, double* tflops) {
+  CUDA_OK(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int tpb = 256, blocks = sms * 8, iters = 20000;
+  double* out;
+  CUDA_OK(cudaMalloc((void**)&out, sizeof(double) * tpb * blocks));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(e0);
+    k_peak_dmma<<<blocks, tpb>>>(out, iters);
+    cudaEventRecord(e1);
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = 2.0 * 8 * 8 * 4 * 8 * (double)iters * blocks * (tpb / 32) / best / 1e9;
+  return 0;
+}
+
+// device ms per kernel family since the last reset (only while option "profile" = 1):
+// [0] sweep-1 QR, [1] kron_carry, [2] kron_proj, [3] gemm_m2t, [4] qr_small, [5] jacobi_project, [6] finalize, [7] belief
+int mpbp_kernel_times(mpbp_handle h, double* out, int n, int reset) {
+  if (!h || !out) return fail("null argument");
+  for (int i = 0; i < n; ++i) out[i] = i < 16 ? h->fam_ms[i] : 0.0;
+  if (reset) for (int i = 0; i < 16; ++i) h->fam_ms[i] = 0.0;
+  return 0;
+}
+
 int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   if (!h || !name) return fail("null argument");
   std::string n(name);
@@ -1108,6 +1203,51 @@ int mpbp_test_qr(const double* A, int batch, int m, int n, double* R) {
   CUDA_OK(cudaMemcpy(R, dR, sizeof(double) * batch * k * n, cudaMemcpyDeviceToHost));
   cudaFree(dA);
   cudaFree(dR);
+  return 0;
+}
+}  // extern "C"
+template <int H>
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_test_qr_ft(const double* A, int m, int n, double* R) {
+  extern __shared__ double smem[];
+  qr_ft_cta<H>(A + (size_t)blockIdx.x * m * n, m, n, n, R + (size_t)blockIdx.x * n * n, n, false, smem);
+}
+extern "C" {
+// flat-tree DMMA QR: R is n x n per matrix (rows >= min(m,n) are noise); ms = device time of the launch
+int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, double* ms) {
+  double *dA, *dR;
+  CUDA_OK(cudaMalloc((void**)&dA, sizeof(double) * (size_t)batch * m * n));
+  CUDA_OK(cudaMalloc((void**)&dR, sizeof(double) * (size_t)batch * n * n));
+  CUDA_OK(cudaMemcpy(dA, A, sizeof(double) * (size_t)batch * m * n, cudaMemcpyHostToDevice));
+  const size_t sm = (H == 32 ? ft_smem_doubles<32>(n) : ft_smem_doubles<16>(n)) * 8;
+  int maxs = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0));
+  if (sm > (size_t)maxs) return fail("test_qr_ft: n too large for H=%d", H);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    if (H == 32) {
+      CUDA_OK(cudaFuncSetAttribute(k_test_qr_ft<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_test_qr_ft<32><<<batch, NT, sm>>>(dA, m, n, dR);
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(k_test_qr_ft<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_test_qr_ft<16><<<batch, NT, sm>>>(dA, m, n, dR);
+    }
+    cudaEventRecord(e1);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventSynchronize(e1));
+    float t;
+    cudaEventElapsedTime(&t, e0, e1);
+    if (t < best) best = t;
+  }
+  if (ms) *ms = best;
+  CUDA_OK(cudaMemcpy(R, dR, sizeof(double) * (size_t)batch * n * n, cudaMemcpyDeviceToHost));
+  cudaFree(dA);
+  cudaFree(dR);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
 }
 __global__ void __launch_bounds__(NT) k_test_jacobi(double* A, int p, int c, double* sig, int* order) {

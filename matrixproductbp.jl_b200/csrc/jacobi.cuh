@@ -136,4 +136,46 @@ __device__ inline void jacobi_sort(const double* A, const int p, const int c, co
   __syncthreads();
 }
 
+// Deflation + pre-sorting: column norms of Ag (p x c, column-major, lda = p), columns at or below
+// JACOBI_ZERO x (largest norm) are dropped (they carry < 1e-15 of the matrix), the others are copied to `dst`
+// (p x c_eff, lda = p) in order of decreasing norm (a norm-sorted start converges in fewer sweeps).
+// sig / order: scratch of c entries.  Returns c_eff (>= 1 unless the matrix is exactly zero).
+__device__ inline int jacobi_compact(const double* Ag, const int p, const int c, double* dst, double* sig, int* order,
+                                     int* s_int) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int j = w; j < c; j += NW) {
+    const double* aj = Ag + (size_t)j * p;
+    double s = 0.0;
+    for (int k = lane; k < p; k += 32) s += aj[k] * aj[k];
+    s = warp_sum(s);
+    if (lane == 0) sig[j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *s_int = 0;
+  __syncthreads();
+  double mx = 0.0;
+  for (int j = 0; j < c; ++j) mx = fmax(mx, sig[j]);
+  const double thr2 = JACOBI_ZERO * JACOBI_ZERO * mx;
+  for (int j = threadIdx.x; j < c; j += NT) {
+    const double sj = sig[j];
+    if (sj > thr2) {
+      int rank = 0;
+      for (int i = 0; i < c; ++i) {
+        const double si = sig[i];
+        rank += (si > sj) || (si == sj && i < j);
+      }
+      order[rank] = j;  // every kept column outranks every dropped one
+      atomicAdd(s_int, 1);
+    }
+  }
+  __syncthreads();
+  const int ceff = *s_int;
+  for (int idx = threadIdx.x; idx < ceff * p; idx += NT) {
+    const int kk = idx / p, k = idx % p;
+    dst[idx] = Ag[k + (size_t)order[kk] * p];
+  }
+  __syncthreads();
+  return ceff;
+}
+
 }  // namespace mpbp

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "jacobi.cuh"
 #include "qr.cuh"
+#include "qr_ft.cuh"
 
 namespace mpbp {
 
@@ -175,6 +176,33 @@ __global__ void __launch_bounds__(NT) k_qr_stage(const OpDesc* ops, int t, int s
   }
 }
 
+// Sweep-1 factor of site t with the flat-tree DMMA QR: L_t = R^T of M_t ((rn*X) x Dl), r[t] = min(rows, Dl).
+template <int H>
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* ops, int t, double* flops) {
+  extern __shared__ double smem[];
+  const OpDesc& op = ops[blockIdx.x];
+  const int Dl = op.a.bonds[t] * op.b.bonds[t];
+  const int m = op.r[t + 1] * op.nyo * op.q;
+  if (flops && threadIdx.x == 0) {
+    const double mm = m, nn = Dl;
+    atomicAdd(flops, mm >= nn ? 2.0 * mm * nn * nn - (2.0 / 3.0) * nn * nn * nn : 2.0 * nn * mm * mm - (2.0 / 3.0) * mm * mm * mm);
+  }
+  double* Lt = op.Lbuf + (size_t)t * op.Lstride;
+  if (m <= Dl) {
+    // wide case: M_t^T (m x Dl) itself is a valid factor (L = A^T, L L^T = A^T A); no factorisation needed
+    __shared__ double redc[NW + 1];
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < m * Dl; idx += NT) mx = fmax(mx, fabs(op.M[idx]));
+    mx = block_max(mx, redc);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < m * Dl; idx += NT) Lt[idx] = op.M[idx] * f;
+    if (threadIdx.x == 0) op.r[t] = m;
+    return;
+  }
+  qr_ft_cta<H>(op.M, m, Dl, Dl, Lt, Dl, true, smem);
+  if (threadIdx.x == 0) op.r[t] = Dl;
+}
+
 // G_t[mt, (n1,n2), y, x] = sum_{y1,y2} Pyy sum_{m1,m2} Pc[mt,(m1,m2)] B1[m1,n1,y1,x] B2[m2,n2,y2,x]
 // grid (nops, q, nyo_max); dyn smem dcap*dcap*dcap doubles
 __global__ void __launch_bounds__(NT) k_kron_proj(const OpDesc* ops, int t) {
@@ -276,22 +304,69 @@ __global__ void __launch_bounds__(NT) k_gemm_m2t(const OpDesc* ops, int t) {
 }
 
 // if r_{t+1} > dX: R2 = R-factor of M2T (r x dX); Jacobi then runs on R2^T (dX x dX)
-__global__ void __launch_bounds__(NT) k_qr_small(const OpDesc* ops, int t, int vrows) {
+__host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles);
+template <int H>
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_small(const OpDesc* ops, int t, int jac_doubles) {
   extern __shared__ double smem[];
   const OpDesc& op = ops[blockIdx.x];
   const int dX = op.o.bonds[t] * op.nyo * op.q;
   const int rn = op.r[t + 1];
-  if (rn <= dX) return;
-  qr_r_cta(op.M2T, rn, dX, dX, op.R2, dX, true, smem, vrows);
+  if (rn <= dX || !svd_direct(dX, rn, jac_doubles)) return;
+  qr_ft_cta<H>(op.M2T, rn, dX, dX, op.R2, dX, true, smem);
+}
+
+// ---- truncated SVD of M2 (p x n, p = d~X, n = r_{t+1}) : only the leading left singular vectors are needed ----
+// small matrices : one-sided Jacobi on the (QR-reduced) matrix in shared memory ("direct");
+// large matrices : blocked subspace iteration  Z <- orth(M^T Q), Q <- orth(M Z)  with b <= 64 columns, the
+//                  tall-skinny blocks orthonormalised by one-sided Jacobi in shared memory.  Converges like
+//                  (sigma_{b+1}/sigma_k)^2 per iteration; validated against exact SVDs in DESIGN.md / tests.
+constexpr int SUB_BMAX = 64;
+constexpr int SUB_MAXIT = 40;
+__host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles) {
+  const int c = p < n ? p : n;
+  return c <= SUB_BMAX && (long long)p * c <= jac_doubles;
+}
+__device__ inline void normalize_cols(double* W, int rows, int b, const double* sig) {
+  double smax = 0.0;
+  for (int j = 0; j < b; ++j) smax = fmax(smax, sig[j]);
+  for (int j = threadIdx.x >> 5; j < b; j += NW) {
+    const double f = jacobi_inv_sigma(sig[j], smax);
+    for (int k = threadIdx.x & 31; k < rows; k += 32) W[k + (size_t)j * rows] *= f;
+  }
+  __syncthreads();
+}
+// OUT[r + rows_out*j] = sum_k MT(k, r) * W[k + kdim*j]   with M addressed as M[a + p*rr]
+//   transposed = true  : OUT = M^T W   (rows_out = n, kdim = p):  thread per rr, k = a
+//   transposed = false : OUT = M W     (rows_out = p, kdim = n):  thread per a,  k = rr
+template <bool TRANSPOSED>
+__device__ inline void sub_gemm(const double* __restrict__ M, int p, int n, const double* W, int b, double* OUT) {
+  const int rows_out = TRANSPOSED ? n : p, kdim = TRANSPOSED ? p : n;
+  for (int r = threadIdx.x; r < rows_out; r += NT) {
+    for (int j0 = 0; j0 < b; j0 += 8) {
+      double acc[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
+      const double* w = W + (size_t)j0 * kdim;
+      for (int k = 0; k < kdim; ++k) {
+        const double m = TRANSPOSED ? M[k + (size_t)p * r] : M[r + (size_t)p * k];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) acc[jj] += m * w[k + (size_t)jj * kdim];
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (j0 + jj < b) OUT[r + (size_t)rows_out * (j0 + jj)] = acc[jj];
+    }
+  }
 }
 
 // truncated SVD (left vectors) of M2 (dX x r), output site, new carry Pc_t = U^T G_t (rescaled).
-// dyn smem: jac_doubles (matrix cache) + scratch
+// dyn smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles]
 __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t, Trunc tr, int dcap, int jac_doubles,
                                                        int* err) {
   extern __shared__ double smem[];
   __shared__ int flag;
   __shared__ int s_keep;
+  __shared__ int s_done;
   __shared__ double red[NW + 1];
   const OpDesc& op = ops[blockIdx.x];
   const int br1 = op.a.bonds[t + 1], br2 = op.b.bonds[t + 1];
@@ -301,29 +376,111 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
   const int p = dt * X;
   const int rn = op.r[t + 1];
   const int c = min(p, rn);
-  double* Ag = (rn > p) ? op.R2 : op.M2T;  // column-major p x c, lda = p
-  double* sig = smem;                      // c
-  int* order = reinterpret_cast<int*>(smem + c);  // c ints
-  double* cache = smem + c + (c + 1) / 2 + 1;
-  double* A = Ag;
-  if ((long long)p * c <= jac_doubles) {
-    for (int i = threadIdx.x; i < p * c; i += NT) cache[i] = Ag[i];
-    A = cache;
+  double* sig = smem;                                   // 64
+  int* order = reinterpret_cast<int*>(smem + SUB_BMAX);  // 64 ints
+  double* sprev = smem + SUB_BMAX + SUB_BMAX / 2;        // 64
+  double* W = sprev + SUB_BMAX;                          // jac_doubles
+  double* A;
+  int ceff;
+  double nrm2_all = -1.0;
+  if (svd_direct(p, rn, jac_doubles)) {
+    double* Ag = (rn > p) ? op.R2 : op.M2T;  // column-major p x c, lda = p
+    for (int i = threadIdx.x; i < p * c; i += NT) W[i] = Ag[i];
     __syncthreads();
+    A = W;
+    ceff = c;
+    const int sweeps = jacobi_cols(A, p, ceff, p, &flag);
+    if (sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
+    jacobi_sort(A, p, ceff, p, sig, order);
+    normalize_cols(A, p, ceff, sig);
+  } else {
+    const int n = rn;
+    const double* M = op.M2T;  // column-major p x n
+    double* Qg = op.R2;        // p x b
+    double* Zg = op.M;         // n x b  (sweep-1 scratch, free during sweep 2)
+    int b = min(min(SUB_BMAX, c), jac_doubles / max(p, n));
+    b &= ~7;
+    if (b < 8 || b < min(c, (tr.kind == 1 ? dcap : tr.d))) {
+      if (threadIdx.x == 0) atomicOr(err, ERR_BOND_OVERFLOW);  // shared memory cannot hold a block wide enough
+      b = max(b, 8);
+    }
+    // ---- start block: the b largest-norm columns of M ----
+    double* nrm = W;
+    int* sel = reinterpret_cast<int*>(W + n);
+    for (int rr = threadIdx.x >> 5; rr < n; rr += NW) {
+      double s = 0.0;
+      for (int a = threadIdx.x & 31; a < p; a += 32) { const double x = M[a + (size_t)p * rr]; s += x * x; }
+      s = warp_sum(s);
+      if ((threadIdx.x & 31) == 0) nrm[rr] = s;
+    }
+    __syncthreads();
+    double fro = 0.0;
+    for (int rr = threadIdx.x; rr < n; rr += NT) fro += nrm[rr];
+    nrm2_all = block_sum1(fro, red);
+    for (int rr = threadIdx.x; rr < n; rr += NT) {
+      const double sj = nrm[rr];
+      int rank = 0;
+      for (int i = 0; i < n; ++i) rank += (nrm[i] > sj) || (nrm[i] == sj && i < rr);
+      if (rank < b) sel[rank] = rr;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < b; j += NT) order[j] = sel[j];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = M[(idx % p) + (size_t)p * order[idx / p]];
+    for (int j = threadIdx.x; j < SUB_BMAX; j += NT) sprev[j] = 0.0;
+    __syncthreads();
+    int sw = jacobi_cols(W, p, b, p, &flag);
+    jacobi_sort(W, p, b, p, sig, order);
+    normalize_cols(W, p, b, sig);
+    int extra = -1;
+    const int kchk = min(b, tr.kind == 1 ? dcap : tr.d);
+    for (int it = 0; it < SUB_MAXIT; ++it) {
+      sub_gemm<true>(M, p, n, W, b, Zg);  // Zraw = M^T Q
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < n * b; idx += NT) W[idx] = Zg[idx];
+      __syncthreads();
+      sw = max(sw, jacobi_cols(W, n, b, n, &flag));
+      jacobi_sort(W, n, b, n, sig, order);
+      normalize_cols(W, n, b, sig);
+      sub_gemm<false>(M, p, n, W, b, Qg);  // Y = M Z
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
+      __syncthreads();
+      sw = max(sw, jacobi_cols(W, p, b, p, &flag));
+      jacobi_sort(W, p, b, p, sig, order);
+      if (threadIdx.x == 0) {
+        double dmax = 0.0;
+        for (int i = 0; i < kchk; ++i) {
+          const double s = sig[order[i]];
+          dmax = fmax(dmax, fabs(s - sprev[i]));
+          sprev[i] = s;
+        }
+        if (extra < 0 && dmax <= 1e-14 * sig[order[0]]) extra = 2;
+        else if (extra > 0) extra--;
+        s_done = (extra == 0);
+      }
+      __syncthreads();
+      if (s_done) break;
+      normalize_cols(W, p, b, sig);
+    }
+    if (s_done) normalize_cols(W, p, b, sig);
+    else if (threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
+    if (sw >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
+    A = W;
+    ceff = b;
   }
-  const int sweeps = jacobi_cols(A, p, c, p, &flag);
-  if (sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
-  jacobi_sort(A, p, c, p, sig, order);
   if (threadIdx.x == 0) {
-    // sorted view for the policy
+    // truncation policy on the sorted singular values (c = number of singular values of the reference's SVD)
     double nrm2 = 0.0;
-    for (int i = 0; i < c; ++i) nrm2 += sig[i] * sig[i];
+    for (int i = 0; i < ceff; ++i) nrm2 += sig[i] * sig[i];
+    if (nrm2_all >= 0.0) nrm2 = nrm2_all;  // subspace path: Frobenius norm of the whole matrix
     int k = c;
     if (tr.kind == 1 || tr.kind == 2) {
       const double lim = tr.eps * sqrt(nrm2);
       int last = 0;
-      for (int i = 0; i < c; ++i)
+      for (int i = 0; i < ceff; ++i)
         if (sig[order[i]] > lim) last = i + 1;
+      if (last == ceff && ceff < c && tr.kind == 1) atomicOr(err, ERR_BOND_OVERFLOW);  // more values above eps than the block holds
       k = last > 0 ? last : 1;
     }
     if (tr.kind == 0 || tr.kind == 2) k = min(k, tr.d);
@@ -337,28 +494,21 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
   }
   __syncthreads();
   const int keep = s_keep;
-  // normalise the kept columns in place -> U
-  for (int kk = threadIdx.x >> 5; kk < keep; kk += NW) {
-    const int col = order[kk];
-    const double s = sig[col];
-    const double f = jacobi_inv_sigma(s, sig[order[0]]);
-    for (int k = threadIdx.x & 31; k < p; k += 32) A[k + (size_t)col * p] *= f;
-  }
-  __syncthreads();
+  const int kuse = min(keep, ceff);  // columns kuse..keep-1 of U are zero
   // output site A_t[mt, kk, yx] = U[mt + dt*yx, kk]
   double* O = op.o.data + (size_t)t * op.o.stride;
   for (int idx = threadIdx.x; idx < dt * keep * X; idx += NT) {
     const int mt = idx % dt, kk = (idx / dt) % keep, yx = idx / (dt * keep);
-    O[idx] = A[(mt + dt * yx) + (size_t)order[kk] * p];
+    O[idx] = kk < kuse ? A[(mt + dt * yx) + (size_t)order[kk] * p] : 0.0;
   }
   // carry Pc_t[kk + keep*n] = sum_a U[a,kk] G[a; n]
   double* Pn = op.Pc[t & 1];
   double mx = 0.0;
   for (int idx = threadIdx.x; idx < keep * Dr; idx += NT) {
     const int kk = idx % keep, n = idx / keep;
-    const double* u = A + (size_t)order[kk] * p;
+    const double* u = A + (size_t)order[kk < kuse ? kk : 0] * p;
     double acc = 0.0;
-    for (int yx = 0; yx < X; ++yx) {
+    for (int yx = 0; yx < (kk < kuse ? X : 0); ++yx) {
       const double* g = op.G + (size_t)dt * (n + (size_t)Dr * yx);
       const double* uu = u + dt * yx;
       for (int mt = 0; mt < dt; ++mt) acc += uu[mt] * g[mt];

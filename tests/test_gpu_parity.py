@@ -41,6 +41,24 @@ def test_qr_r_factor(m, n):
         assert np.max(np.abs(R[b].T @ R[b] - A[b].T @ A[b])) < 1e-11 * np.abs(A[b].T @ A[b]).max()
 
 
+@pytest.mark.parametrize("m,n,H", [(1, 1, 32), (5, 3, 32), (3, 5, 32), (40, 8, 32), (160, 40, 16), (257, 17, 32), (700, 100, 32),
+                                   (1600, 400, 32), (4000, 400, 32), (333, 77, 16), (64, 600, 16), (900, 450, 16)])
+def test_qr_flat_tree_dmma(m, n, H):
+    rng = np.random.default_rng(m * 1000 + n)
+    A = rng.standard_normal((3, m, n))
+    A[1, :, n // 2] = A[1, :, 0] * 2.0
+    A[2] *= np.logspace(0, -12, n)[None, :]
+    R = np.zeros((3, n, n))
+    ms = np.zeros(1)
+    Ac = np.ascontiguousarray(A)
+    _lib.check(_lib.lib().mpbp_test_qr_ft(Ac.ctypes.data_as(_lib.c_dp), 3, m, n, H, R.ctypes.data_as(_lib.c_dp), ms.ctypes.data_as(_lib.c_dp)))
+    for b in range(3):
+        # R is n x n upper triangular (for m < n up to m rows are non-negligible, not necessarily the first m)
+        assert np.allclose(np.tril(R[b], -1), 0)
+        G = A[b].T @ A[b]
+        assert np.max(np.abs(R[b].T @ R[b] - G)) < 1e-11 * np.abs(G).max()
+
+
 @pytest.mark.parametrize("p,c", [(4, 2), (80, 40), (80, 80), (33, 7), (40, 60), (135, 45)])
 def test_jacobi_singular_values(p, c):
     rng = np.random.default_rng(p * 100 + c)
@@ -167,6 +185,39 @@ def test_glauber_degree5_star_truncated_vs_oracle():
     tr = M.TruncBond(4)
     O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0)
     M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_glauber_4regular_bond10_subspace_svd_vs_oracle():
+    # D = 100, d~X up to 100 > 64: the truncating SVDs take the blocked subspace-iteration path
+    import networkx as nx
+    T, N, d = 5, 6, 10
+    G = nx.random_regular_graph(4, N, seed=3)
+    und = [(int(a), int(b)) for a, b in G.edges()]
+    kinds = [("glauber", (0.5, 0.1 + 0.03 * i, 1.0)) for i in range(N)]
+    phi = [[np.array([0.2, 0.8]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[1][3] = np.array([0.7, 0.4])
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=d)
+    tr = M.TruncBond(d)
+    O.iterate(bo, maxiter=4, trunc=otrunc(tr), tol=0.0, schedule="parallel")
+    M.iterate_(bd, maxiter=4, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule="parallel")
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_isolated_node_and_leaf_vs_oracle():
+    # degree-0 node (cavity of an empty neighbourhood) next to a 2-chain
+    T = 3
+    und = [(0, 1)]
+    N = 3
+    kinds = [("glauber", (0.3, 0.2, 1.0)), ("glauber", (0.3, -0.1, 1.0)), ("glauber", (0.3, 0.4, 1.0))]
+    phi = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][2] = np.array([0.9, 0.2])
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=4)
+    tr = M.TruncBond(4)
+    O.iterate(bo, maxiter=2, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=2, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
     eb, ef, ep = compare(bo, bd)
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
 
