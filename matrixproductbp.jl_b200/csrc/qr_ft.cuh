@@ -5,14 +5,16 @@
 //   R (n x n, upper triangular) lives in global memory and stays L2-resident (n = 400: 1.3 MB);
 //   the matrix is consumed in row blocks of H rows staged ONCE in shared memory (HBM traffic = one read of A):
 //     for each row block A_i (H x n):   [R; A_i] = Q [R'; 0]
-//       for each panel of 8 columns:
-//         warp 0  : Householder factorisation of [R_jj (8x8 upper); A_i[:, panel] (H x 8)]  -> V (H x 8), T (8x8)
-//         8 warps : for each 8-column slab c of the trailing columns, all warp-local:
-//                     W  = R_jc + V^T A_ic        (DMMA, K = H)
-//                     W' = T^T W                  (DMMA)
-//                     R_jc -= W' ;  A_ic -= V W'  (DMMA, K = 8)
-//   The per-column chain of the panel (one warp-wide reduction per column) is sequential; two CTAs per SM
-//   (two independent matrices) overlap the chain of one with the DMMA updates of the other.
+//       for each panel j of 8 columns:
+//         warp 0    : (look-ahead) applies the update of panel j to the 8 columns of panel j+1, then factors
+//                     [R_jj (8x8 upper); A_i[:, panel j+1] (H x 8)]  -> V (H x 8), T (8x8)   (double-buffered)
+//         warps 1-7 : update of panel j on the remaining 8-column slabs c, all warp-local:
+//                       W  = R_jc + V^T A_ic        (DMMA, K = H)
+//                       W' = T^T W                  (DMMA)
+//                       R_jc -= W' ;  A_ic -= V W'  (DMMA, K = 8)
+//       one __syncthreads per panel.
+//   The per-column chain of the panel (one warp-wide batched reduction per column) therefore runs concurrently
+//   with the DMMA updates; two CTAs per SM (two independent matrices) fill the remaining bubbles.
 //
 // Reflectors have the structure [e_k ; v] (the R part is a unit vector), so V^T V = I + V_A^T V_A and the
 // compact-WY factor T follows the LAPACK dlarft recurrence.
@@ -31,16 +33,193 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, 
 
 __host__ __device__ inline int ft_ld(int n) {
   const int n8 = (n + 7) & ~7;
-  return n8 + 4 + ((n8 & 8) ? 8 : 0);  // ld % 16 == 4 : conflict-free B-fragment loads
+  return n8 + 8 + ((n8 & 8) ? 8 : 0);  // ld % 16 == 8; with the XOR-4 column swizzle of rows (i>>1)&1 both the
+                                        // DMMA B-fragment loads and the 128-bit C-tile accesses are conflict-free
 }
+__device__ __forceinline__ int ft_sw(int row) { return ((row >> 1) & 1) << 2; }
 template <int H>
 __host__ __device__ inline size_t ft_smem_doubles(int n) {
-  return (size_t)H * ft_ld(n) + FT_B * (H + 4) + FT_B * FT_B + NW * 72 + 16;
+  return (size_t)H * ft_ld(n) + 2 * (FT_B * (H + 4) + FT_B * FT_B) + NW * 72 + 16;
 }
 
-// A: m x n row-major (lda), read-only.  R: n x n row-major (ldr) in global memory, fully overwritten; on return
-// rows 0..min(m,n)-1 hold the R factor (rows >= m are rounding noise when m < n and must be ignored).
-// If normalize: rows 0..min(m,n)-1 are divided by their max-abs.
+// Householder factorisation of [R_jj ; Ablk[:, j0..j0+8)] by ONE warp.  Writes V^T (A part) to Vt (8 x LDV), the
+// compact-WY T (8x8) to Tm, the new R_jj block to global R.
+template <int H>
+__device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const int j0, const int n, double* __restrict__ R,
+                                         const int ldr, double* Vt, double* Tm) {
+  constexpr int LDV = H + 4;
+  const int lane = threadIdx.x & 31;
+  double a[FT_B];
+  const bool rowok = lane < H;
+#pragma unroll
+  for (int c = 0; c < FT_B; ++c) a[c] = rowok ? Ablk[(size_t)lane * ld + ((j0 + c) ^ ft_sw(lane))] : 0.0;
+  // R_jj (8x8 upper) preloaded once: lane k holds row j0+k; rows are broadcast with shuffles
+  double rrow[FT_B];
+#pragma unroll
+  for (int c = 0; c < FT_B; ++c)
+    rrow[c] = (lane < FT_B && j0 + lane < n && j0 + c < n && c >= lane) ? R[(size_t)(j0 + lane) * ldr + j0 + c] : 0.0;
+  double T[FT_B][FT_B];
+#pragma unroll
+  for (int x = 0; x < FT_B; ++x)
+#pragma unroll
+    for (int y = 0; y < FT_B; ++y) T[x][y] = 0.0;
+#pragma unroll
+  for (int k = 0; k < FT_B; ++k) {
+    // one batched reduction: red[c] = a_k . a_c (c >= k)  and  red[l] = v_l . a_k (l < k)
+    double red[FT_B];
+    {
+      // transpose-reduce: 4+2+1+1+1 shuffles leave every lane with one complete sum, 8 more broadcast them
+      double w4[4], w2[2];
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double lo = a[k] * a[i], hi = a[k] * a[i + 4];
+        const double send = b4 ? lo : hi, keep = b4 ? hi : lo;
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double send = b3 ? w4[i] : w4[i + 2], keep = b3 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      double tsum;
+      {
+        const double send = b2 ? w2[0] : w2[1], keep = b2 ? w2[1] : w2[0];
+        tsum = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+#pragma unroll
+      for (int c = 0; c < FT_B; ++c)
+        red[c] = __shfl_sync(0xffffffffu, tsum, (((c >> 2) & 1) << 4) | (((c >> 1) & 1) << 3) | ((c & 1) << 2));
+    }
+    double rk[FT_B];
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) rk[c] = (c >= k) ? __shfl_sync(0xffffffffu, rrow[c], k) : 0.0;
+    const double alpha = rk[k], sig2 = red[k];
+    double tau = 0.0, sc = 0.0, beta = alpha;
+    if (sig2 > 0.0) {
+      const double n2 = alpha * alpha + sig2;
+      const double rs = rsqrt(n2);          // 1/||x||
+      const double nrm = n2 * rs;
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      const double u = alpha - beta;         // |u| = |alpha| + nrm, no cancellation
+      tau = alpha >= 0.0 ? u * rs : -u * rs; // (beta - alpha)/beta = -u/beta
+      sc = 1.0 / u;
+    }
+    const double v = a[k] * sc;
+    a[k] = v;
+#pragma unroll
+    for (int c = k + 1; c < FT_B; ++c) {
+      const double s = tau * (rk[c] + sc * red[c]);
+      a[c] -= s * v;
+      rk[c] -= s;
+    }
+    if (lane == k) {
+      rrow[k] = beta;
+#pragma unroll
+      for (int c = k + 1; c < FT_B; ++c) rrow[c] = rk[c];
+    }
+    // T(0:k,k) = -tau * T(0:k,0:k) * (V_A(:,0:k)^T v_k);   V_l^T v_k = sc * red[l]
+    T[k][k] = tau;
+#pragma unroll
+    for (int x = 0; x < k; ++x) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = x; l < k; ++l) acc += T[x][l] * (sc * red[l]);
+      T[x][k] = -tau * acc;
+    }
+  }
+  if (lane < FT_B && j0 + lane < n) {
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c)
+      if (c >= lane && j0 + c < n) R[(size_t)(j0 + lane) * ldr + j0 + c] = rrow[c];
+  }
+  if (rowok) {
+#pragma unroll
+    for (int k = 0; k < FT_B; ++k) Vt[k * LDV + lane] = a[k];
+  }
+  // T is replicated in every lane: lane x writes row x
+#pragma unroll
+  for (int x = 0; x < FT_B; ++x)
+    if (lane == x) {
+#pragma unroll
+      for (int y = 0; y < FT_B; ++y) Tm[x * FT_B + y] = T[x][y];
+    }
+}
+
+// fragments of V^T / T of the current panel held in registers by an updating warp
+template <int H>
+struct FtFrags {
+  double va1[H / 4], va2[H / 8][2], at[2];
+  __device__ __forceinline__ void load(const double* Vt, const double* Tm) {
+    constexpr int LDV = H + 4;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+#pragma unroll
+    for (int s = 0; s < H / 4; ++s) va1[s] = Vt[g * LDV + 4 * s + q4];
+#pragma unroll
+    for (int r = 0; r < H / 8; ++r)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) va2[r][s] = Vt[(4 * s + q4) * LDV + 8 * r + g];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) at[s] = Tm[(4 * s + q4) * FT_B + g];  // T^T[g][4s+q4]
+  }
+};
+
+// update of one 8-column slab at column c0 by panel rows j0..j0+7 (warp-local).  (r0, r1) = R_jc fragment.
+template <int H>
+__device__ __forceinline__ void ft_update_slab(double* Ablk, const int ld, const int c0, const FtFrags<H>& f, double* Ws,
+                                               double* rp, const bool ok0, const bool ok1, const double r0, const double r1) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+  const int cc = c0 + 2 * q4;
+  double w0 = 0.0, w1 = 0.0, x0 = 0.0, x1 = 0.0;
+  // B fragments of GEMM1: rows 4s+q4 (swizzle bit = q4 bit 1), column c0+g
+  const double* bp = Ablk + (size_t)q4 * ld + ((c0 + g) ^ (((q4 >> 1) & 1) << 2));
+  double bf[H / 4];
+#pragma unroll
+  for (int s = 0; s < H / 4; ++s) bf[s] = bp[(size_t)(4 * s) * ld];
+  // C tiles of GEMM2 (rows 8r+g, columns cc, cc+1), loaded early so that their latency hides behind GEMM1
+  double2* cp[H / 8];
+  double2 cv[H / 8];
+#pragma unroll
+  for (int r = 0; r < H / 8; ++r) {
+    cp[r] = reinterpret_cast<double2*>(Ablk + (size_t)(8 * r + g) * ld + (cc ^ ft_sw(g)));
+    cv[r] = *cp[r];
+  }
+#pragma unroll
+  for (int s = 0; s < H / 4; s += 2) {
+    dmma884(w0, w1, f.va1[s], bf[s]);
+    dmma884(x0, x1, f.va1[s + 1], bf[s + 1]);
+  }
+  w0 += x0 + r0;
+  w1 += x1 + r1;
+  // per-warp 8x8 scratch, ld 8, column swizzle 4*((row>>1)&1): C-layout 128-bit stores and B-layout loads conflict-free
+  double2* wst = reinterpret_cast<double2*>(Ws + g * 8 + ((2 * q4) ^ ft_sw(g)));
+  const double* wld0 = Ws + q4 * 8 + (g ^ ft_sw(q4));
+  const double* wld1 = Ws + (4 + q4) * 8 + (g ^ ft_sw(4 + q4));
+  __syncwarp();
+  *wst = make_double2(w0, w1);
+  __syncwarp();
+  double p0 = 0.0, p1 = 0.0;
+  dmma884(p0, p1, f.at[0], *wld0);
+  dmma884(p0, p1, f.at[1], *wld1);
+  if (ok0) rp[0] = r0 - p0;
+  if (ok1) rp[1] = r1 - p1;
+  __syncwarp();
+  *wst = make_double2(-p0, -p1);
+  __syncwarp();
+  const double b0 = *wld0, b1 = *wld1;
+#pragma unroll
+  for (int r = 0; r < H / 8; ++r) dmma884(cv[r].x, cv[r].y, f.va2[r][0], b0);
+#pragma unroll
+  for (int r = 0; r < H / 8; ++r) dmma884(cv[r].x, cv[r].y, f.va2[r][1], b1);
+#pragma unroll
+  for (int r = 0; r < H / 8; ++r) *cp[r] = cv[r];
+}
+
+// A: m x n row-major (lda), read-only.  R: n x n row-major (ldr) in global memory, fully overwritten with the
+// upper-triangular factor (R^T R = A^T A).  For m < n use the matrix itself as the factor instead (callers do).
+// If normalize: R is divided by its max-abs.
 template <int H>
 __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n, const int lda, double* __restrict__ R,
                           const int ldr, const bool normalize, double* smem) {
@@ -48,181 +227,81 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
   const int n8 = (n + 7) & ~7;
   const int ld = ft_ld(n);
   constexpr int LDV = H + 4;
-  double* Ablk = smem;                        // H x ld
-  double* Vt = Ablk + (size_t)H * ld;         // 8 x LDV   (V^T, A-part of the reflectors)
-  double* Tm = Vt + FT_B * LDV;               // 8 x 8
-  double* Ws = Tm + FT_B * FT_B + warp * 72;  // per-warp 8x8 scratch (ld 9)
-  // zero R
+  constexpr int VT_SZ = FT_B * LDV + FT_B * FT_B;
+  double* Ablk = smem;                       // H x ld
+  double* VT0 = Ablk + (size_t)H * ld;       // 2 x (V^T 8 x LDV, T 8x8)
+  double* Ws = VT0 + 2 * VT_SZ + warp * 72;  // per-warp 8x8 scratch (ld 9)
   for (int idx = tid; idx < n * n; idx += NT) R[(size_t)(idx / n) * ldr + (idx % n)] = 0.0;
   const int g = lane >> 2, q4 = lane & 3;  // DMMA fragment coordinates
+  const int npanel = n8 / FT_B;
   for (int row0 = 0; row0 < m; row0 += H) {
     __syncthreads();
     // ---- stage the row block (zero padded) ----
     for (int idx = tid; idx < H * n8; idx += NT) {
       const int i = idx / n8, c = idx % n8;
       const int gi = row0 + i;
-      Ablk[(size_t)i * ld + c] = (gi < m && c < n) ? A[(size_t)gi * lda + c] : 0.0;
+      Ablk[(size_t)i * ld + (c ^ ft_sw(i))] = (gi < m && c < n) ? A[(size_t)gi * lda + c] : 0.0;
     }
     __syncthreads();
-    for (int j0 = 0; j0 < n; j0 += FT_B) {
-      // trailing-slab geometry; the first R fragment of every warp is prefetched across the panel phase
-      const int nslab = (n8 - j0 - FT_B) / FT_B;
+    if (warp == 0) ft_panel<H>(Ablk, ld, 0, n, R, ldr, VT0, VT0 + FT_B * LDV);
+    for (int jp = 0; jp < npanel; ++jp) {
+      const int j0 = jp * FT_B;
+      double* Vt = VT0 + (jp & 1) * VT_SZ;
+      double* Tm = Vt + FT_B * LDV;
+      double* Vtn = VT0 + ((jp + 1) & 1) * VT_SZ;
+      __syncthreads();  // V/T of panel jp ready; update of panel jp-1 complete
+      const int nslab = npanel - jp - 1;
+      if (nslab <= 0) continue;
       const int rr = j0 + g;
-      double nr0 = 0.0, nr1 = 0.0;
-      {
-        const int cc = j0 + FT_B + warp * FT_B + 2 * q4;
-        if (warp < nslab && rr < n) {
+      FtFrags<H> f;
+      f.load(Vt, Tm);
+      if (warp == 0) {
+        // look-ahead: bring the next panel's columns up to date, then factor it while warps 1-7 update the rest
+        const int c0 = j0 + FT_B, cc = c0 + 2 * q4;
+        const bool ok0 = (rr < n) && (cc < n), ok1 = (rr < n) && (cc + 1 < n);
+        double* rp = R + (size_t)rr * ldr + cc;
+        const double r0 = ok0 ? rp[0] : 0.0, r1 = ok1 ? rp[1] : 0.0;
+        ft_update_slab<H>(Ablk, ld, c0, f, Ws, rp, ok0, ok1, r0, r1);
+        __syncwarp();
+        ft_panel<H>(Ablk, ld, c0, n, R, ldr, Vtn, Vtn + FT_B * LDV);
+      } else {
+        int sl = warp;  // slabs 1 .. nslab-1 over warps 1..7
+        double nr0 = 0.0, nr1 = 0.0;
+        if (sl < nslab && rr < n) {
+          const int cc = j0 + FT_B + sl * FT_B + 2 * q4;
           if (cc < n) nr0 = R[(size_t)rr * ldr + cc];
           if (cc + 1 < n) nr1 = R[(size_t)rr * ldr + cc + 1];
         }
-      }
-      // ================= panel factorisation (warp 0) =================
-      if (warp == 0) {
-        double a[FT_B];
-        const bool rowok = lane < H;
-#pragma unroll
-        for (int c = 0; c < FT_B; ++c) a[c] = rowok ? Ablk[(size_t)lane * ld + j0 + c] : 0.0;
-        // R_jj (8x8 upper) preloaded once: lane k holds row j0+k; rows are broadcast with shuffles
-        double rrow[FT_B];
-#pragma unroll
-        for (int c = 0; c < FT_B; ++c)
-          rrow[c] = (lane < FT_B && j0 + lane < n && j0 + c < n && c >= lane) ? R[(size_t)(j0 + lane) * ldr + j0 + c] : 0.0;
-        double T[FT_B][FT_B];
-#pragma unroll
-        for (int x = 0; x < FT_B; ++x)
-#pragma unroll
-          for (int y = 0; y < FT_B; ++y) T[x][y] = 0.0;
-#pragma unroll
-        for (int k = 0; k < FT_B; ++k) {
-          // one batched reduction: g[c] = a_k . a_c (c >= k)  and  z[l] = v_l . a_k (l < k)
-          double red[FT_B];
-#pragma unroll
-          for (int c = 0; c < FT_B; ++c) red[c] = a[k] * a[c];
-#pragma unroll
-          for (int c = 0; c < FT_B; ++c) red[c] = warp_sum(red[c]);
-          double rk[FT_B];
-#pragma unroll
-          for (int c = 0; c < FT_B; ++c) rk[c] = __shfl_sync(0xffffffffu, rrow[c], k);
-          const double alpha = rk[k], sig2 = red[k];
-          double tau = 0.0, sc = 0.0, beta = alpha;
-          if (sig2 > 0.0) {
-            const double nrm = sqrt(alpha * alpha + sig2);
-            beta = alpha >= 0.0 ? -nrm : nrm;
-            tau = (beta - alpha) / beta;
-            sc = 1.0 / (alpha - beta);
-          }
-          const double v = a[k] * sc;
-          a[k] = v;
-#pragma unroll
-          for (int c = k + 1; c < FT_B; ++c) {
-            const double s = tau * (rk[c] + sc * red[c]);
-            a[c] -= s * v;
-            rk[c] -= s;
-          }
-          if (lane == k) {
-            rrow[k] = beta;
-#pragma unroll
-            for (int c = k + 1; c < FT_B; ++c) rrow[c] = rk[c];
-          }
-          // T(0:k,k) = -tau * T(0:k,0:k) * (V_A(:,0:k)^T v_k);   z[l] = sc * (v_l . a_k) = sc * red[l]
-          T[k][k] = tau;
-#pragma unroll
-          for (int x = 0; x < k; ++x) {
-            double acc = 0.0;
-#pragma unroll
-            for (int l = x; l < k; ++l) acc += T[x][l] * (sc * red[l]);
-            T[x][k] = -tau * acc;
-          }
-        }
-        if (lane < FT_B && j0 + lane < n) {
-#pragma unroll
-          for (int c = 0; c < FT_B; ++c)
-            if (c >= lane && j0 + c < n) R[(size_t)(j0 + lane) * ldr + j0 + c] = rrow[c];
-        }
-        if (rowok) {
-#pragma unroll
-          for (int k = 0; k < FT_B; ++k) Vt[k * LDV + lane] = a[k];
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int x = 0; x < FT_B; ++x)
-#pragma unroll
-            for (int y = 0; y < FT_B; ++y) Tm[x * FT_B + y] = T[x][y];
-        }
-        __threadfence_block();
-      }
-      __syncthreads();
-      // ================= trailing update (all warps, one 8-column slab at a time) =================
-      if (nslab > 0) {
-        double va1[H / 4], va2[H / 8][2], at[2];
-#pragma unroll
-        for (int s = 0; s < H / 4; ++s) va1[s] = Vt[g * LDV + 4 * s + q4];
-#pragma unroll
-        for (int r = 0; r < H / 8; ++r)
-#pragma unroll
-          for (int s = 0; s < 2; ++s) va2[r][s] = Vt[(4 * s + q4) * LDV + 8 * r + g];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) at[s] = Tm[(4 * s + q4) * FT_B + g];  // T^T[g][4s+q4]
-        for (int sl = warp; sl < nslab; sl += NW) {
-          const int c0 = j0 + FT_B + sl * FT_B;
-          // R_jc fragment (C layout): rows j0+g, cols c0 + 2*q4 + {0,1}; the next slab's fragment is prefetched
-          const int cc = c0 + 2 * q4;
+        for (; sl < nslab; sl += NW - 1) {
+          const int c0 = j0 + FT_B + sl * FT_B, cc = c0 + 2 * q4;
           const bool ok0 = (rr < n) && (cc < n), ok1 = (rr < n) && (cc + 1 < n);
           double* rp = R + (size_t)rr * ldr + cc;
           const double r0 = nr0, r1 = nr1;
           {
-            const int ccn = cc + NW * FT_B;
-            nr0 = (sl + NW < nslab && rr < n && ccn < n) ? rp[NW * FT_B] : 0.0;
-            nr1 = (sl + NW < nslab && rr < n && ccn + 1 < n) ? rp[NW * FT_B + 1] : 0.0;
+            const int ccn = cc + (NW - 1) * FT_B;
+            const bool more = (sl + NW - 1 < nslab) && (rr < n);
+            nr0 = (more && ccn < n) ? rp[(NW - 1) * FT_B] : 0.0;
+            nr1 = (more && ccn + 1 < n) ? rp[(NW - 1) * FT_B + 1] : 0.0;
           }
-          double w0 = 0.0, w1 = 0.0;
-          const double* bp = Ablk + (size_t)q4 * ld + c0 + g;
-#pragma unroll
-          for (int s = 0; s < H / 4; ++s) dmma884(w0, w1, va1[s], bp[(size_t)(4 * s) * ld]);
-          w0 += r0;
-          w1 += r1;
-          __syncwarp();
-          Ws[g * 9 + 2 * q4] = w0;
-          Ws[g * 9 + 2 * q4 + 1] = w1;
-          __syncwarp();
-          double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-          for (int s = 0; s < 2; ++s) dmma884(p0, p1, at[s], Ws[(4 * s + q4) * 9 + g]);
-          if (ok0) rp[0] = r0 - p0;
-          if (ok1) rp[1] = r1 - p1;
-          __syncwarp();
-          Ws[g * 9 + 2 * q4] = -p0;
-          Ws[g * 9 + 2 * q4 + 1] = -p1;
-          __syncwarp();
-          const double b0 = Ws[q4 * 9 + g], b1 = Ws[(4 + q4) * 9 + g];
-#pragma unroll
-          for (int r = 0; r < H / 8; ++r) {
-            double2* cp = reinterpret_cast<double2*>(Ablk + (size_t)(8 * r + g) * ld + cc);
-            double2 cv = *cp;
-            dmma884(cv.x, cv.y, va2[r][0], b0);
-            dmma884(cv.x, cv.y, va2[r][1], b1);
-            *cp = cv;
-          }
+          ft_update_slab<H>(Ablk, ld, c0, f, Ws, rp, ok0, ok1, r0, r1);
         }
       }
-      __syncthreads();
     }
   }
   __syncthreads();
   if (normalize) {
     __shared__ double redn[NW + 1];
-    const int k = min(m, n);
     double mx = 0.0;
-    for (int idx = tid; idx < k * n; idx += NT) {
+    for (int idx = tid; idx < n * n; idx += NT) {
       const int i = idx / n, c = idx % n;
       if (c >= i) mx = fmax(mx, fabs(R[(size_t)i * ldr + c]));
     }
     mx = block_max(mx, redn);
     if (mx > 0.0 && isfinite(mx)) {
-      const double f = 1.0 / mx;
-      for (int idx = tid; idx < k * n; idx += NT) {
+      const double fs = 1.0 / mx;
+      for (int idx = tid; idx < n * n; idx += NT) {
         const int i = idx / n, c = idx % n;
-        if (c >= i) R[(size_t)i * ldr + c] *= f;
+        if (c >= i) R[(size_t)i * ldr + c] *= fs;
       }
     }
   }
