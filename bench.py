@@ -262,7 +262,7 @@ def run_gpu(args, rank, world, local_rank):
                                   unit="TFLOP/s", frac=qr_tf / float(peak[0]) if peak[0] > 0 else None, traffic=traffic,
                                   peak_source="FP64 DMMA (mma.sync m8n8k4 f64) measured live by mpbp_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 entry",
                                   algorithmic_flops=ctr["qr_flops"], kernel_ms=ctr["qr_ms"], share_of_step=ctr["qr_ms"] / ms if ms > 0 else None,
-                                  heavy_ops=int(ctr["ops"]), kernel_family_ms={k: round(v, 1) for k, v in fam.items()}))
+                                  heavy_ops=int(ctr["ops"]), subspace_svd=dict(calls=int(ctr["svd_calls"]), iters=int(ctr["svd_iters"]), unconverged=int(ctr["svd_unconverged"])), kernel_family_ms={k: round(v, 1) for k, v in fam.items()}))
         if world == 1 and not args.no_cpu:
             degs = np.array([g.degree(i) for i in range(g.N)])
             line["cpu_baseline"], _ = cpu_baseline(T, d, degs)

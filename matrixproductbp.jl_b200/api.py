@@ -276,7 +276,7 @@ class MPBP:
     def counters(self, reset=False):
         out = np.zeros(8)
         _lib.check(_lib.lib().mpbp_counters(self._h, _p(out, _lib.c_dp), int(reset)))
-        return dict(launches=out[0], qr_flops=out[1], qr_ms=out[3], ops=out[4], edge_updates=out[5], arena_bytes=out[6])
+        return dict(launches=out[0], qr_flops=out[1], qr_ms=out[3], ops=out[4], edge_updates=out[5], svd_calls=out[2], svd_iters=out[6], svd_unconverged=out[7])
 
     def kernel_times(self, reset=False):
         out = np.zeros(9)

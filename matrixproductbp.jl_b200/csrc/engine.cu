@@ -32,6 +32,8 @@ static int fail(const char* fmt, ...) {
 
 namespace {
 
+constexpr int QR_NSPLIT_MAX = 8;
+
 struct NodeClass {
   int z = 0, q = 0, nt = 1;
   bool generic = false;
@@ -96,6 +98,7 @@ struct mpbp_state {
   bool own_stream = true;
   // options
   double arena_gb = 0;       // 0 = auto
+  double qr_fill = 296;      // CTAs that fill the GPU for the QR kernel (2 per SM); fewer ops per launch -> TSQR split
   double max_group_ops = 1e9;
   int profile = 0;
   // counters
@@ -152,6 +155,8 @@ int common_init(mpbp_state* h) {
     CUDA_OK(cudaFuncSetAttribute(k_qr_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_ft_merge<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_ft_merge<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_kron_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
@@ -197,7 +202,7 @@ int common_init(mpbp_state* h) {
   if (upload(&h->d_logzij, zeros.data(), nzij)) return 1;
   if (upload(&h->d_f, zeros.data(), h->N)) return 1;
   if (upload(&h->d_delta, zeros.data(), 1)) return 1;
-  if (upload(&h->d_flops, zeros.data(), 1)) return 1;
+  if (upload(&h->d_flops, zeros.data(), 8)) return 1;
   int zero = 0;
   if (upload(&h->d_err, &zero, 1)) return 1;
   if (alloc_msg_store(h, h->msg[0])) return 1;
@@ -267,7 +272,8 @@ size_t op_scratch_bytes(const mpbp_state* h, int capA, int capB, int X) {
   const size_t D = (size_t)capA * capB, d = h->dmax, L = h->L;
   const size_t mrows = D * X;
   const size_t nch = (mrows + QR_MAX_M - 1) / QR_MAX_M;
-  size_t dbl = L * D * D + mrows * D + (nch > 1 ? nch * D * D : 0) + d * D * X + D * d * X + (d * X) * (d * X) + 2 * d * D;
+  (void)nch;
+  size_t dbl = L * D * D + mrows * D + QR_NSPLIT_MAX * D * D + d * D * X + D * d * X + (d * X) * (d * X) + 2 * d * D;
   return dbl * 8 + 4 * (L + 1) + 10 * 256;
 }
 
@@ -492,6 +498,8 @@ int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int 
   const size_t ft32_small = ft_smem_doubles<32>(dXcap) * 8, ft16_small = ft_smem_doubles<16>(dXcap) * 8;
   if (ft16_big > (size_t)h->max_smem || ft16_small > (size_t)h->max_smem)
     return fail("bond capacity %d (D=%d, d*X=%d) exceeds the shared-memory row block of the QR kernel", d, maxDcap, dXcap);
+  // under-filled launches: split tall matrices over several CTAs (TSQR)
+  const int nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(nops, 1))));
   // ---- sweep 1 (R->L) ----
   for (int t = L - 1; t >= 1; --t) {
     dim3 g1(nops, maxq, (maxDcap + KC_RC - 1) / KC_RC);
@@ -500,9 +508,17 @@ int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int 
     ev_end(h);
     h->n_launch++;
     ev_begin(h, F_QR);
-    if (ft32_big <= (size_t)h->max_smem) k_qr_ft<32><<<nops, NT, ft32_big, st>>>(d_ops, t, h->d_flops);
-    else k_qr_ft<16><<<nops, NT, ft16_big, st>>>(d_ops, t, h->d_flops);
-    h->n_launch++;
+    {
+      dim3 gq(nops, nsplit);
+      if (ft32_big <= (size_t)h->max_smem) k_qr_ft<32><<<gq, NT, ft32_big, st>>>(d_ops, t, nsplit, h->d_flops);
+      else k_qr_ft<16><<<gq, NT, ft16_big, st>>>(d_ops, t, nsplit, h->d_flops);
+      h->n_launch++;
+      if (nsplit > 1) {
+        if (ft32_big <= (size_t)h->max_smem) k_qr_ft_merge<32><<<nops, NT, ft32_big, st>>>(d_ops, t, nsplit, h->d_flops);
+        else k_qr_ft_merge<16><<<nops, NT, ft16_big, st>>>(d_ops, t, nsplit, h->d_flops);
+        h->n_launch++;
+      }
+    }
     ev_end(h);
   }
   // ---- sweep 2 (L->R) ----
@@ -524,7 +540,7 @@ int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int 
       else k_qr_small<16><<<nops, NT, ft16_small, st>>>(d_ops, t, (int)jac_doubles);
       ev_end(h);
       ev_begin(h, F_JAC);
-      k_jacobi_project<<<nops, NT, jac_smem, st>>>(d_ops, t, tr, d, (int)jac_doubles, h->d_err);
+      k_jacobi_project<<<nops, NT, jac_smem, st>>>(d_ops, t, tr, d, (int)jac_doubles, h->d_err, h->d_flops + 1);
       ev_end(h);
       h->n_launch += 3;
     } else {
@@ -582,13 +598,14 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         op.Lstride = (long long)(D * D);
         op.Lbuf = (double*)h->arena.take(8 * (size_t)L * D * D);
         op.M = (double*)h->arena.take(8 * mrows * D);
-        op.Ms = nch > 1 ? (double*)h->arena.take(8 * nch * D * D) : nullptr;
+        (void)nch;
+        op.Ms = (double*)h->arena.take(8 * (size_t)QR_NSPLIT_MAX * D * D);
         op.G = (double*)h->arena.take(8 * (size_t)d * D * X);
         op.M2T = (double*)h->arena.take(8 * D * (size_t)d * X);
         op.R2 = (double*)h->arena.take(8 * (size_t)(d * X) * (d * X));
         op.Pc[0] = (double*)h->arena.take(8 * (size_t)d * D);
         op.Pc[1] = (double*)h->arena.take(8 * (size_t)d * D);
-        if (!op.r || !op.Lbuf || !op.M || (nch > 1 && !op.Ms) || !op.G || !op.M2T || !op.R2 || !op.Pc[0] || !op.Pc[1]) break;
+        if (!op.r || !op.Lbuf || !op.M || !op.Ms || !op.G || !op.M2T || !op.R2 || !op.Pc[0] || !op.Pc[1]) break;
         maxD = std::max(maxD, (int)D);
         maxX = std::max(maxX, X);
         maxNy = std::max(maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
@@ -1089,19 +1106,20 @@ int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, con
 int mpbp_counters(mpbp_handle h, double* out8, int reset) {
   if (!h || !out8) return fail("null argument");
   CUDA_OK(cudaSetDevice(h->device));
-  double fl = 0;
-  CUDA_OK(cudaMemcpy(&fl, h->d_flops, sizeof(double), cudaMemcpyDeviceToHost));
+  double fl5[6] = {0, 0, 0, 0, 0, 0};
+  CUDA_OK(cudaMemcpy(fl5, h->d_flops, 6 * sizeof(double), cudaMemcpyDeviceToHost));
+  const double fl = fl5[0];
   out8[0] = h->n_launch;
   out8[1] = fl;
-  out8[2] = 0;
+  out8[2] = fl5[1];  // subspace-SVD calls
   out8[3] = h->qr_ms;
   out8[4] = h->n_ops;
   out8[5] = h->n_edge_updates;
-  out8[6] = (double)h->arena.cap;
-  out8[7] = 0;
+  out8[6] = fl5[2];  // subspace-SVD iterations (sum)
+  out8[7] = fl5[5];  // subspace-SVD calls that hit the iteration cap
   if (reset) {
     h->n_launch = h->qr_ms = h->n_ops = h->n_edge_updates = 0;
-    CUDA_OK(cudaMemset(h->d_flops, 0, sizeof(double)));
+    CUDA_OK(cudaMemset(h->d_flops, 0, 8 * sizeof(double)));
   }
   return 0;
 }
@@ -1178,6 +1196,7 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
     h->arena_gb = value;
   } else if (n == "max_group_ops") h->max_group_ops = value;
   else if (n == "profile") h->profile = (int)value;
+  else if (n == "qr_fill") h->qr_fill = value;
   else return fail("unknown option %s", name);
   return 0;
 }

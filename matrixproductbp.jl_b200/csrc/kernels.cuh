@@ -177,18 +177,27 @@ __global__ void __launch_bounds__(NT) k_qr_stage(const OpDesc* ops, int t, int s
 }
 
 // Sweep-1 factor of site t with the flat-tree DMMA QR: L_t = R^T of M_t ((rn*X) x Dl), r[t] = min(rows, Dl).
+// When a launch holds few matrices (nsplit > 1) tall matrices are split TSQR-style over several CTAs: row chunks
+// are factored independently into op.Ms (n x n each) and k_qr_ft_merge factors the stack.
+__device__ __forceinline__ void ft_split(int m, int n, int nsplit, int& nch, int& ch_rows) {
+  const int n8 = (n + 7) & ~7;
+  nch = min(nsplit, m / (2 * n8));  // a chunk must stay well above n rows to be worth a second stage
+  if (nch < 2) { nch = 1; ch_rows = m; return; }
+  ch_rows = (((m + nch - 1) / nch) + 31) & ~31;
+  nch = (m + ch_rows - 1) / ch_rows;
+}
+__device__ __forceinline__ double qr_flops(double mm, double nn) {
+  return mm >= nn ? 2.0 * mm * nn * nn - (2.0 / 3.0) * nn * nn * nn : 2.0 * nn * mm * mm - (2.0 / 3.0) * mm * mm * mm;
+}
 template <int H>
-__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* ops, int t, double* flops) {
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* ops, int t, int nsplit, double* flops) {
   extern __shared__ double smem[];
   const OpDesc& op = ops[blockIdx.x];
   const int Dl = op.a.bonds[t] * op.b.bonds[t];
   const int m = op.r[t + 1] * op.nyo * op.q;
-  if (flops && threadIdx.x == 0) {
-    const double mm = m, nn = Dl;
-    atomicAdd(flops, mm >= nn ? 2.0 * mm * nn * nn - (2.0 / 3.0) * nn * nn * nn : 2.0 * nn * mm * mm - (2.0 / 3.0) * mm * mm * mm);
-  }
   double* Lt = op.Lbuf + (size_t)t * op.Lstride;
   if (m <= Dl) {
+    if (blockIdx.y > 0) return;
     // wide case: M_t^T (m x Dl) itself is a valid factor (L = A^T, L L^T = A^T A); no factorisation needed
     __shared__ double redc[NW + 1];
     double mx = 0.0;
@@ -199,7 +208,31 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* o
     if (threadIdx.x == 0) op.r[t] = m;
     return;
   }
-  qr_ft_cta<H>(op.M, m, Dl, Dl, Lt, Dl, true, smem);
+  int nch, ch_rows;
+  ft_split(m, Dl, nsplit, nch, ch_rows);
+  const int ch = blockIdx.y;
+  if (ch >= nch) return;
+  const int row0 = ch * ch_rows, rows = min(ch_rows, m - row0);
+  if (flops && threadIdx.x == 0) atomicAdd(flops, qr_flops(rows, Dl));
+  if (nch == 1) {
+    qr_ft_cta<H>(op.M, m, Dl, Dl, Lt, Dl, true, smem);
+    if (threadIdx.x == 0) op.r[t] = Dl;
+  } else {
+    qr_ft_cta<H>(op.M + (size_t)row0 * Dl, rows, Dl, Dl, op.Ms + (size_t)ch * Dl * Dl, Dl, false, smem);
+  }
+}
+template <int H>
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft_merge(const OpDesc* ops, int t, int nsplit, double* flops) {
+  extern __shared__ double smem[];
+  const OpDesc& op = ops[blockIdx.x];
+  const int Dl = op.a.bonds[t] * op.b.bonds[t];
+  const int m = op.r[t + 1] * op.nyo * op.q;
+  if (m <= Dl) return;
+  int nch, ch_rows;
+  ft_split(m, Dl, nsplit, nch, ch_rows);
+  if (nch == 1) return;
+  if (flops && threadIdx.x == 0) atomicAdd(flops, qr_flops((double)nch * Dl, Dl));
+  qr_ft_cta<H>(op.Ms, nch * Dl, Dl, Dl, op.Lbuf + (size_t)t * op.Lstride, Dl, true, smem);
   if (threadIdx.x == 0) op.r[t] = Dl;
 }
 
@@ -326,35 +359,44 @@ __host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles) {
   const int c = p < n ? p : n;
   return c <= SUB_BMAX && (long long)p * c <= jac_doubles;
 }
-__device__ inline void normalize_cols(double* W, int rows, int b, const double* sig) {
+__device__ inline void normalize_cols(double* W, int rows, int b, const double* sig, const bool squared = false) {
   double smax = 0.0;
   for (int j = 0; j < b; ++j) smax = fmax(smax, sig[j]);
+  if (squared) smax *= smax;
   for (int j = threadIdx.x >> 5; j < b; j += NW) {
-    const double f = jacobi_inv_sigma(sig[j], smax);
+    const double f = jacobi_inv_sigma(squared ? sig[j] * sig[j] : sig[j], smax);
     for (int k = threadIdx.x & 31; k < rows; k += 32) W[k + (size_t)j * rows] *= f;
   }
   __syncthreads();
 }
 // OUT[r + rows_out*j] = sum_k MT(k, r) * W[k + kdim*j]   with M addressed as M[a + p*rr]
-//   transposed = true  : OUT = M^T W   (rows_out = n, kdim = p):  thread per rr, k = a
-//   transposed = false : OUT = M W     (rows_out = p, kdim = n):  thread per a,  k = rr
-template <bool TRANSPOSED>
-__device__ inline void sub_gemm(const double* __restrict__ M, int p, int n, const double* W, int b, double* OUT) {
-  const int rows_out = TRANSPOSED ? n : p, kdim = TRANSPOSED ? p : n;
+// OUT (rows_out x b) = Mx W  where Mx (rows_out x kdim) is column-major with leading dimension rows_out
+// (thread per output row: consecutive lanes read consecutive addresses of Mx), W (kdim x b) in shared memory.
+__device__ inline void sub_gemm(const double* __restrict__ Mx, int rows_out, int kdim, const double* W, int b, double* OUT) {
   for (int r = threadIdx.x; r < rows_out; r += NT) {
-    for (int j0 = 0; j0 < b; j0 += 8) {
-      double acc[8];
+    for (int j0 = 0; j0 < b; j0 += 16) {
+      double acc[16];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
+      for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
       const double* w = W + (size_t)j0 * kdim;
-      for (int k = 0; k < kdim; ++k) {
-        const double m = TRANSPOSED ? M[k + (size_t)p * r] : M[r + (size_t)p * k];
+      const int nj = min(16, b - j0);
+      if (nj == 16) {
+#pragma unroll 2
+        for (int k = 0; k < kdim; ++k) {
+          const double m = Mx[r + (size_t)rows_out * k];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) acc[jj] += m * w[k + (size_t)jj * kdim];
+          for (int jj = 0; jj < 16; ++jj) acc[jj] += m * w[k + (size_t)jj * kdim];
+        }
+      } else {
+        for (int k = 0; k < kdim; ++k) {
+          const double m = Mx[r + (size_t)rows_out * k];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) acc[jj] += m * w[k + (size_t)jj * kdim];
+        }
       }
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj)
-        if (j0 + jj < b) OUT[r + (size_t)rows_out * (j0 + jj)] = acc[jj];
+      for (int jj = 0; jj < 16; ++jj)
+        if (jj < nj) OUT[r + (size_t)rows_out * (j0 + jj)] = acc[jj];
     }
   }
 }
@@ -362,7 +404,7 @@ __device__ inline void sub_gemm(const double* __restrict__ M, int p, int n, cons
 // truncated SVD (left vectors) of M2 (dX x r), output site, new carry Pc_t = U^T G_t (rescaled).
 // dyn smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles]
 __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t, Trunc tr, int dcap, int jac_doubles,
-                                                       int* err) {
+                                                       int* err, double* stats) {
   extern __shared__ double smem[];
   __shared__ int flag;
   __shared__ int s_keep;
@@ -398,6 +440,8 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
     const double* M = op.M2T;  // column-major p x n
     double* Qg = op.R2;        // p x b
     double* Zg = op.M;         // n x b  (sweep-1 scratch, free during sweep 2)
+    double* Mt = op.M + 32768; // n x p  transposed copy of M so that both products read coalesced
+    for (int idx = threadIdx.x; idx < p * n; idx += NT) Mt[(idx / p) + (size_t)n * (idx % p)] = M[idx];
     int b = min(min(SUB_BMAX, c), jac_doubles / max(p, n));
     b &= ~7;
     if (b < 8 || b < min(c, (tr.kind == 1 ? dcap : tr.d))) {
@@ -434,37 +478,67 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
     normalize_cols(W, p, b, sig);
     int extra = -1;
     const int kchk = min(b, tr.kind == 1 ? dcap : tr.d);
+    int nit = 0;
     for (int it = 0; it < SUB_MAXIT; ++it) {
-      sub_gemm<true>(M, p, n, W, b, Zg);  // Zraw = M^T Q
+      // one application of M M^T per iteration, ONE orthonormalisation: the kept singular values span only a few
+      // orders of magnitude, so the squared spectrum of the block stays far inside FP64 range
+      sub_gemm(Mt, n, p, W, b, Zg);  // Z = M^T Q   (n x b, not orthonormalised)
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < n * b; idx += NT) W[idx] = Zg[idx];
+      __syncthreads();
+      sub_gemm(M, p, n, W, b, Qg);  // Y = M Z
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
+      __syncthreads();
+      sw = max(sw, jacobi_cols(W, p, b, p, &flag));
+      jacobi_sort(W, p, b, p, sig, order);
+      for (int j = threadIdx.x; j < b; j += NT) sig[j] = sqrt(sig[j]);  // singular values of M (Y ~ U Sigma^2)
+      __syncthreads();
+      ++nit;
+      if (threadIdx.x == 0) {
+        // Ritz values of the squared iteration carry a noise floor eps*sigma_1^2/sigma_i: tolerate it here, the
+        // final un-squared refinement below restores the small directions
+        const double s1 = sig[order[0]];
+        bool conv = true;
+        for (int i = 0; i < kchk; ++i) {
+          const double s = sig[order[i]];
+          const double tol_i = 1e-13 * s1 + 8e-16 * s1 * s1 / fmax(s, 1e-300);
+          conv = conv && (fabs(s - sprev[i]) <= tol_i);
+          sprev[i] = s;
+        }
+        if (extra < 0 && conv) extra = 1;
+        else if (extra > 0) extra--;
+        s_done = (extra == 0);
+      }
+      __syncthreads();
+      normalize_cols(W, p, b, sig, true);
+      if (s_done) break;
+    }
+    const bool converged = s_done;
+    {
+      // final un-squared Rayleigh-Ritz refinement: Z = orth(M^T Q), Y = M Z, SVD(Y) -> U, sigma
+      sub_gemm(Mt, n, p, W, b, Zg);
       __syncthreads();
       for (int idx = threadIdx.x; idx < n * b; idx += NT) W[idx] = Zg[idx];
       __syncthreads();
       sw = max(sw, jacobi_cols(W, n, b, n, &flag));
       jacobi_sort(W, n, b, n, sig, order);
       normalize_cols(W, n, b, sig);
-      sub_gemm<false>(M, p, n, W, b, Qg);  // Y = M Z
+      sub_gemm(M, p, n, W, b, Qg);
       __syncthreads();
       for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
       __syncthreads();
       sw = max(sw, jacobi_cols(W, p, b, p, &flag));
       jacobi_sort(W, p, b, p, sig, order);
-      if (threadIdx.x == 0) {
-        double dmax = 0.0;
-        for (int i = 0; i < kchk; ++i) {
-          const double s = sig[order[i]];
-          dmax = fmax(dmax, fabs(s - sprev[i]));
-          sprev[i] = s;
-        }
-        if (extra < 0 && dmax <= 1e-14 * sig[order[0]]) extra = 2;
-        else if (extra > 0) extra--;
-        s_done = (extra == 0);
-      }
-      __syncthreads();
-      if (s_done) break;
       normalize_cols(W, p, b, sig);
     }
-    if (s_done) normalize_cols(W, p, b, sig);
-    else if (threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
+    if (stats && threadIdx.x == 0) {
+      atomicAdd(stats + 0, 1.0);
+      atomicAdd(stats + 1, (double)nit);
+      atomicAdd(stats + 2, (double)b);
+      atomicAdd(stats + 3, (double)sw);
+      if (!converged) atomicAdd(stats + 4, 1.0);  // hit SUB_MAXIT: result is the best available (reported, not fatal)
+    }
     if (sw >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
     A = W;
     ceff = b;
