@@ -277,7 +277,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nodes-per-gpu", type=int, default=int(os.environ.get("MPBP_BENCH_NODES", 128)))
+    ap.add_argument("--nodes-per-gpu", type=int, default=int(os.environ.get("MPBP_BENCH_NODES", 384)))
     ap.add_argument("--T", type=int, default=50)
     ap.add_argument("--d", type=int, default=20)
     ap.add_argument("--arena-gb", type=float, default=0.0)

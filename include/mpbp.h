@@ -130,6 +130,10 @@ int mpbp_measure_fp64_peak(int device, double* tflops);
 int mpbp_test_qr(const double* A, int batch, int m, int n, double* R);
 /* flat-tree DMMA QR (the sweep-1 kernel): R is n x n per matrix; H = 32 or 16; *ms = best device time of 3 launches */
 int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, double* ms);
+/* leading-d left singular vectors of `batch` column-major p x n matrices through the op-truncation SVD core (direct
+ * Jacobi or blocked subspace iteration, chosen as in the engine).  U: [batch][p x d], S: [batch][d]; stats5 =
+ * {subspace calls, iterations, sum of block sizes, sum of max sweeps, calls that hit the iteration cap}. */
+int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, double* S, double* stats5, double* ms);
 int mpbp_test_jacobi(double* A, int batch, int p, int c, double* sig, int32_t* order);
 
 #ifdef __cplusplus

@@ -41,6 +41,7 @@ SIGNATURES = {
     "mpbp_measure_fp64_peak": (C.c_int, [C.c_int, c_dp]),
     "mpbp_test_qr": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, c_dp]),
     "mpbp_test_qr_ft": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]),
+    "mpbp_test_svd": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     "mpbp_test_jacobi": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_i32p]),
 }
 

@@ -577,6 +577,20 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
   const size_t persistent = h->arena.used;
   for (size_t lev = 1; lev < P.levels.size(); ++lev) {
     auto& ops = P.levels[lev];
+    {
+      // longest-processing-time first: CTAs are dispatched in blockIdx order, so the heaviest matrices
+      // (largest D*X) start first and the light ones fill the tail of the launch
+      std::vector<size_t> idx(ops.size());
+      for (size_t k = 0; k < idx.size(); ++k) idx[k] = k;
+      auto cost = [&](size_t k) { return (double)P.capA[lev][k] * P.capB[lev][k] * ops[k].nyo * ops[k].q; };
+      std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+      std::vector<OpDesc> o2(ops.size());
+      std::vector<int> a2(ops.size()), b2(ops.size());
+      for (size_t k = 0; k < idx.size(); ++k) { o2[k] = ops[idx[k]]; a2[k] = P.capA[lev][idx[k]]; b2[k] = P.capB[lev][idx[k]]; }
+      ops.swap(o2);
+      P.capA[lev].swap(a2);
+      P.capB[lev].swap(b2);
+    }
     size_t i0 = 0;
     while (i0 < ops.size()) {
       h->arena.used = persistent;
@@ -1267,6 +1281,79 @@ int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, 
   cudaFree(dR);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  return 0;
+}
+__global__ void __launch_bounds__(NT) k_test_svd(const double* M, int p, int n, Trunc tr, int jac_doubles, double* scratch,
+                                                 size_t scratch_per, double* U, double* S, int* err, double* stats) {
+  extern __shared__ double smem[];
+  __shared__ int flag, s_done;
+  __shared__ double red[NW + 1];
+  const double* Mb = M + (size_t)blockIdx.x * p * n;
+  double* sc = scratch + (size_t)blockIdx.x * scratch_per;
+  double* R2 = sc;                       // p*p (direct, n > p) or p*64
+  double* Zg = R2 + (size_t)p * max(p, 64);
+  double* Mt = Zg + (size_t)n * 64;
+  double* Mcopy = Mt + (size_t)p * n;    // n*p row-major copy for the QR pre-reduction (destroyed)
+  if (n > p && svd_direct(p, n, jac_doubles)) {
+    for (int i = threadIdx.x; i < p * n; i += NT) Mcopy[i] = Mb[i];
+    __syncthreads();
+    qr_ft_cta<16>(Mcopy, n, p, p, R2, p, false, smem);  // M^T (n x p row-major == M col-major) -> R (p x p)
+  }
+  const SvdLeft sv = svd_left_cta(Mb, R2, R2, Zg, Mt, p, n, tr, tr.d, jac_doubles, smem, &flag, &s_done, red, err, stats);
+  const double* sig = smem;
+  const int* order = reinterpret_cast<const int*>(smem + SUB_BMAX);
+  const int keep = min(tr.d, sv.ceff);
+  for (int idx = threadIdx.x; idx < p * tr.d; idx += NT) {
+    const int a = idx % p, kk = idx / p;
+    U[(size_t)blockIdx.x * p * tr.d + idx] = kk < keep ? sv.A[a + (size_t)order[kk] * p] : 0.0;
+  }
+  for (int kk = threadIdx.x; kk < tr.d; kk += NT) S[(size_t)blockIdx.x * tr.d + kk] = kk < keep ? sig[order[kk]] : 0.0;
+}
+// leading-d left singular vectors of `batch` column-major p x n matrices through the op-truncation SVD core
+// (direct Jacobi or blocked subspace iteration, chosen as in the engine).  U: [batch][p x d], S: [batch][d].
+// stats[0..4] = subspace calls, iterations, block sizes (sum), max sweeps (sum), unconverged.  *ms = best of 3.
+int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, double* S, double* stats5, double* ms) {
+  int maxs = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0));
+  maxs -= 2048;
+  const size_t jac_fixed = 3 * SUB_BMAX, jac_doubles = (size_t)maxs / 8 - jac_fixed;
+  CUDA_OK(cudaFuncSetAttribute(k_test_svd, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+  const size_t per = (size_t)p * std::max(p, 64) + (size_t)n * 64 + 2 * (size_t)p * n + 64;
+  double *dM, *dU, *dS, *dscr, *dst;
+  int* derr;
+  CUDA_OK(cudaMalloc((void**)&dM, sizeof(double) * (size_t)batch * p * n));
+  CUDA_OK(cudaMalloc((void**)&dU, sizeof(double) * (size_t)batch * p * d));
+  CUDA_OK(cudaMalloc((void**)&dS, sizeof(double) * (size_t)batch * d));
+  CUDA_OK(cudaMalloc((void**)&dscr, sizeof(double) * per * batch));
+  CUDA_OK(cudaMalloc((void**)&dst, sizeof(double) * 8));
+  CUDA_OK(cudaMalloc((void**)&derr, sizeof(int)));
+  CUDA_OK(cudaMemset(derr, 0, sizeof(int)));
+  CUDA_OK(cudaMemcpy(dM, M, sizeof(double) * (size_t)batch * p * n, cudaMemcpyHostToDevice));
+  Trunc tr{0, d, 0.0};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CUDA_OK(cudaMemset(dst, 0, sizeof(double) * 8));
+    cudaEventRecord(e0);
+    k_test_svd<<<batch, NT, (size_t)maxs>>>(dM, p, n, tr, (int)jac_doubles, dscr, per, dU, dS, derr, dst);
+    cudaEventRecord(e1);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventSynchronize(e1));
+    float t;
+    cudaEventElapsedTime(&t, e0, e1);
+    best = std::min(best, t);
+  }
+  if (ms) *ms = best;
+  int herr = 0;
+  CUDA_OK(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(U, dU, sizeof(double) * (size_t)batch * p * d, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(S, dS, sizeof(double) * (size_t)batch * d, cudaMemcpyDeviceToHost));
+  if (stats5) CUDA_OK(cudaMemcpy(stats5, dst, sizeof(double) * 5, cudaMemcpyDeviceToHost));
+  cudaFree(dM); cudaFree(dU); cudaFree(dS); cudaFree(dscr); cudaFree(dst); cudaFree(derr);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (herr) return fail("test_svd: device error flags 0x%x", herr);
   return 0;
 }
 __global__ void __launch_bounds__(NT) k_test_jacobi(double* A, int p, int c, double* sig, int* order) {

@@ -23,11 +23,83 @@ constexpr double JACOBI_ZERO = 1e-15;
 __device__ __forceinline__ double jacobi_inv_sigma(double s, double smax) {
   return (s > 2.0 * JACOBI_ZERO * smax && s > 0.0) ? 1.0 / s : 0.0;
 }
+// G lanes cooperate on one column pair (G = 8, 16 or 32): 32/G pairs run concurrently per warp, which is what the
+// latency-bound pair step needs (a b = 64 block has 32 pairs per round = one pass over 8 warps at G = 8).
+template <int G>
+__device__ inline int jacobi_cols_g(double* A, const int p, const int c, const int lda, int* flag, const double thr2) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int GPW = 32 / G;                 // groups per warp
+  const int grp = w * GPW + lane / G, lg = lane % G;
+  const int ngrp = NW * GPW;
+  const int ce = c + (c & 1);
+  const double tol = 2.0 * JACOBI_EPS * sqrt((double)max(p, 64));
+  const double tol2 = tol * tol;
+  int sweep = 0;
+  for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = 0;
+    __syncthreads();
+    for (int round = 0; round < ce - 1; ++round) {
+      for (int pr0 = 0; pr0 < ce / 2; pr0 += ngrp) {
+        const int pr = pr0 + grp;
+        int i = 0, j = 0;
+        bool act = pr < ce / 2;
+        if (act) {
+          if (pr == 0) {
+            i = ce - 1;
+            j = round;
+          } else {
+            i = (round + pr) % (ce - 1);
+            j = (round - pr + (ce - 1)) % (ce - 1);
+          }
+          act = (i < c) && (j < c);
+          if (i > j) {
+            const int t = i;
+            i = j;
+            j = t;
+          }
+        }
+        double* ai = A + (size_t)i * lda;
+        double* aj = A + (size_t)j * lda;
+        double a = 0.0, b = 0.0, g = 0.0;
+        if (act) {
+          for (int k = lg; k < p; k += G) {
+            const double x = ai[k], y = aj[k];
+            a += x * x;
+            b += y * y;
+            g += x * y;
+          }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+          g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        // rotate when |g| > tol*sqrt(a*b) (sqrt-free test) and neither column is numerically zero
+        if (act && g * g > tol2 * a * b && a > thr2 && b > thr2 && a * b > 0.0) {
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+          for (int k = lg; k < p; k += G) {
+            const double x = ai[k], y = aj[k];
+            ai[k] = cs * x - sn * y;
+            aj[k] = sn * x + cs * y;
+          }
+          if (lg == 0) *flag = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (*flag == 0) break;
+  }
+  __syncthreads();
+  return sweep;
+}
+
 __device__ inline int jacobi_cols(double* A, const int p, const int c, const int lda, int* flag) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (c < 2) return 0;
-  const int ce = c + (c & 1);
-  const double tol = 2.0 * JACOBI_EPS * sqrt((double)max(p, 64));
   __shared__ double s_scale[NW];
   {
     double mx = 0.0;
@@ -44,69 +116,13 @@ __device__ inline int jacobi_cols(double* A, const int p, const int c, const int
 #pragma unroll
   for (int ww = 0; ww < NW; ++ww) scale2 = fmax(scale2, s_scale[ww]);
   const double thr2 = JACOBI_ZERO * JACOBI_ZERO * scale2;
-  int sweep = 0;
-  for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
-    __syncthreads();
-    if (threadIdx.x == 0) *flag = 0;
-    __syncthreads();
-    for (int round = 0; round < ce - 1; ++round) {
-      for (int pr = w; pr < ce / 2; pr += NW) {
-        int i, j;
-        if (pr == 0) {
-          i = ce - 1;
-          j = round;
-        } else {
-          i = (round + pr) % (ce - 1);
-          j = (round - pr + (ce - 1)) % (ce - 1);
-        }
-        if (i >= c || j >= c) continue;
-        if (i > j) {
-          const int t = i;
-          i = j;
-          j = t;
-        }
-        double* ai = A + (size_t)i * lda;
-        double* aj = A + (size_t)j * lda;
-        double a = 0.0, b = 0.0, g = 0.0;
-        for (int k = lane; k < p; k += 32) {
-          const double x = ai[k], y = aj[k];
-          a += x * x;
-          b += y * y;
-          g += x * y;
-        }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        g = warp_sum(g);
-        const double lim = tol * sqrt(a) * sqrt(b);
-        if (fabs(g) > lim && lim > 0.0 && a > thr2 && b > thr2) {
-          const double zeta = (b - a) / (2.0 * g);
-          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-          for (int k = lane; k < p; k += 32) {
-            const double x = ai[k], y = aj[k];
-            ai[k] = cs * x - sn * y;
-            aj[k] = sn * x + cs * y;
-          }
-          if (lane == 0) *flag = 1;
-        }
-      }
-      __syncthreads();
-    }
-    if (*flag == 0) break;
-  }
-  __syncthreads();
+  const int npair = (c + 1) / 2;
+  int sweep;
+  if (npair > 2 * NW && p >= 16) sweep = jacobi_cols_g<8>(A, p, c, lda, flag, thr2);
+  else if (npair > NW && p >= 32) sweep = jacobi_cols_g<16>(A, p, c, lda, flag, thr2);
+  else sweep = jacobi_cols_g<32>(A, p, c, lda, flag, thr2);
   if (sweep >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) {
-    // diagnostics: worst remaining pair
-    double worst = 0.0; int wi = -1, wj = -1; bool nan = false;
-    for (int i = 0; i < c; ++i)
-      for (int j = i + 1; j < c; ++j) {
-        double a = 0, b = 0, g = 0;
-        for (int k = 0; k < p; ++k) { const double x = A[k + (size_t)i * lda], y = A[k + (size_t)j * lda]; a += x * x; b += y * y; g += x * y; }
-        if (!(g == g)) nan = true;
-        const double r = (a > 0 && b > 0) ? fabs(g) / (sqrt(a) * sqrt(b)) : 0.0;
-        if (r > worst) { worst = r; wi = i; wj = j; }
-      }
-    printf("[mpbp] jacobi not converged: p=%d c=%d worst |cos|=%.3e at (%d,%d) nan=%d tol=%.2e\n", p, c, worst, wi, wj, (int)nan, tol);
+    printf("[mpbp] jacobi not converged: p=%d c=%d\n", p, c);
   }
   return sweep;
 }

@@ -380,19 +380,29 @@ __device__ inline void sub_gemm(const double* __restrict__ Mx, int rows_out, int
       for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
       const double* w = W + (size_t)j0 * kdim;
       const int nj = min(16, b - j0);
-      if (nj == 16) {
-#pragma unroll 2
-        for (int k = 0; k < kdim; ++k) {
-          const double m = Mx[r + (size_t)rows_out * k];
+      // the Mx loads come from L2: keep 8 of them in flight per thread
+      int k = 0;
+      for (; k + 8 <= kdim; k += 8) {
+        double m8[8];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) acc[jj] += m * w[k + (size_t)jj * kdim];
-        }
-      } else {
-        for (int k = 0; k < kdim; ++k) {
-          const double m = Mx[r + (size_t)rows_out * k];
+        for (int u = 0; u < 8; ++u) m8[u] = Mx[r + (size_t)rows_out * (k + u)];
+        if (nj == 16) {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) acc[jj] += m * w[k + (size_t)jj * kdim];
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) acc[jj] += m8[u] * w[k + u + (size_t)jj * kdim];
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) acc[jj] += m8[u] * w[k + u + (size_t)jj * kdim];
         }
+      }
+      for (; k < kdim; ++k) {
+        const double m = Mx[r + (size_t)rows_out * k];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+          if (jj < nj) acc[jj] += m * w[k + (size_t)jj * kdim];
       }
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj)
@@ -401,22 +411,21 @@ __device__ inline void sub_gemm(const double* __restrict__ Mx, int rows_out, int
   }
 }
 
-// truncated SVD (left vectors) of M2 (dX x r), output site, new carry Pc_t = U^T G_t (rescaled).
-// dyn smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles]
-__global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t, Trunc tr, int dcap, int jac_doubles,
-                                                       int* err, double* stats) {
-  extern __shared__ double smem[];
-  __shared__ int flag;
-  __shared__ int s_keep;
-  __shared__ int s_done;
-  __shared__ double red[NW + 1];
-  const OpDesc& op = ops[blockIdx.x];
-  const int br1 = op.a.bonds[t + 1], br2 = op.b.bonds[t + 1];
-  const int Dr = br1 * br2;
-  const int dt = op.o.bonds[t];
-  const int X = op.nyo * op.q;
-  const int p = dt * X;
-  const int rn = op.r[t + 1];
+// Leading left singular vectors of M (p x n column-major at Mcm; when n > p and the direct path applies, R2 must
+// hold the Q-less QR factor of M^T as produced by k_qr_small).  On return (all threads): columns of A (p x ceff,
+// lda = p, in shared memory) are orthonormal left singular vectors, sig[col] their singular values, order[] sorts
+// them descending; nrm2_all = ||M||_F^2 when known (subspace path) else -1.
+// smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles].  Scratch (global): Qg >= p*64, Zg >= n*64, Mt >= p*n.
+struct SvdLeft {
+  double* A;
+  int ceff;
+  double nrm2_all;
+};
+__device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, double* Qg, double* Zg, double* Mt, const int p,
+                                       const int rn, const Trunc tr, const int dcap, const int jac_doubles, double* smem,
+                                       int* flagp, int* s_donep, double* red, int* err, double* stats) {
+  int& flag = *flagp;
+  int& s_done = *s_donep;
   const int c = min(p, rn);
   double* sig = smem;                                   // 64
   int* order = reinterpret_cast<int*>(smem + SUB_BMAX);  // 64 ints
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
   int ceff;
   double nrm2_all = -1.0;
   if (svd_direct(p, rn, jac_doubles)) {
-    double* Ag = (rn > p) ? op.R2 : op.M2T;  // column-major p x c, lda = p
+    const double* Ag = (rn > p) ? R2 : Mcm;  // column-major p x c, lda = p
     for (int i = threadIdx.x; i < p * c; i += NT) W[i] = Ag[i];
     __syncthreads();
     A = W;
@@ -437,10 +446,7 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
     normalize_cols(A, p, ceff, sig);
   } else {
     const int n = rn;
-    const double* M = op.M2T;  // column-major p x n
-    double* Qg = op.R2;        // p x b
-    double* Zg = op.M;         // n x b  (sweep-1 scratch, free during sweep 2)
-    double* Mt = op.M + 32768; // n x p  transposed copy of M so that both products read coalesced
+    const double* M = Mcm;  // column-major p x n
     for (int idx = threadIdx.x; idx < p * n; idx += NT) Mt[(idx / p) + (size_t)n * (idx % p)] = M[idx];
     int b = min(min(SUB_BMAX, c), jac_doubles / max(p, n));
     b &= ~7;
@@ -543,6 +549,37 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
     A = W;
     ceff = b;
   }
+  SvdLeft out;
+  out.A = A;
+  out.ceff = ceff;
+  out.nrm2_all = nrm2_all;
+  return out;
+}
+
+// truncated SVD (left vectors) of M2 (dX x r), output site, new carry Pc_t = U^T G_t (rescaled).
+// dyn smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles]
+__global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t, Trunc tr, int dcap, int jac_doubles,
+                                                       int* err, double* stats) {
+  extern __shared__ double smem[];
+  __shared__ int flag;
+  __shared__ int s_keep;
+  __shared__ int s_done;
+  __shared__ double red[NW + 1];
+  const OpDesc& op = ops[blockIdx.x];
+  const int br1 = op.a.bonds[t + 1], br2 = op.b.bonds[t + 1];
+  const int Dr = br1 * br2;
+  const int dt = op.o.bonds[t];
+  const int X = op.nyo * op.q;
+  const int p = dt * X;
+  const int rn = op.r[t + 1];
+  const int c = min(p, rn);
+  double* sig = smem;
+  int* order = reinterpret_cast<int*>(smem + SUB_BMAX);
+  const SvdLeft sv = svd_left_cta(op.M2T, op.R2, op.R2, op.M, op.M + 32768, p, rn, tr, dcap, jac_doubles, smem, &flag, &s_done, red,
+                                  err, stats);
+  double* A = sv.A;
+  const int ceff = sv.ceff;
+  const double nrm2_all = sv.nrm2_all;
   if (threadIdx.x == 0) {
     // truncation policy on the sorted singular values (c = number of singular values of the reference's SVD)
     double nrm2 = 0.0;

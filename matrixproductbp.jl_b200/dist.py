@@ -34,13 +34,14 @@ class LocalProblem:
         keep = mine[und[:, 0]] | mine[und[:, 1]]
         lund = und[keep]
         owned = np.nonzero(mine)[0]
-        halo = np.setdiff1d(np.unique(lund), owned)
-        self.nodes = np.concatenate([owned, halo])  # local -> global
+        # local ids preserve the global order, so every node sees its neighbours in the same order as in the
+        # single-process run (the order of the truncated cavity products, hence the results, depend on it)
+        self.nodes = np.union1d(owned, np.unique(lund))  # local -> global, ascending
         self.n_owned = len(owned)
         self.g2l = -np.ones(N, dtype=np.int64)
         self.g2l[self.nodes] = np.arange(len(self.nodes))
         self.local_und = [(int(self.g2l[a]), int(self.g2l[b])) for a, b in lund]
-        self.owned_local = np.arange(self.n_owned, dtype=np.int64)
+        self.owned_local = self.g2l[owned].astype(np.int64)
 
     def build_exchange(self, lsrc, ldst, world):
         """lsrc/ldst: local directed edge arrays (local node ids, reference edge order).

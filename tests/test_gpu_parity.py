@@ -59,6 +59,32 @@ def test_qr_flat_tree_dmma(m, n, H):
         assert np.max(np.abs(R[b].T @ R[b] - G)) < 1e-11 * np.abs(G).max()
 
 
+@pytest.mark.parametrize("p,n,d,decay", [(200, 400, 20, 0.85), (440, 400, 20, 0.9), (80, 400, 20, 0.7), (100, 100, 10, 0.8),
+                                          (60, 30, 10, 0.5), (640, 400, 20, 0.93)])
+def test_truncation_svd_core_vs_numpy(p, n, d, decay):
+    """the op-truncation SVD (direct Jacobi / blocked subspace iteration) against LAPACK: what matters is the
+    rank-d projection P M, weighted by the singular values"""
+    rng = np.random.default_rng(p + n)
+    batch, c = 2, min(p, n)
+    Ms = []
+    for b in range(batch):
+        Uq, _ = np.linalg.qr(rng.standard_normal((p, c)))
+        Vq, _ = np.linalg.qr(rng.standard_normal((n, c)))
+        s = decay ** np.arange(c) * (1 + 0.3 * rng.random(c))
+        Ms.append((Uq * s) @ Vq.T)
+    Mall = np.ascontiguousarray(np.stack([m.T for m in Ms]))  # column-major p x n == row-major n x p
+    U = np.zeros((batch, d, p)); S = np.zeros((batch, d)); st = np.zeros(5); ms = np.zeros(1)
+    _lib.check(_lib.lib().mpbp_test_svd(Mall.ctypes.data_as(_lib.c_dp), batch, p, n, d, U.ctypes.data_as(_lib.c_dp),
+                                        S.ctypes.data_as(_lib.c_dp), st.ctypes.data_as(_lib.c_dp), ms.ctypes.data_as(_lib.c_dp)))
+    for b in range(batch):
+        Un, sn, _ = np.linalg.svd(Ms[b], full_matrices=False)
+        Ud = U[b].T  # p x d
+        assert np.allclose(S[b], sn[:d], rtol=1e-9, atol=1e-13 * sn[0])
+        assert np.max(np.abs(Ud.T @ Ud - np.eye(d))) < 1e-10
+        err = np.linalg.norm(Un[:, :d] @ (Un[:, :d].T @ Ms[b]) - Ud @ (Ud.T @ Ms[b])) / sn[0]
+        assert err < 1e-11, (err, st)
+
+
 @pytest.mark.parametrize("p,c", [(4, 2), (80, 40), (80, 80), (33, 7), (40, 60), (135, 45)])
 def test_jacobi_singular_values(p, c):
     rng = np.random.default_rng(p * 100 + c)
@@ -220,6 +246,28 @@ def test_isolated_node_and_leaf_vs_oracle():
     M.iterate_(bd, maxiter=2, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
     eb, ef, ep = compare(bo, bd)
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_pack_unpack_roundtrip():
+    # multi-GPU plumbing: device-side pack/unpack of message slots must round-trip bit-exactly
+    import torch
+    T = 3
+    und = [(0, 1), (1, 2), (0, 2)]
+    kinds = [("sis", (0.2, 0.1, 0.0))] * 3
+    phi = [[np.array([0.8, 0.2]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(3)]
+    bo, bd = build_pair(3, und, T, kinds, [2] * 3, phi, dmax=4)
+    M.iterate_(bd, maxiter=2, svd_trunc=M.TruncBond(3), tol=0.0, shuffle_nodes=False)
+    before = [bd.get_message(e) for e in range(bd.E2)]
+    sb = int(_lib.lib().mpbp_message_slot_bytes(bd._h))
+    edges = np.arange(bd.E2, dtype=np.int64)
+    buf = torch.empty(bd.E2 * sb, dtype=torch.uint8, device="cuda:0")
+    _lib.check(_lib.lib().mpbp_pack_messages_dev(bd._h, bd.E2, edges.ctypes.data_as(_lib.c_i64p), buf.data_ptr()))
+    M.reset_messages_(bd)
+    perm = edges[::-1].copy()  # unpack into the reversed edge order, then back
+    _lib.check(_lib.lib().mpbp_unpack_messages_dev(bd._h, bd.E2, edges.ctypes.data_as(_lib.c_i64p), buf.data_ptr()))
+    after = [bd.get_message(e) for e in range(bd.E2)]
+    for a, b in zip(before, after):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
 def test_errors_are_loud():
