@@ -96,6 +96,9 @@ struct mpbp_state {
   Arena arena;
   cudaStream_t st = nullptr;
   bool own_stream = true;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // extra streams: op groups of one level run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  double nstreams = 4;
   // options
   double arena_gb = 0;       // 0 = auto
   double qr_fill = 296;      // CTAs that fill the GPU for the QR kernel (2 per SM); fewer ops per launch -> TSQR split
@@ -147,6 +150,11 @@ int flat_messages(mpbp_state* h, MsgStore& m) {
 int common_init(mpbp_state* h) {
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaStreamCreate(&h->st));
+  for (int k = 0; k < 3; ++k) {
+    CUDA_OK(cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+  }
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUDA_OK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   h->max_smem -= 2048;  // head-room for the kernels' static shared memory
   {
@@ -437,7 +445,7 @@ int upload_jobs(mpbp_state* h, const std::vector<J>& v, J** d) {
 }
 
 enum { F_QR = 0, F_KC = 1, F_KP = 2, F_GEMM = 3, F_QRS = 4, F_JAC = 5, F_FIN = 6, F_BEL = 7, F_BT = 8, F_NFAM = 9 };
-void ev_begin(mpbp_state* h, int tag = F_QR) {
+void ev_begin(mpbp_state* h, int tag, cudaStream_t st) {
   if (!h->profile) return;
   if (h->ev_used == h->ev_pool.size()) {
     cudaEvent_t a, b;
@@ -447,11 +455,12 @@ void ev_begin(mpbp_state* h, int tag = F_QR) {
     h->ev_tag.push_back(0);
   }
   h->ev_tag[h->ev_used] = tag;
-  cudaEventRecord(h->ev_pool[h->ev_used].first, h->st);
+  cudaEventRecord(h->ev_pool[h->ev_used].first, st);
 }
 void ev_flush(mpbp_state* h) {
   if (!h->profile || h->ev_used == 0) return;
   cudaStreamSynchronize(h->st);
+  for (int k = 0; k < 3; ++k) cudaStreamSynchronize(h->aux[k]);
   for (size_t k = 0; k < h->ev_used; ++k) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_pool[k].first, h->ev_pool[k].second);
@@ -460,92 +469,93 @@ void ev_flush(mpbp_state* h) {
   }
   h->ev_used = 0;
 }
-void ev_end(mpbp_state* h) {
+void ev_end(mpbp_state* h, cudaStream_t st) {
   if (!h->profile) return;
-  cudaEventRecord(h->ev_pool[h->ev_used].second, h->st);
+  cudaEventRecord(h->ev_pool[h->ev_used].second, st);
   h->ev_used++;
 }
 
-// run one group of ops of one level (scratch already assigned)
-int run_op_group(mpbp_state* h, const OpDesc* d_ops, int nops, int maxDcap, int maxX, int maxNy, int maxq, const Trunc& tr) {
+// one group of ops of one level (scratch already assigned) and the stream it runs on
+struct GroupRun {
+  const OpDesc* d_ops;
+  int nops, maxD, maxX, maxNy, maxq;
+  cudaStream_t st;
+  size_t kc_smem, ft_big, ft_small;
+  bool big32, small32;
+  int dXcap;
+};
+
+// run the groups of one level concurrently: the per-site launch sequences of the groups are issued interleaved on
+// their own streams, so the tail of one group's launch is filled by the other groups' kernels
+int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr, int nsplit) {
   const int L = h->L, d = h->dmax;
-  cudaStream_t st = h->st;
-  k_op_setup<<<(nops + 127) / 128, 128, 0, st>>>(d_ops, nops, L);
-  h->n_launch++;
-  // shared-memory budgets
-  const int qr_vrows_big = std::min(QR_MAX_M, (int)((h->max_smem - 4096) / 8 / QB) - 64);
-  const size_t qr_smem_big = qr_shared_doubles(qr_vrows_big) * 8;
-  const size_t kc_smem = ((size_t)maxDcap + (size_t)d * d * maxNy) * 8;
   const size_t kp_smem = (size_t)d * d * d * 8;
-  if (kc_smem > (size_t)h->max_smem || kp_smem > (size_t)h->max_smem)
-    return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, maxNy);
-  const int dXcap = d * maxX;
   const size_t jac_fixed = 3 * SUB_BMAX;
   const size_t jac_doubles = (size_t)h->max_smem / 8 - jac_fixed;
   const size_t jac_smem = (jac_fixed + jac_doubles) * 8;
-  const int mrows_cap = maxDcap * maxX;
-  // number of TSQR stages for the capacity
-  int nstages = 1;
-  {
-    long long m = mrows_cap;
-    while (m > QR_MAX_M) {
-      m = ((m + QR_MAX_M - 1) / QR_MAX_M) * maxDcap;
-      nstages++;
-      if (nstages > 6) return fail("TSQR does not converge for D=%d", maxDcap);
-    }
+  if (kp_smem > (size_t)h->max_smem) return fail("bond capacity %d exceeds the shared-memory tiling of k_kron_proj", d);
+  for (auto& g : groups) {
+    g.kc_smem = ((size_t)g.maxD + (size_t)d * d * g.maxNy) * 8;
+    if (g.kc_smem > (size_t)h->max_smem)
+      return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, g.maxNy);
+    g.dXcap = d * g.maxX;
+    const size_t b32 = ft_smem_doubles<32>(g.maxD) * 8, b16 = ft_smem_doubles<16>(g.maxD) * 8;
+    const size_t s32 = ft_smem_doubles<32>(g.dXcap) * 8, s16 = ft_smem_doubles<16>(g.dXcap) * 8;
+    if (b16 > (size_t)h->max_smem || s16 > (size_t)h->max_smem)
+      return fail("bond capacity %d (D=%d, d*X=%d) exceeds the shared-memory row block of the QR kernel", d, g.maxD, g.dXcap);
+    g.big32 = b32 <= (size_t)h->max_smem;
+    g.small32 = s32 <= (size_t)h->max_smem;
+    g.ft_big = g.big32 ? b32 : b16;
+    g.ft_small = g.small32 ? s32 : s16;
+    k_op_setup<<<(g.nops + 127) / 128, 128, 0, g.st>>>(g.d_ops, g.nops, L);
+    h->n_launch++;
   }
-  const size_t ft32_big = ft_smem_doubles<32>(maxDcap) * 8, ft16_big = ft_smem_doubles<16>(maxDcap) * 8;
-  const size_t ft32_small = ft_smem_doubles<32>(dXcap) * 8, ft16_small = ft_smem_doubles<16>(dXcap) * 8;
-  if (ft16_big > (size_t)h->max_smem || ft16_small > (size_t)h->max_smem)
-    return fail("bond capacity %d (D=%d, d*X=%d) exceeds the shared-memory row block of the QR kernel", d, maxDcap, dXcap);
-  // under-filled launches: split tall matrices over several CTAs (TSQR)
-  const int nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(nops, 1))));
   // ---- sweep 1 (R->L) ----
   for (int t = L - 1; t >= 1; --t) {
-    dim3 g1(nops, maxq, (maxDcap + KC_RC - 1) / KC_RC);
-    ev_begin(h, F_KC);
-    k_kron_carry<<<g1, NT, kc_smem, st>>>(d_ops, t, L);
-    ev_end(h);
-    h->n_launch++;
-    ev_begin(h, F_QR);
-    {
-      dim3 gq(nops, nsplit);
-      if (ft32_big <= (size_t)h->max_smem) k_qr_ft<32><<<gq, NT, ft32_big, st>>>(d_ops, t, nsplit, h->d_flops);
-      else k_qr_ft<16><<<gq, NT, ft16_big, st>>>(d_ops, t, nsplit, h->d_flops);
+    for (auto& g : groups) {
+      dim3 g1(g.nops, g.maxq, (g.maxD + KC_RC - 1) / KC_RC);
+      ev_begin(h, F_KC, g.st);
+      k_kron_carry<<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
+      ev_end(h, g.st);
+      h->n_launch++;
+      ev_begin(h, F_QR, g.st);
+      dim3 gq(g.nops, nsplit);
+      if (g.big32) k_qr_ft<32><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+      else k_qr_ft<16><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
       h->n_launch++;
       if (nsplit > 1) {
-        if (ft32_big <= (size_t)h->max_smem) k_qr_ft_merge<32><<<nops, NT, ft32_big, st>>>(d_ops, t, nsplit, h->d_flops);
-        else k_qr_ft_merge<16><<<nops, NT, ft16_big, st>>>(d_ops, t, nsplit, h->d_flops);
+        if (g.big32) k_qr_ft_merge<32><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+        else k_qr_ft_merge<16><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
         h->n_launch++;
       }
+      ev_end(h, g.st);
     }
-    ev_end(h);
   }
   // ---- sweep 2 (L->R) ----
-  const int qr_vrows_small = std::min(qr_vrows_big, std::max(64, maxDcap));
-  const size_t qr_smem_small = qr_shared_doubles(qr_vrows_small) * 8;
   for (int t = 0; t < L; ++t) {
-    dim3 g3(nops, maxq, maxNy);
-    ev_begin(h, F_KP);
-    k_kron_proj<<<g3, NT, kp_smem, st>>>(d_ops, t);
-    ev_end(h);
-    h->n_launch++;
-    if (t < L - 1) {
-      dim3 g4(nops, (dXcap + 31) / 32, (maxDcap + 31) / 32);
-      ev_begin(h, F_GEMM);
-      k_gemm_m2t<<<g4, NT, 0, st>>>(d_ops, t);
-      ev_end(h);
-      ev_begin(h, F_QRS);
-      if (ft32_small <= (size_t)h->max_smem) k_qr_small<32><<<nops, NT, ft32_small, st>>>(d_ops, t, (int)jac_doubles);
-      else k_qr_small<16><<<nops, NT, ft16_small, st>>>(d_ops, t, (int)jac_doubles);
-      ev_end(h);
-      ev_begin(h, F_JAC);
-      k_jacobi_project<<<nops, NT, jac_smem, st>>>(d_ops, t, tr, d, (int)jac_doubles, h->d_err, h->d_flops + 1);
-      ev_end(h);
-      h->n_launch += 3;
-    } else {
-      k_op_last<<<nops, NT, 0, st>>>(d_ops, t);
+    for (auto& g : groups) {
+      dim3 g3(g.nops, g.maxq, g.maxNy);
+      ev_begin(h, F_KP, g.st);
+      k_kron_proj<<<g3, NT, kp_smem, g.st>>>(g.d_ops, t);
+      ev_end(h, g.st);
       h->n_launch++;
+      if (t < L - 1) {
+        dim3 g4(g.nops, (g.dXcap + 31) / 32, (g.maxD + 31) / 32);
+        ev_begin(h, F_GEMM, g.st);
+        k_gemm_m2t<<<g4, NT, 0, g.st>>>(g.d_ops, t);
+        ev_end(h, g.st);
+        ev_begin(h, F_QRS, g.st);
+        if (g.small32) k_qr_small<32><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
+        else k_qr_small<16><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
+        ev_end(h, g.st);
+        ev_begin(h, F_JAC, g.st);
+        k_jacobi_project<<<g.nops, NT, jac_smem, g.st>>>(g.d_ops, t, tr, d, (int)jac_doubles, h->d_err, h->d_flops + 1);
+        ev_end(h, g.st);
+        h->n_launch += 3;
+      } else {
+        k_op_last<<<g.nops, NT, 0, g.st>>>(g.d_ops, t);
+        h->n_launch++;
+      }
     }
   }
   CUDA_OK(cudaGetLastError());
@@ -628,8 +638,43 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
       }
       if (i1 == i0) return fail("arena too small for a single op (need %.1f MB)", op_scratch_bytes(h, d, d, ops[i0].nyo * ops[i0].q) / 1e6);
       const int nops = (int)(i1 - i0);
-      CUDA_OK(cudaMemcpyAsync(d_ops, ops.data() + i0, sizeof(OpDesc) * nops, cudaMemcpyHostToDevice, st));
-      if (run_op_group(h, d_ops, nops, maxD, maxX, maxNy, maxq, tr)) return 1;
+      // deal the (cost-sorted) ops round-robin into up to `nstreams` groups that run on concurrent streams
+      const int G = std::max(1, std::min((int)h->nstreams, nops / 48));
+      std::vector<std::vector<OpDesc>> gops(G);
+      std::vector<GroupRun> groups(G);
+      for (int gi = 0; gi < G; ++gi) {
+        GroupRun& gr = groups[gi];
+        gr.nops = 0; gr.maxD = 1; gr.maxX = 1; gr.maxNy = 1; gr.maxq = 1;
+        gr.st = gi == 0 ? st : h->aux[gi - 1];
+      }
+      for (int k = 0; k < nops; ++k) {
+        const OpDesc& op = ops[i0 + k];
+        GroupRun& gr = groups[k % G];
+        gops[k % G].push_back(op);
+        gr.nops++;
+        gr.maxD = std::max(gr.maxD, P.capA[lev][i0 + k] * P.capB[lev][i0 + k]);
+        gr.maxX = std::max(gr.maxX, op.nyo * op.q);
+        gr.maxNy = std::max(gr.maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
+        gr.maxq = std::max(gr.maxq, op.q);
+      }
+      {
+        size_t off = 0;
+        for (int gi = 0; gi < G; ++gi) {
+          groups[gi].d_ops = d_ops + off;
+          CUDA_OK(cudaMemcpyAsync(d_ops + off, gops[gi].data(), sizeof(OpDesc) * gops[gi].size(), cudaMemcpyHostToDevice, st));
+          off += gops[gi].size();
+        }
+      }
+      if (G > 1) {
+        CUDA_OK(cudaEventRecord(h->ev_fork, st));
+        for (int gi = 1; gi < G; ++gi) CUDA_OK(cudaStreamWaitEvent(h->aux[gi - 1], h->ev_fork, 0));
+      }
+      const int nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(nops, 1))));
+      if (run_op_groups(h, groups, tr, nsplit)) return 1;
+      for (int gi = 1; gi < G; ++gi) {
+        CUDA_OK(cudaEventRecord(h->ev_join[gi - 1], h->aux[gi - 1]));
+        CUDA_OK(cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
+      }
       // descriptors / scratch are reused by the next group: wait for the stream
       CUDA_OK(cudaStreamSynchronize(st));
       ev_flush(h);
@@ -653,15 +698,15 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     }
     const size_t smem = (qrd + jac_fixed + jac_doubles) * 8;
     if (!P.fin.empty()) {
-      ev_begin(h, F_FIN);
+      ev_begin(h, F_FIN, st);
       k_finalize<<<(unsigned)P.fin.size(), NT, smem, st>>>(d_fin, L, tr, d, vrows, (int)jac_doubles, h->d_err);
-      ev_end(h);
+      ev_end(h, st);
       h->n_launch++;
     }
     const size_t bsm = 2 * (size_t)d * qm * 8;
-    ev_begin(h, F_BEL);
+    ev_begin(h, F_BEL, st);
     k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
-    ev_end(h);
+    ev_end(h, st);
     k_free_energy<<<(unsigned)(P.fj.size() + 127) / 128, 128, 0, st>>>(d_fj, (int)P.fj.size());
     h->n_launch += 2;
   }
@@ -787,6 +832,8 @@ int mpbp_destroy(mpbp_handle h) {
   cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->arena.base);
   for (auto& e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (h->own_stream) cudaStreamDestroy(h->st);
+  for (int k = 0; k < 3; ++k) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
   return 0;
 }
@@ -1211,6 +1258,7 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   } else if (n == "max_group_ops") h->max_group_ops = value;
   else if (n == "profile") h->profile = (int)value;
   else if (n == "qr_fill") h->qr_fill = value;
+  else if (n == "nstreams") h->nstreams = std::max(1.0, std::min(4.0, value));
   else return fail("unknown option %s", name);
   return 0;
 }
