@@ -272,7 +272,7 @@ def run_gpu(args, rank, world, local_rank):
                     clocks=clocks,
                     e2e=dict(value=edges_total / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=launches,
-                    roofline=dict(kernel="k_qr_stage (Q-less Householder QR of the bond-D sweep)", bound="tensor", achieved=qr_tf, peak=float(peak[0]),
+                    roofline=dict(kernel="k_qr_ft (flat-tree DMMA Q-less QR of the bond-D sweep, csrc/qr_ft.cuh)", bound="tensor", achieved=qr_tf, peak=float(peak[0]),
                                   unit="TFLOP/s", frac=qr_tf / float(peak[0]) if peak[0] > 0 else None, traffic=traffic,
                                   peak_source="FP64 DMMA (mma.sync m8n8k4 f64) measured live by mpbp_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 entry",
                                   algorithmic_flops=ctr["qr_flops"], kernel_ms=ctr["qr_ms"], share_of_step=ctr["qr_ms"] / prof_ms if prof_ms > 0 else None,

@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(NT) k_qr_stage(const OpDesc* ops, int t, int s
 // are factored independently into op.Ms (n x n each) and k_qr_ft_merge factors the stack.
 __device__ __forceinline__ void ft_split(int m, int n, int nsplit, int& nch, int& ch_rows) {
   const int n8 = (n + 7) & ~7;
-  nch = min(nsplit, m / (2 * n8));  // a chunk must stay well above n rows to be worth a second stage
+  // latency of chunk stage + merge stage ~ m/k + k*n rows  ->  k ~ sqrt(m/n)  (the merge factors a k*n-row stack)
+  nch = min(nsplit, (int)(sqrt((double)m / (double)n8) + 0.5));
   if (nch < 2) { nch = 1; ch_rows = m; return; }
   ch_rows = (((m + nch - 1) / nch) + 31) & ~31;
   nch = (m + ch_rows - 1) / ch_rows;
