@@ -101,7 +101,7 @@ struct mpbp_state {
   double nstreams = 4;
   // options
   double arena_gb = 0;       // 0 = auto
-  double qr_fill = 296;      // CTAs that fill the GPU for the QR kernel (2 per SM); fewer ops per launch -> TSQR split
+  double qr_fill = 148;      // CTAs that fill the GPU for the QR kernel (H = 64: one per SM); fewer ops per launch -> TSQR split
   double max_group_ops = 1e9;
   int profile = 0;
   // counters
@@ -161,6 +161,9 @@ int common_init(mpbp_state* h) {
     const int ms = h->max_smem;
     CUDA_OK(cudaFuncSetAttribute(k_kron_carry, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_ft<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_ft_merge<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_qr_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft_merge<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
@@ -481,7 +484,7 @@ struct GroupRun {
   int nops, maxD, maxX, maxNy, maxq;
   cudaStream_t st;
   size_t kc_smem, ft_big, ft_small;
-  bool big32, small32;
+  int bigH, smallH;  // row-block height of the flat-tree QR: 64 (one CTA/SM, D >= 200), 32 (two CTAs/SM) or 16
   int dXcap;
 };
 
@@ -499,14 +502,17 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr,
     if (g.kc_smem > (size_t)h->max_smem)
       return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, g.maxNy);
     g.dXcap = d * g.maxX;
-    const size_t b32 = ft_smem_doubles<32>(g.maxD) * 8, b16 = ft_smem_doubles<16>(g.maxD) * 8;
-    const size_t s32 = ft_smem_doubles<32>(g.dXcap) * 8, s16 = ft_smem_doubles<16>(g.dXcap) * 8;
-    if (b16 > (size_t)h->max_smem || s16 > (size_t)h->max_smem)
+    auto pickH = [&](int n, size_t& bytes) -> int {
+      const size_t s64 = ft_smem_doubles<64>(n) * 8, s32 = ft_smem_doubles<32>(n) * 8, s16 = ft_smem_doubles<16>(n) * 8;
+      if (n >= 200 && s64 <= (size_t)h->max_smem) { bytes = s64; return 64; }
+      if (s32 <= (size_t)h->max_smem) { bytes = s32; return 32; }
+      bytes = s16;
+      return s16 <= (size_t)h->max_smem ? 16 : 0;
+    };
+    g.bigH = pickH(g.maxD, g.ft_big);
+    g.smallH = pickH(g.dXcap, g.ft_small);
+    if (!g.bigH || !g.smallH)
       return fail("bond capacity %d (D=%d, d*X=%d) exceeds the shared-memory row block of the QR kernel", d, g.maxD, g.dXcap);
-    g.big32 = b32 <= (size_t)h->max_smem;
-    g.small32 = s32 <= (size_t)h->max_smem;
-    g.ft_big = g.big32 ? b32 : b16;
-    g.ft_small = g.small32 ? s32 : s16;
     k_op_setup<<<(g.nops + 127) / 128, 128, 0, g.st>>>(g.d_ops, g.nops, L);
     h->n_launch++;
   }
@@ -520,11 +526,13 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr,
       h->n_launch++;
       ev_begin(h, F_QR, g.st);
       dim3 gq(g.nops, nsplit);
-      if (g.big32) k_qr_ft<32><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+      if (g.bigH == 64) k_qr_ft<64><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+      else if (g.bigH == 32) k_qr_ft<32><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
       else k_qr_ft<16><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
       h->n_launch++;
       if (nsplit > 1) {
-        if (g.big32) k_qr_ft_merge<32><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+        if (g.bigH == 64) k_qr_ft_merge<64><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+        else if (g.bigH == 32) k_qr_ft_merge<32><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
         else k_qr_ft_merge<16><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
         h->n_launch++;
       }
@@ -545,7 +553,8 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr,
         k_gemm_m2t<<<g4, NT, 0, g.st>>>(g.d_ops, t);
         ev_end(h, g.st);
         ev_begin(h, F_QRS, g.st);
-        if (g.small32) k_qr_small<32><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
+        if (g.smallH == 64) k_qr_small<64><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
+        else if (g.smallH == 32) k_qr_small<32><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
         else k_qr_small<16><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
         ev_end(h, g.st);
         ev_begin(h, F_JAC, g.st);
@@ -1299,7 +1308,7 @@ int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, 
   CUDA_OK(cudaMalloc((void**)&dA, sizeof(double) * (size_t)batch * m * n));
   CUDA_OK(cudaMalloc((void**)&dR, sizeof(double) * (size_t)batch * n * n));
   CUDA_OK(cudaMemcpy(dA, A, sizeof(double) * (size_t)batch * m * n, cudaMemcpyHostToDevice));
-  const size_t sm = (H == 32 ? ft_smem_doubles<32>(n) : ft_smem_doubles<16>(n)) * 8;
+  const size_t sm = (H == 64 ? ft_smem_doubles<64>(n) : H == 32 ? ft_smem_doubles<32>(n) : ft_smem_doubles<16>(n)) * 8;
   int maxs = 0;
   CUDA_OK(cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0));
   if (sm > (size_t)maxs) return fail("test_qr_ft: n too large for H=%d", H);
@@ -1309,7 +1318,10 @@ int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, 
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    if (H == 32) {
+    if (H == 64) {
+      CUDA_OK(cudaFuncSetAttribute(k_test_qr_ft<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_test_qr_ft<64><<<batch, NT, sm>>>(dA, m, n, dR);
+    } else if (H == 32) {
       CUDA_OK(cudaFuncSetAttribute(k_test_qr_ft<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       k_test_qr_ft<32><<<batch, NT, sm>>>(dA, m, n, dR);
     } else {

@@ -48,11 +48,15 @@ template <int H>
 __device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const int j0, const int n, double* __restrict__ R,
                                          const int ldr, double* Vt, double* Tm) {
   constexpr int LDV = H + 4;
+  constexpr int RPL = (H + 31) / 32;  // rows of the block per lane
   const int lane = threadIdx.x & 31;
-  double a[FT_B];
-  const bool rowok = lane < H;
+  double a[RPL][FT_B];
 #pragma unroll
-  for (int c = 0; c < FT_B; ++c) a[c] = rowok ? Ablk[(size_t)lane * ld + ((j0 + c) ^ ft_sw(lane))] : 0.0;
+  for (int r = 0; r < RPL; ++r) {
+    const int row = lane + 32 * r;
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) a[r][c] = (row < H) ? Ablk[(size_t)row * ld + ((j0 + c) ^ ft_sw(row))] : 0.0;
+  }
   // R_jj (8x8 upper) preloaded once: lane k holds row j0+k; rows are broadcast with shuffles
   double rrow[FT_B];
 #pragma unroll
@@ -73,7 +77,12 @@ __device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const
       const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double lo = a[k] * a[i], hi = a[k] * a[i + 4];
+        double lo = 0.0, hi = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+          lo += a[r][k] * a[r][i];
+          hi += a[r][k] * a[r][i + 4];
+        }
         const double send = b4 ? lo : hi, keep = b4 ? hi : lo;
         w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
       }
@@ -107,12 +116,17 @@ __device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const
       tau = alpha >= 0.0 ? u * rs : -u * rs; // (beta - alpha)/beta = -u/beta
       sc = 1.0 / u;
     }
-    const double v = a[k] * sc;
-    a[k] = v;
+    double v[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      v[r] = a[r][k] * sc;
+      a[r][k] = v[r];
+    }
 #pragma unroll
     for (int c = k + 1; c < FT_B; ++c) {
       const double s = tau * (rk[c] + sc * red[c]);
-      a[c] -= s * v;
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) a[r][c] -= s * v[r];
       rk[c] -= s;
     }
     if (lane == k) {
@@ -135,9 +149,13 @@ __device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const
     for (int c = 0; c < FT_B; ++c)
       if (c >= lane && j0 + c < n) R[(size_t)(j0 + lane) * ldr + j0 + c] = rrow[c];
   }
-  if (rowok) {
 #pragma unroll
-    for (int k = 0; k < FT_B; ++k) Vt[k * LDV + lane] = a[k];
+  for (int r = 0; r < RPL; ++r) {
+    const int row = lane + 32 * r;
+    if (row < H) {
+#pragma unroll
+      for (int k = 0; k < FT_B; ++k) Vt[k * LDV + row] = a[r][k];
+    }
   }
   // T is replicated in every lane: lane x writes row x
 #pragma unroll

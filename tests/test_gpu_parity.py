@@ -42,7 +42,8 @@ def test_qr_r_factor(m, n):
 
 
 @pytest.mark.parametrize("m,n,H", [(1, 1, 32), (5, 3, 32), (3, 5, 32), (40, 8, 32), (160, 40, 16), (257, 17, 32), (700, 100, 32),
-                                   (1600, 400, 32), (4000, 400, 32), (333, 77, 16), (64, 600, 16), (900, 450, 16)])
+                                   (1600, 400, 32), (4000, 400, 32), (333, 77, 16), (64, 600, 16), (900, 450, 16), (1600, 400, 64), (333, 77, 64),
+                                   (70, 9, 64)])
 def test_qr_flat_tree_dmma(m, n, H):
     rng = np.random.default_rng(m * 1000 + n)
     A = rng.standard_normal((3, m, n))
