@@ -159,8 +159,8 @@ int common_init(mpbp_state* h) {
   h->max_smem -= 2048;  // head-room for the kernels' static shared memory
   {
     const int ms = h->max_smem;
-    CUDA_OK(cudaFuncSetAttribute(k_kron_carry, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
-    CUDA_OK(cudaFuncSetAttribute(k_qr_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_kron_carry<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_kron_carry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft_merge<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
@@ -484,6 +484,7 @@ struct GroupRun {
   int nops, maxD, maxX, maxNy, maxq;
   cudaStream_t st;
   size_t kc_smem, ft_big, ft_small;
+  int kc_rb;
   int bigH, smallH;  // row-block height of the flat-tree QR: 64 (one CTA/SM, D >= 200), 32 (two CTAs/SM) or 16
   int dXcap;
 };
@@ -499,6 +500,8 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr,
   if (kp_smem > (size_t)h->max_smem) return fail("bond capacity %d exceeds the shared-memory tiling of k_kron_proj", d);
   for (auto& g : groups) {
     g.kc_smem = ((size_t)g.maxD + (size_t)d * d * g.maxNy) * 8;
+    g.kc_rb = (4 * g.kc_smem <= (size_t)h->max_smem / 2) ? 4 : 1;  // keep >= 2 CTAs/SM
+    g.kc_smem *= g.kc_rb;
     if (g.kc_smem > (size_t)h->max_smem)
       return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, g.maxNy);
     g.dXcap = d * g.maxX;
@@ -521,7 +524,8 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr,
     for (auto& g : groups) {
       dim3 g1(g.nops, g.maxq, (g.maxD + KC_RC - 1) / KC_RC);
       ev_begin(h, F_KC, g.st);
-      k_kron_carry<<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
+      if (g.kc_rb == 4) k_kron_carry<4><<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
+      else k_kron_carry<1><<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
       ev_end(h, g.st);
       h->n_launch++;
       ev_begin(h, F_QR, g.st);

@@ -26,7 +26,8 @@ __device__ __forceinline__ double jacobi_inv_sigma(double s, double smax) {
 // G lanes cooperate on one column pair (G = 8, 16 or 32): 32/G pairs run concurrently per warp, which is what the
 // latency-bound pair step needs (a b = 64 block has 32 pairs per round = one pass over 8 warps at G = 8).
 template <int G>
-__device__ inline int jacobi_cols_g(double* A, const int p, const int c, const int lda, int* flag, const double thr2) {
+__device__ inline int jacobi_cols_g(double* A, const int p, const int c, const int lda, int* flag, const double thr2,
+                                    const int max_sweeps) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   constexpr int GPW = 32 / G;                 // groups per warp
   const int grp = w * GPW + lane / G, lg = lane % G;
@@ -35,7 +36,7 @@ __device__ inline int jacobi_cols_g(double* A, const int p, const int c, const i
   const double tol = 2.0 * JACOBI_EPS * sqrt((double)max(p, 64));
   const double tol2 = tol * tol;
   int sweep = 0;
-  for (; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+  for (; sweep < max_sweeps; ++sweep) {
     __syncthreads();
     if (threadIdx.x == 0) *flag = 0;
     __syncthreads();
@@ -97,7 +98,9 @@ __device__ inline int jacobi_cols_g(double* A, const int p, const int c, const i
   return sweep;
 }
 
-__device__ inline int jacobi_cols(double* A, const int p, const int c, const int lda, int* flag) {
+// max_sweeps < JACOBI_MAX_SWEEPS: approximate orthogonalisation (enough inside a subspace iteration)
+__device__ inline int jacobi_cols(double* A, const int p, const int c, const int lda, int* flag,
+                                  const int max_sweeps = JACOBI_MAX_SWEEPS) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (c < 2) return 0;
   __shared__ double s_scale[NW];
@@ -118,10 +121,10 @@ __device__ inline int jacobi_cols(double* A, const int p, const int c, const int
   const double thr2 = JACOBI_ZERO * JACOBI_ZERO * scale2;
   const int npair = (c + 1) / 2;
   int sweep;
-  if (npair > 2 * NW && p >= 16) sweep = jacobi_cols_g<8>(A, p, c, lda, flag, thr2);
-  else if (npair > NW && p >= 32) sweep = jacobi_cols_g<16>(A, p, c, lda, flag, thr2);
-  else sweep = jacobi_cols_g<32>(A, p, c, lda, flag, thr2);
-  if (sweep >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) {
+  if (npair > 2 * NW && p >= 16) sweep = jacobi_cols_g<8>(A, p, c, lda, flag, thr2, max_sweeps);
+  else if (npair > NW && p >= 32) sweep = jacobi_cols_g<16>(A, p, c, lda, flag, thr2, max_sweeps);
+  else sweep = jacobi_cols_g<32>(A, p, c, lda, flag, thr2, max_sweeps);
+  if (sweep >= JACOBI_MAX_SWEEPS && max_sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) {
     printf("[mpbp] jacobi not converged: p=%d c=%d\n", p, c);
   }
   return sweep;

@@ -83,7 +83,9 @@ __global__ void k_op_setup(const OpDesc* ops, int nops, int L) {
 constexpr int KC_RC = 8;  // right-bond columns per CTA in k_kron_carry
 
 // M_t[(m1,m2), rr, y, x] = sum_{y1,y2} Pyy sum_{n1,n2} B1[m1,n1,y1,x] B2[m2,n2,y2,x] L_{t+1}[(n1,n2), rr]
-// grid (nops, q, ceil(rcap/KC_RC)); dyn smem: (Dcap + d*d*nymax) doubles
+// grid (nops, q, ceil(rcap/KC_RC)).  RB right-bond columns are processed together so that every operand load
+// (B1/B2 element) feeds RB independent FMAs.  dyn smem: RB * (Dcap + d*d*nymax) doubles.
+template <int RB>
 __global__ void __launch_bounds__(NT) k_kron_carry(const OpDesc* ops, int t, int L) {
   extern __shared__ double smem[];
   const OpDesc& op = ops[blockIdx.x];
@@ -99,80 +101,63 @@ __global__ void __launch_bounds__(NT) k_kron_carry(const OpDesc* ops, int t, int
   const double* Lm = (t + 1 < L) ? op.Lbuf + (size_t)(t + 1) * op.Lstride : nullptr;
   const double* pyy = op.pyy + (size_t)t * op.pyy_tstride;
   const int ny1 = op.ny1, ny2 = op.ny2, nyo = op.nyo;
-  double* Lcol = smem;
-  double* Z = smem + Dr;
+  const int nz = bl2 * br1 * ny2;
+  double* Lcol = smem;            // RB x Dr
+  double* Z = smem + RB * Dr;     // RB x nz
   const int rr1 = min(rr0 + KC_RC, rn);
-  for (int rr = rr0; rr < rr1; ++rr) {
-    for (int i = threadIdx.x; i < Dr; i += NT) Lcol[i] = Lm ? Lm[i + (size_t)Dr * rr] : 1.0;
+  for (int rb = rr0; rb < rr1; rb += RB) {
+    const int nb = min(RB, rr1 - rb);
+    for (int i = threadIdx.x; i < RB * Dr; i += NT) {
+      const int u = i / Dr, e = i % Dr;
+      Lcol[i] = (u < nb) ? (Lm ? Lm[e + (size_t)Dr * (rb + u)] : 1.0) : 0.0;
+    }
     __syncthreads();
-    const int nz = bl2 * br1 * ny2;
     for (int idx = threadIdx.x; idx < nz; idx += NT) {
       const int m2 = idx % bl2, n1 = (idx / bl2) % br1, y2 = idx / (bl2 * br1);
       const double* a2 = A2 + m2 + (size_t)bl2 * br2 * (y2 + ny2 * x);
-      double acc = 0.0;
-      for (int n2 = 0; n2 < br2; ++n2) acc += a2[bl2 * n2] * Lcol[n1 + br1 * n2];
-      Z[idx] = acc;
+      double acc[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) acc[u] = 0.0;
+      for (int n2 = 0; n2 < br2; ++n2) {
+        const double a = a2[bl2 * n2];
+        const double* lc = Lcol + n1 + br1 * n2;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) acc[u] += a * lc[u * Dr];
+      }
+#pragma unroll
+      for (int u = 0; u < RB; ++u) Z[u * nz + idx] = acc[u];
     }
     __syncthreads();
     const int no = Dl * nyo;
     for (int idx = threadIdx.x; idx < no; idx += NT) {
       const int c = idx % Dl, y = idx / Dl;
       const int m1 = c % bl1, m2 = c / bl1;
-      double acc = 0.0;
+      double acc[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) acc[u] = 0.0;
       for (int y2 = 0; y2 < ny2; ++y2)
         for (int y1 = 0; y1 < ny1; ++y1) {
           const double pv = pyy[y + nyo * (y1 + ny1 * (y2 + ny2 * x))];
           if (pv != 0.0) {
             const double* a1 = A1 + m1 + (size_t)bl1 * br1 * (y1 + ny1 * x);
             const double* z = Z + m2 + bl2 * br1 * y2;
-            double s = 0.0;
-            for (int n1 = 0; n1 < br1; ++n1) s += a1[bl1 * n1] * z[bl2 * n1];
-            acc += pv * s;
+            double s[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) s[u] = 0.0;
+            for (int n1 = 0; n1 < br1; ++n1) {
+              const double a = a1[bl1 * n1];
+#pragma unroll
+              for (int u = 0; u < RB; ++u) s[u] += a * z[bl2 * n1 + u * nz];
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) acc[u] += pv * s[u];
           }
         }
-      op.M[c + (size_t)Dl * (rr + (size_t)rn * (y + nyo * x))] = acc;
+#pragma unroll
+      for (int u = 0; u < RB; ++u)
+        if (u < nb) op.M[c + (size_t)Dl * (rb + u + (size_t)rn * (y + nyo * x))] = acc[u];
     }
     __syncthreads();
-  }
-}
-
-// Q-less QR of the sweep-1 matrix, TSQR over row chunks of QR_MAX_M rows.
-// stage 0 reads op.M ((rn*X) x Dl); chunk results are stacked (each block padded to Dl rows) into op.Ms;
-// a later stage reduces the stack.  The final stage writes L_t (= R^T, stored as row-major R) and r[t].
-// grid (nops, nchunks_cap).  `src_sel`: 0 = M, 1 = Ms ; dst: final ? Lbuf : the other buffer.
-__device__ __forceinline__ int qr_stage_rows(int m0, int n, int stage) {
-  int m = m0;
-  for (int s = 0; s < stage; ++s) m = ((m + QR_MAX_M - 1) / QR_MAX_M) * n;
-  return m;
-}
-__global__ void __launch_bounds__(NT) k_qr_stage(const OpDesc* ops, int t, int stage, int vrows, double* flops) {
-  extern __shared__ double smem[];
-  const OpDesc& op = ops[blockIdx.x];
-  const int Dl = op.a.bonds[t] * op.b.bonds[t];
-  const int rn = op.r[t + 1];
-  const int X = op.nyo * op.q;
-  const int m0 = rn * X;
-  if (stage > 0 && qr_stage_rows(m0, Dl, stage - 1) <= QR_MAX_M) return;  // already finished
-  const int m = qr_stage_rows(m0, Dl, stage);
-  const int ch = blockIdx.y;
-  const int row0 = ch * QR_MAX_M;
-  if (row0 >= m) return;
-  const int rows = min(QR_MAX_M, m - row0);
-  const bool single = (m <= QR_MAX_M);  // this stage finishes the factorisation
-  double* src = ((stage & 1) ? op.Ms : op.M) + (size_t)row0 * Dl;
-  if (flops && threadIdx.x == 0) {
-    const double mm = rows, nn = Dl;
-    atomicAdd(flops, mm >= nn ? 2.0 * mm * nn * nn - (2.0 / 3.0) * nn * nn * nn : 2.0 * nn * mm * mm - (2.0 / 3.0) * mm * mm * mm);
-  }
-  if (single) {
-    double* dst = op.Lbuf + (size_t)t * op.Lstride;
-    qr_r_cta(src, rows, Dl, Dl, dst, Dl, true, smem, vrows);
-    if (threadIdx.x == 0) op.r[t] = min(rows, Dl);
-  } else {
-    double* dst = ((stage & 1) ? op.M : op.Ms) + (size_t)ch * Dl * Dl;
-    qr_r_cta(src, rows, Dl, Dl, dst, Dl, true, smem, vrows);
-    const int k = min(rows, Dl);
-    for (int idx = threadIdx.x + k * Dl; idx < Dl * Dl; idx += NT) dst[idx] = 0.0;
   }
 }
 
@@ -356,6 +341,7 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_small(const OpDesc
 //                  (sigma_{b+1}/sigma_k)^2 per iteration; validated against exact SVDs in DESIGN.md / tests.
 constexpr int SUB_BMAX = 64;
 constexpr int SUB_MAXIT = 40;
+constexpr int SUB_ORTH_SWEEPS = JACOBI_MAX_SWEEPS;  // (capping the sweeps was tried: it breaks the Ritz-value convergence test)
 __host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles) {
   const int c = p < n ? p : n;
   return c <= SUB_BMAX && (long long)p * c <= jac_doubles;
@@ -497,7 +483,9 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       __syncthreads();
       for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
       __syncthreads();
-      sw = max(sw, jacobi_cols(W, p, b, p, &flag));
+      // a subspace iteration only needs a well-conditioned basis: SUB_ORTH_SWEEPS Jacobi sweeps (Y is already
+      // nearly orthogonal after the first iteration); the final Rayleigh-Ritz step below converges fully
+      jacobi_cols(W, p, b, p, &flag, SUB_ORTH_SWEEPS);
       jacobi_sort(W, p, b, p, sig, order);
       for (int j = threadIdx.x; j < b; j += NT) sig[j] = sqrt(sig[j]);  // singular values of M (Y ~ U Sigma^2)
       __syncthreads();
