@@ -208,12 +208,12 @@ int common_init(mpbp_state* h) {
   if (upload(&h->d_marg, marg.data(), marg.size())) return 1;
   if (upload(&h->d_means, means.data(), means.size())) return 1;
   const int64_t nzij = h->inf_k > 0 ? h->inf_k : h->E2;
-  std::vector<double> zeros(std::max<int64_t>(std::max<int64_t>(h->N, nzij), 8), 0.0);
+  std::vector<double> zeros(std::max<int64_t>(std::max<int64_t>(h->N, nzij), 32), 0.0);
   if (upload(&h->d_logzi, zeros.data(), h->N)) return 1;
   if (upload(&h->d_logzij, zeros.data(), nzij)) return 1;
   if (upload(&h->d_f, zeros.data(), h->N)) return 1;
   if (upload(&h->d_delta, zeros.data(), 1)) return 1;
-  if (upload(&h->d_flops, zeros.data(), 8)) return 1;
+  if (upload(&h->d_flops, zeros.data(), 24)) return 1;
   int zero = 0;
   if (upload(&h->d_err, &zero, 1)) return 1;
   if (alloc_msg_store(h, h->msg[0])) return 1;
@@ -1193,7 +1193,7 @@ int mpbp_counters(mpbp_handle h, double* out8, int reset) {
   out8[7] = fl5[5];  // subspace-SVD calls that hit the iteration cap
   if (reset) {
     h->n_launch = h->qr_ms = h->n_ops = h->n_edge_updates = 0;
-    CUDA_OK(cudaMemset(h->d_flops, 0, 8 * sizeof(double)));
+    CUDA_OK(cudaMemset(h->d_flops, 0, 24 * sizeof(double)));
   }
   return 0;
 }
@@ -1389,7 +1389,7 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
   CUDA_OK(cudaMalloc((void**)&dU, sizeof(double) * (size_t)batch * p * d));
   CUDA_OK(cudaMalloc((void**)&dS, sizeof(double) * (size_t)batch * d));
   CUDA_OK(cudaMalloc((void**)&dscr, sizeof(double) * per * batch));
-  CUDA_OK(cudaMalloc((void**)&dst, sizeof(double) * 8));
+  CUDA_OK(cudaMalloc((void**)&dst, sizeof(double) * 16));
   CUDA_OK(cudaMalloc((void**)&derr, sizeof(int)));
   CUDA_OK(cudaMemset(derr, 0, sizeof(int)));
   CUDA_OK(cudaMemcpy(dM, M, sizeof(double) * (size_t)batch * p * n, cudaMemcpyHostToDevice));
@@ -1399,7 +1399,7 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
   cudaEventCreate(&e1);
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
-    CUDA_OK(cudaMemset(dst, 0, sizeof(double) * 8));
+    CUDA_OK(cudaMemset(dst, 0, sizeof(double) * 16));
     cudaEventRecord(e0);
     k_test_svd<<<batch, NT, (size_t)maxs>>>(dM, p, n, tr, (int)jac_doubles, dscr, per, dU, dS, derr, dst);
     cudaEventRecord(e1);
@@ -1415,6 +1415,11 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
   CUDA_OK(cudaMemcpy(U, dU, sizeof(double) * (size_t)batch * p * d, cudaMemcpyDeviceToHost));
   CUDA_OK(cudaMemcpy(S, dS, sizeof(double) * (size_t)batch * d, cudaMemcpyDeviceToHost));
   if (stats5) CUDA_OK(cudaMemcpy(stats5, dst, sizeof(double) * 5, cudaMemcpyDeviceToHost));
+  {
+    double ph[6];
+    CUDA_OK(cudaMemcpy(ph, dst + 8, sizeof(double) * 6, cudaMemcpyDeviceToHost));
+    if (getenv("MPBP_SVD_PHASES")) printf("svd phases (Mcycles/call): transpose %.2f  select %.2f  start-jacobi %.2f  iter-gemms %.2f  iter-jacobi %.2f  final %.2f\n", ph[0] / batch / 1e6, ph[1] / batch / 1e6, ph[2] / batch / 1e6, ph[3] / batch / 1e6, ph[4] / batch / 1e6, ph[5] / batch / 1e6);
+  }
   cudaFree(dM); cudaFree(dU); cudaFree(dS); cudaFree(dscr); cudaFree(dst); cudaFree(derr);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (herr) return fail("test_svd: device error flags 0x%x", herr);

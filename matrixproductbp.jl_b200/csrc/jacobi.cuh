@@ -64,12 +64,28 @@ __device__ inline int jacobi_cols_g(double* A, const int p, const int c, const i
         double* aj = A + (size_t)j * lda;
         double a = 0.0, b = 0.0, g = 0.0;
         if (act) {
-          for (int k = lg; k < p; k += G) {
+          // two independent accumulator sets break the loop-carried DFMA chains
+          double a2 = 0.0, b2 = 0.0, g2 = 0.0;
+          int k = lg;
+#pragma unroll 2
+          for (; k + G < p; k += 2 * G) {
+            const double x = ai[k], y = aj[k], x2 = ai[k + G], y2 = aj[k + G];
+            a += x * x;
+            b += y * y;
+            g += x * y;
+            a2 += x2 * x2;
+            b2 += y2 * y2;
+            g2 += x2 * y2;
+          }
+          if (k < p) {
             const double x = ai[k], y = aj[k];
             a += x * x;
             b += y * y;
             g += x * y;
           }
+          a += a2;
+          b += b2;
+          g += g2;
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
@@ -79,9 +95,11 @@ __device__ inline int jacobi_cols_g(double* A, const int p, const int c, const i
         }
         // rotate when |g| > tol*sqrt(a*b) (sqrt-free test) and neither column is numerically zero
         if (act && g * g > tol2 * a * b && a > thr2 && b > thr2 && a * b > 0.0) {
-          const double zeta = (b - a) / (2.0 * g);
-          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          // t = sign(zeta)/(|zeta| + sqrt(1+zeta^2)), zeta = (b-a)/(2g)  ==  2g*sign(d)/(|d| + sqrt(d^2 + 4g^2)), d = b-a
+          const double d = b - a;
+          const double t = (d >= 0.0 ? 2.0 * g : -2.0 * g) / (fabs(d) + sqrt(d * d + 4.0 * g * g));
           const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll 4
           for (int k = lg; k < p; k += G) {
             const double x = ai[k], y = aj[k];
             ai[k] = cs * x - sn * y;

@@ -339,9 +339,9 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_small(const OpDesc
 // large matrices : blocked subspace iteration  Z <- orth(M^T Q), Q <- orth(M Z)  with b <= 64 columns, the
 //                  tall-skinny blocks orthonormalised by one-sided Jacobi in shared memory.  Converges like
 //                  (sigma_{b+1}/sigma_k)^2 per iteration; validated against exact SVDs in DESIGN.md / tests.
-constexpr int SUB_BMAX = 64;
+constexpr int SUB_BMAX = 64;   // storage bound of the block
+constexpr int SUB_BLOCK = 48;  // block width used (>= 2d+8 at d = 20): Jacobi cost ~ b^2, convergence ~ (sigma_{b+1}/sigma_k)^2
 constexpr int SUB_MAXIT = 40;
-constexpr int SUB_ORTH_SWEEPS = JACOBI_MAX_SWEEPS;  // (capping the sweeps was tried: it breaks the Ritz-value convergence test)
 __host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles) {
   const int c = p < n ? p : n;
   return c <= SUB_BMAX && (long long)p * c <= jac_doubles;
@@ -373,7 +373,17 @@ __device__ inline void sub_gemm(const double* __restrict__ Mx, int rows_out, int
         double m8[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) m8[u] = Mx[r + (size_t)rows_out * (k + u)];
-        if (nj == 16) {
+        if (nj == 16 && (kdim & 1) == 0) {
+          // 128-bit shared-memory loads: two consecutive k per load (kdim even -> 16-byte aligned)
+#pragma unroll
+          for (int u = 0; u < 8; u += 2)
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const double2 ww = *reinterpret_cast<const double2*>(w + k + u + (size_t)jj * kdim);
+              acc[jj] += m8[u] * ww.x;
+              acc[jj] += m8[u + 1] * ww.y;
+            }
+        } else if (nj == 16) {
 #pragma unroll
           for (int u = 0; u < 8; ++u)
 #pragma unroll
@@ -434,8 +444,16 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
   } else {
     const int n = rn;
     const double* M = Mcm;  // column-major p x n
+    long long tph = clock64();
+    auto phase = [&](int which) {
+      __syncthreads();
+      const long long now = clock64();
+      if (stats && threadIdx.x == 0) atomicAdd(stats + 8 + which, (double)(now - tph));
+      tph = now;
+    };
     for (int idx = threadIdx.x; idx < p * n; idx += NT) Mt[(idx / p) + (size_t)n * (idx % p)] = M[idx];
-    int b = min(min(SUB_BMAX, c), jac_doubles / max(p, n));
+    phase(0);
+    int b = min(min(max(SUB_BLOCK, min(SUB_BMAX, 2 * (tr.kind == 1 ? dcap : tr.d) + 8)), c), jac_doubles / max(p, n));
     b &= ~7;
     if (b < 8 || b < min(c, (tr.kind == 1 ? dcap : tr.d))) {
       if (threadIdx.x == 0) atomicOr(err, ERR_BOND_OVERFLOW);  // shared memory cannot hold a block wide enough
@@ -466,9 +484,13 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
     for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = M[(idx % p) + (size_t)p * order[idx / p]];
     for (int j = threadIdx.x; j < SUB_BMAX; j += NT) sprev[j] = 0.0;
     __syncthreads();
-    int sw = jacobi_cols(W, p, b, p, &flag);
+    phase(1);
+    // start block: two sweeps are enough (only a well-conditioned basis is needed here)
+    int sw = 0;
+    jacobi_cols(W, p, b, p, &flag, 2);
     jacobi_sort(W, p, b, p, sig, order);
     normalize_cols(W, p, b, sig);
+    phase(2);
     int extra = -1;
     const int kchk = min(b, tr.kind == 1 ? dcap : tr.d);
     int nit = 0;
@@ -482,10 +504,8 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       sub_gemm(M, p, n, W, b, Qg);  // Y = M Z
       __syncthreads();
       for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
-      __syncthreads();
-      // a subspace iteration only needs a well-conditioned basis: SUB_ORTH_SWEEPS Jacobi sweeps (Y is already
-      // nearly orthogonal after the first iteration); the final Rayleigh-Ritz step below converges fully
-      jacobi_cols(W, p, b, p, &flag, SUB_ORTH_SWEEPS);
+      phase(3);
+      jacobi_cols(W, p, b, p, &flag);
       jacobi_sort(W, p, b, p, sig, order);
       for (int j = threadIdx.x; j < b; j += NT) sig[j] = sqrt(sig[j]);  // singular values of M (Y ~ U Sigma^2)
       __syncthreads();
@@ -507,6 +527,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       }
       __syncthreads();
       normalize_cols(W, p, b, sig, true);
+      phase(4);
       if (s_done) break;
     }
     const bool converged = s_done;
@@ -526,6 +547,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       sw = max(sw, jacobi_cols(W, p, b, p, &flag));
       jacobi_sort(W, p, b, p, sig, order);
       normalize_cols(W, p, b, sig);
+      phase(5);
     }
     if (stats && threadIdx.x == 0) {
       atomicAdd(stats + 0, 1.0);
