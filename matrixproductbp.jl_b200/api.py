@@ -15,14 +15,14 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .factors import (BPFactor, DampedFactor, GenericGlauberFactor, HomogeneousGlauberFactor, IntegerGlauberFactor,
+from .factors import (BPFactor, DampedFactor, GenericFactor, GenericGlauberFactor, HomogeneousGlauberFactor, IntegerGlauberFactor,
                       PMJGlauberFactor, RecursiveBPFactor, SIRSFactor, SISFactor, tabulate_class)
 from .truncations import SVDTrunc, TruncBond, TruncBondMax, TruncBondThresh, TruncThresh
 
 __all__ = [
     "BPFactor", "RecursiveBPFactor", "HomogeneousGlauberFactor", "PMJGlauberFactor", "IntegerGlauberFactor",
     "GenericGlauberFactor", "SISFactor", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
-    "TruncBondThresh", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
+    "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
     "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "pair_beliefs", "bethe_free_energy", "means",
     "reset_messages_", "glauber_factors", "MPBPError",
 ]
@@ -226,9 +226,31 @@ class MPBP:
                 continue
             qn = np.array([self.q[0]] * z if self.infinite else [self.q[j] for j in self.g.neighbors(i)], dtype=np.int32)
             wi = self.w[i]
-            if not isinstance(wi[0], RecursiveBPFactor):
-                raise MPBPError("generic BPFactor (exhaustive trace, bp_core.jl:18-57) is not supported by the device path yet")
             keys = [w.key() for w in wi]
+            if not isinstance(wi[0], RecursiveBPFactor):
+                # generic BPFactor: only the functor w(x', x_neighbours, x) exists -> dense table, exhaustive-trace path
+                same = all(w is wi[0] for w in wi) or (keys[0] is not None and all(k == keys[0] for k in keys))
+                ck = ("generic", keys[0], z, int(self.q[i]), tuple(qn.tolist())) if same and keys[0] is not None else None
+                if ck is not None and ck in cache:
+                    cls[i] = cache[ck]
+                    continue
+                if z == 0:
+                    raise MPBPError("generic BPFactor on an isolated node is not supported")
+                ws = [wi[0]] if same else list(wi)
+                qi = int(self.q[i])
+                tabs = []
+                for w in ws:
+                    tab = np.zeros([qi] + [int(v) for v in qn] + [qi])
+                    for idx in np.ndindex(*tab.shape):
+                        tab[idx] = w(idx[0] + 1, [v + 1 for v in idx[1:-1]], idx[-1] + 1)
+                    tabs.append(tab.ravel(order="F"))
+                wt = np.ascontiguousarray(np.concatenate(tabs))
+                cid = C.c_int32()
+                _lib.check(L.mpbp_add_generic_class(self._h, z, qi, _p(qn, _lib.c_i32p), len(ws), _p(wt, _lib.c_dp), C.byref(cid)))
+                cls[i] = cid.value
+                if ck is not None:
+                    cache[ck] = cid.value
+                continue
             same = all(w is wi[0] for w in wi) or (keys[0] is not None and all(k == keys[0] for k in keys))
             ck = None
             if same and keys[0] is not None:

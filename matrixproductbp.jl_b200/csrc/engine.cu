@@ -50,6 +50,7 @@ struct NodeClass {
   size_t wd_ts = 0;
   double* d_minit = nullptr;
   size_t minit_ts = 0;
+  std::vector<int> gen_ny;  // generic: joint neighbour states with neighbour j removed; gen_ny[z] = all neighbours
 };
 
 struct MsgStore {
@@ -239,6 +240,7 @@ int ensure_arena(mpbp_state* h) {
 
 struct Plan {
   std::vector<BtJob> bt;
+  std::vector<GenJob> gen;
   std::vector<InitJob> init;
   std::vector<std::vector<OpDesc>> levels;  // ops by level (scratch pointers filled per group)
   std::vector<std::vector<int>> capA, capB;  // bond capacities of the operands per op (1 or dmax)
@@ -264,6 +266,15 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
   const int z = c.z, q = c.q, d = h->dmax, L = h->L;
   auto tt = [&](int cap, int ny) { return (size_t)L * cap * cap * ny * q * 8 + 4 * (L + 1) + 8 + 3 * 256; };
   size_t b = 0;
+  if (c.generic) {
+    for (int j = 0; j <= z; ++j) b += tt(d, c.gen_ny[j]);
+    const int qjm = h->qmax;
+    const size_t fin = (size_t)(L + 1) * (d * q) * (d * q) + (size_t)d * d * q * q * q * qjm + (size_t)d * d * q * q * qjm +
+                       (size_t)d * d * q * qjm + 2 * (size_t)d * d * q + (L + 1) + (size_t)(d * q * qjm) * (d * q * qjm);
+    b += (size_t)z * (fin * 8 + 8 * 256) + ((size_t)L * d * q + (size_t)d * d * q * q) * 8 + 2 * 256;
+    if (h->inf_k > 0) b += (size_t)z * (h->slot * 8 + 4 * (L + 1) + 8 + 3 * 256);
+    return b;
+  }
   if (z > 0) b += (size_t)z * tt(d, c.ny[1]);
   b += tt(1, c.ny[0]);
   for (int k = 1; k < z; ++k) b += tt(d, c.ny[k + 1]) + tt(d, c.ny[z - k]) + tt(d, c.ny[z - 1]);
@@ -295,8 +306,91 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
     const int ci = h->class_of_node[i];
     if (ci < 0 || ci >= (int)h->classes.size()) return fail("node %lld has no factor class", (long long)i);
     const NodeClass& c = h->classes[ci];
-    if (c.generic) return fail("generic BPFactor classes are not supported by the device path yet");
     const int z = c.z, q = c.q;
+    if (c.generic) {
+      // exhaustive-trace path (src/mpbp.jl:117-154, src/bp_core.jl:18-93): Kronecker of the other neighbours' messages,
+      // then the same MPEM3->MPEM2 / compress / normalize kernel with the dense factor table as W
+      const int64_t e0g = h->inf_k > 0 ? 0 : h->colptr[i];
+      const int degg = h->inf_k > 0 ? h->inf_k : (int)(h->colptr[i + 1] - h->colptr[i]);
+      if (degg != z) return fail("node %lld has degree %d but its class has z=%d", (long long)i, degg, z);
+      if (q != h->q[i]) return fail("node %lld: class q mismatch", (long long)i);
+      auto make_gen = [&](int skip, int ny) -> TTRef {
+        GenJob gj;
+        memset(&gj, 0, sizeof gj);
+        gj.nk = z;
+        gj.skip = skip;
+        gj.q = q;
+        for (int k = 0; k < z; ++k) {
+          const int64_t eout = h->inf_k > 0 ? 0 : e0g + k;
+          const int64_t ein = h->inf_k > 0 ? 0 : h->rev[eout];
+          gj.qk[k] = c.qn[k];
+          gj.msg[k] = msg_ref(h, h->msg[rb], ein, c.qn[k] * q);
+          gj.psi[k] = h->d_psi + h->psi_off[eout];
+        }
+        gj.out = arena_tt(h, d, ny * q, ok);
+        P.gen.push_back(gj);
+        return gj.out;
+      };
+      for (int j = 0; j < z; ++j) {
+        const int64_t eout = h->inf_k > 0 ? 0 : e0g + j;
+        const int qj = c.qn[j];
+        FinJob fj;
+        memset(&fj, 0, sizeof fj);
+        fj.c = make_gen(j, c.gen_ny[j]);
+        if (h->inf_k > 0 && j < z - 1) {
+          TTRef scratch;
+          scratch.stride = h->sstride;
+          scratch.P = q * qj;
+          scratch.data = (double*)h->arena.take(sizeof(double) * h->slot);
+          scratch.bonds = (int*)h->arena.take(sizeof(int) * (L + 1));
+          scratch.ls = (double*)h->arena.take(sizeof(double));
+          ok = ok && scratch.data && scratch.bonds && scratch.ls;
+          fj.out = scratch;
+        } else {
+          fj.out = msg_ref(h, h->msg[wb], eout, q * qj);
+        }
+        fj.nyc = c.gen_ny[j];
+        fj.q = q;
+        fj.qj = qj;
+        fj.W = c.d_w + c.w_off[j];
+        fj.w_tstride = (int)c.w_ts;
+        fj.phi = h->d_phi + h->phi_off[i];
+        fj.logz_out = h->d_logzij + (h->inf_k > 0 ? j : eout);
+        const size_t dq = (size_t)d * q;
+        fj.rstride = (int)(dq * dq);
+        fj.Rbuf = (double*)h->arena.take(8 * (size_t)(L + 1) * fj.rstride);
+        fj.kdim = (int*)h->arena.take(4 * (L + 1));
+        fj.Bt = (double*)h->arena.take(8 * (size_t)d * d * q * qj * q);
+        fj.S = (double*)h->arena.take(8 * (size_t)d * d * q * q * q * qj);
+        fj.H = (double*)h->arena.take(8 * (size_t)d * d * q * qj);
+        fj.R2 = (double*)h->arena.take(8 * (size_t)(d * q * qj) * (d * q * qj));
+        fj.Pr[0] = (double*)h->arena.take(8 * (size_t)d * d * q);
+        fj.Pr[1] = (double*)h->arena.take(8 * (size_t)d * d * q);
+        ok = ok && fj.Rbuf && fj.kdim && fj.Bt && fj.S && fj.H && fj.R2 && fj.Pr[0] && fj.Pr[1];
+        P.fin.push_back(fj);
+      }
+      BelJob bj;
+      memset(&bj, 0, sizeof bj);
+      bj.full = make_gen(-1, c.gen_ny[z]);
+      bj.ny = c.gen_ny[z];
+      bj.q = q;
+      bj.Wd = c.d_wd;
+      bj.w_tstride = (int)c.wd_ts;
+      bj.phi = h->d_phi + h->phi_off[i];
+      bj.marg = h->d_marg + h->marg_off[i];
+      bj.logz = h->d_logzi + i;
+      bj.bw = (double*)h->arena.take(8 * (size_t)L * d * q);
+      bj.Bt = (double*)h->arena.take(8 * (size_t)d * d * q * q);
+      ok = ok && bj.bw && bj.Bt;
+      P.bel.push_back(bj);
+      FJob f;
+      f.logzi = h->d_logzi + i;
+      f.logzij = h->d_logzij + (h->inf_k > 0 ? 0 : e0g);
+      f.z = z;
+      f.f = h->d_f + i;
+      P.fj.push_back(f);
+      continue;
+    }
     const int64_t e0 = h->inf_k > 0 ? 0 : h->colptr[i];
     const int deg = h->inf_k > 0 ? h->inf_k : (int)(h->colptr[i + 1] - h->colptr[i]);
     if (deg != z) return fail("node %lld has degree %d but its class has z=%d", (long long)i, deg, z);
@@ -594,8 +688,17 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     k_btilde<<<g, NT, 0, st>>>(d_bt, L);
     h->n_launch++;
   }
-  k_init_tt<<<(unsigned)P.init.size(), 64, 0, st>>>(d_init, (int)P.init.size(), L);
-  h->n_launch++;
+  if (!P.gen.empty()) {
+    GenJob* d_gen;
+    if (upload_jobs(h, P.gen, &d_gen)) return 1;
+    dim3 gg((unsigned)P.gen.size(), L);
+    k_generic_kron<<<gg, NT, 0, st>>>(d_gen, L, d, h->d_err);
+    h->n_launch++;
+  }
+  if (!P.init.empty()) {
+    k_init_tt<<<(unsigned)P.init.size(), 64, 0, st>>>(d_init, (int)P.init.size(), L);
+    h->n_launch++;
+  }
   // ---- cavity levels ----
   const size_t persistent = h->arena.used;
   for (size_t lev = 1; lev < P.levels.size(); ++lev) {
@@ -778,7 +881,7 @@ int mpbp_create(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* c
                 const int64_t* rev, int dmax, int device, mpbp_handle* out) {
   if (!out) return fail("null out");
   if (N <= 0 || E2 < 0 || T < 0 || dmax < 1) return fail("invalid sizes N=%lld E2=%lld T=%d dmax=%d", (long long)N, (long long)E2, T, dmax);
-  if (dmax > 32) return fail("dmax=%d exceeds the supported bond capacity 32", dmax);
+  if (dmax > 30) return fail("dmax=%d exceeds the supported bond capacity 30 (shared-memory tiling of the contraction kernels)", dmax);
   mpbp_state* h = new mpbp_state();
   h->device = device;
   h->N = N;
@@ -812,7 +915,7 @@ int mpbp_create(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* c
 int mpbp_create_infinite(int k, int T, int q, int dmax, int device, mpbp_handle* out) {
   if (!out) return fail("null out");
   if (k < 1 || T < 0 || dmax < 1 || q < 1 || q > 8) return fail("invalid arguments");
-  if (dmax > 32) return fail("dmax=%d exceeds the supported bond capacity 32", dmax);
+  if (dmax > 30) return fail("dmax=%d exceeds the supported bond capacity 30 (shared-memory tiling of the contraction kernels)", dmax);
   mpbp_state* h = new mpbp_state();
   h->device = device;
   h->N = 1;
@@ -904,8 +1007,55 @@ int mpbp_add_node_class(mpbp_handle h, int z, int q, const int32_t* qn, int nt, 
   return 0;
 }
 
-int mpbp_add_generic_class(mpbp_handle, int, int, const int32_t*, int, const double*, int32_t*) {
-  return fail("generic BPFactor classes (exhaustive trace, src/bp_core.jl:18-57) are not implemented on the device yet");
+int mpbp_add_generic_class(mpbp_handle h, int z, int q, const int32_t* qn, int nt, const double* wtab, int32_t* class_id) {
+  if (!h || !wtab) return fail("null argument");
+  if (z < 1 || z > GEN_MAXZ) return fail("generic BPFactor classes support degrees 1..%d (the trace is exponential in z)", GEN_MAXZ);
+  if (nt != 1 && nt != h->L) return fail("nt must be 1 or T+1");
+  CUDA_OK(cudaSetDevice(h->device));
+  NodeClass c;
+  c.generic = true;
+  c.z = z;
+  c.q = q;
+  c.nt = nt;
+  c.qn.assign(qn, qn + z);
+  const bool td = nt > 1;
+  size_t Yall = 1;
+  for (int k = 0; k < z; ++k) Yall *= qn[k];
+  const size_t wsz = (size_t)q * Yall * q;  // [x', x_0..x_{z-1}, x]
+  c.gen_ny.resize(z + 1);
+  for (int j = 0; j < z; ++j) c.gen_ny[j] = (int)(Yall / qn[j]);
+  c.gen_ny[z] = (int)Yall;
+  // W_j[x' + q*(x + q*(xj + qj*y))], y = (x_k)_{k != j} first fastest ;  Wd[x' + q*(x + q*yall)]
+  c.w_off.resize(z);
+  size_t tot = 0;
+  for (int j = 0; j < z; ++j) { c.w_off[j] = tot; tot += (size_t)q * q * qn[j] * c.gen_ny[j]; }
+  c.w_ts = td ? tot : 0;
+  std::vector<double> W(tot * nt), Wd((size_t)q * q * Yall * nt);
+  for (int t = 0; t < nt; ++t) {
+    const double* wt = wtab + (size_t)t * wsz;
+    std::vector<int> xs(z);
+    for (size_t yall = 0; yall < Yall; ++yall) {
+      size_t r = yall;
+      for (int k = 0; k < z; ++k) { xs[k] = (int)(r % qn[k]); r /= qn[k]; }
+      for (int x = 0; x < q; ++x)
+        for (int xn = 0; xn < q; ++xn) {
+          const double v = wt[xn + (size_t)q * (yall + Yall * x)];
+          Wd[(size_t)t * q * q * Yall + xn + q * (x + (size_t)q * yall)] = v;
+          for (int j = 0; j < z; ++j) {
+            size_t y = 0, mul = 1;
+            for (int k = 0; k < z; ++k)
+              if (k != j) { y += mul * xs[k]; mul *= qn[k]; }
+            W[(size_t)t * tot + c.w_off[j] + xn + q * (x + (size_t)q * (xs[j] + (size_t)qn[j] * y))] = v;
+          }
+        }
+    }
+  }
+  if (upload(&c.d_w, W.data(), W.size())) return 1;
+  c.wd_ts = td ? (size_t)q * q * Yall : 0;
+  if (upload(&c.d_wd, Wd.data(), Wd.size())) return 1;
+  h->classes.push_back(c);
+  if (class_id) *class_id = (int)h->classes.size() - 1;
+  return 0;
 }
 
 int mpbp_set_node_classes(mpbp_handle h, const int32_t* cls) {

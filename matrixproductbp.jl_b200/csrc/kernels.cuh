@@ -53,6 +53,69 @@ __global__ void __launch_bounds__(NT) k_btilde(const BtJob* jobs, int L) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// generic BPFactor (exhaustive trace, src/bp_core.jl:18-57 / :60-93): Kronecker product of the incoming messages of
+// all neighbours but `skip` (skip = -1: all of them, dummy-neighbour path), reweighted by psi:
+//   out[(m_k)_k, (n_k)_k, y = (x_k)_k, x] = prod_k mu_k[m_k, n_k, x_k, x] * psi_k[x, x_k]      (first k fastest)
+// The dense factor table is applied afterwards by k_finalize / k_belief exactly like prob_y_partial / prob_y.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEN_MAXZ = 8;
+struct GenJob {
+  TTRef msg[GEN_MAXZ];
+  const double* psi[GEN_MAXZ];  // [t][x + q*xk]
+  int qk[GEN_MAXZ];
+  int nk, skip, q;
+  TTRef out;
+};
+__global__ void __launch_bounds__(NT) k_generic_kron(const GenJob* jobs, int L, int dcap, int* err) {
+  const GenJob& jb = jobs[blockIdx.x];
+  const int t = blockIdx.y;
+  int bl[GEN_MAXZ], br[GEN_MAXZ];
+  long long Ml = 1, Mr = 1, Y = 1;
+  for (int k = 0; k < jb.nk; ++k) {
+    if (k == jb.skip) continue;
+    bl[k] = jb.msg[k].bonds[t];
+    br[k] = jb.msg[k].bonds[t + 1];
+    Ml *= bl[k];
+    Mr *= br[k];
+    Y *= jb.qk[k];
+  }
+  if (Ml > dcap || Mr > dcap) {
+    if (threadIdx.x == 0) atomicOr(err, ERR_BOND_OVERFLOW);
+    return;
+  }
+  const int q = jb.q;
+  double* O = jb.out.data + (size_t)t * jb.out.stride;
+  const long long tot = Ml * Mr * Y * q;
+  for (long long idx = threadIdx.x; idx < tot; idx += NT) {
+    long long r = idx;
+    long long m = r % Ml; r /= Ml;
+    long long n = r % Mr; r /= Mr;
+    long long y = r % Y;
+    const int x = (int)(r / Y);
+    double v = 1.0;
+    for (int k = 0; k < jb.nk; ++k) {
+      if (k == jb.skip) continue;
+      const int mk = (int)(m % bl[k]); m /= bl[k];
+      const int nk_ = (int)(n % br[k]); n /= br[k];
+      const int xk = (int)(y % jb.qk[k]); y /= jb.qk[k];
+      const double* A = jb.msg[k].data + (size_t)t * jb.msg[k].stride;
+      v *= A[mk + (size_t)bl[k] * (nk_ + (size_t)br[k] * (xk + jb.qk[k] * x))] * jb.psi[k][(size_t)t * q * jb.qk[k] + x + q * xk];
+    }
+    O[idx] = v;
+  }
+  if (threadIdx.x == 0) {
+    jb.out.bonds[t] = (int)Ml;
+    if (t == L - 1) jb.out.bonds[L] = (int)Mr;
+    if (t == 0) {
+      double ls = 0.0;
+      for (int k = 0; k < jb.nk; ++k)
+        if (k != jb.skip) ls += *jb.msg[k].ls;
+      *jb.out.ls = ls;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // heavy op descriptor
 // ------------------------------------------------------------------------------------------------
 struct OpDesc {
@@ -598,7 +661,8 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
     if (nrm2_all >= 0.0) nrm2 = nrm2_all;  // subspace path: Frobenius norm of the whole matrix
     int k = c;
     if (tr.kind == 1 || tr.kind == 2) {
-      const double lim = tr.eps * sqrt(nrm2);
+      // values below 2e-15 sigma_1 are rounding noise (zero columns of U): TruncThresh(0.0) keeps the numerical rank
+      const double lim = fmax(tr.eps * sqrt(nrm2), 2.0 * JACOBI_ZERO * sig[order[0]]);
       int last = 0;
       for (int i = 0; i < ceff; ++i)
         if (sig[order[i]] > lim) last = i + 1;
@@ -838,7 +902,7 @@ __global__ void __launch_bounds__(NT) k_finalize(const FinJob* jobs, int L, Trun
       for (int i = 0; i < ns; ++i) nrm2 += sig[order[i]] * sig[order[i]];
       int k = ns;
       if (tr.kind == 1 || tr.kind == 2) {
-        const double lim = tr.eps * sqrt(nrm2);
+        const double lim = fmax(tr.eps * sqrt(nrm2), 2.0 * JACOBI_ZERO * sig[order[0]]);
         int last = 0;
         for (int i = 0; i < ns; ++i)
           if (sig[order[i]] > lim) last = i + 1;

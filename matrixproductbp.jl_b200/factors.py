@@ -261,6 +261,20 @@ class DampedFactor(RecursiveBPFactor):
         return (1 - self.p) * self.w(xnext, xneigh, x) + self.p * (xnext == x)
 
 
+class GenericFactor(BPFactor):
+    """wraps any factor so that only its functor is used: forces the exhaustive-trace path (src/test_factors.jl:41-45)"""
+
+    def __init__(self, w):
+        self.w = w
+
+    def key(self):
+        k = self.w.key()
+        return None if k is None else ("Generic", k)
+
+    def __call__(self, xnext, xneigh, x):
+        return self.w(xnext, xneigh, x)
+
+
 # --------------------------------------------------------------------------------------
 # tabulation for the C-ABI (mpbp_add_node_class)
 # --------------------------------------------------------------------------------------

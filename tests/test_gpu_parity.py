@@ -233,6 +233,110 @@ def test_glauber_4regular_bond10_subspace_svd_vs_oracle():
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
 
 
+def test_time_dependent_factors_vs_oracle():
+    # w[i][t] differs over t -> the nt = T+1 table path (time-dependent Pxy / Pyy / W slices)
+    from oracle import factors as OF
+    T, N = 4, 4
+    und = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]
+    go = O.BiDiGraph(N, und)
+    gd = M.IndexedBiDiGraph(N, und)
+    lam = [0.1 + 0.05 * t for t in range(T + 1)]
+    wo = [[OF.SISFactor(lam[t] + 0.01 * i, 0.2, 0.01) for t in range(T + 1)] for i in range(N)]
+    wd = [[M.SISFactor(lam[t] + 0.01 * i, 0.2, 0.01) for t in range(T + 1)] for i in range(N)]
+    phi = [[np.array([0.85, 0.15]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[1][2] = np.array([0.4, 0.9])
+    bo = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
+    bd = M.mpbp(gd, wd, [2] * N, T, phi=phi, dmax=5)
+    tr = M.TruncBond(5)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+@pytest.mark.parametrize("kind", ["pmj", "intglauber"])
+def test_pmj_and_integer_glauber_vs_oracle(kind):
+    # factors whose prob_xy depends on the neighbour index k (glauber_bp.jl:58-91,144-179)
+    T, N = 3, 4
+    und = [(0, 1), (0, 2), (0, 3), (1, 2)]
+    deg = {0: 3, 1: 2, 2: 2, 3: 1}
+    kinds = []
+    for i in range(N):
+        z = deg[i]
+        if kind == "pmj":
+            kinds.append(("pmj", ([1, -1, 1][:z], 0.6, 0.1 * i, 1.0)))
+        else:
+            kinds.append(("intglauber", ([1, -2, 1][:z], 0.1 * i, 0.7)))
+    phi = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=8)
+    tr = M.TruncBond(6)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_nodes_subset_and_visiting_order_vs_oracle():
+    # iterate!(bp; nodes=...) with an explicit (shuffled) visiting order: the level-scheduled device sweep must
+    # equal the serial in-place sweep of src/mpbp.jl:189-192
+    T = 3
+    und = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 0), (1, 3)]
+    N = 5
+    kinds = [("sis", (0.25, 0.1, 0.02))] * N
+    phi = [[np.array([0.7, 0.3]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=4)
+    tr = M.TruncBond(4)
+    order = [3, 0, 4, 1]  # node 2 is never updated
+    for it in range(2):
+        O.iterate(bo, maxiter=1, trunc=otrunc(tr), tol=0.0, nodes=order)
+        M.iterate_(bd, maxiter=1, svd_trunc=tr, tol=0.0, nodes=order, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_glauber_infinite_graph_free_energy_known_answer():
+    # /root/reference/test/glauber_infinite_graph.jl:7-18 inputs, run without damping: f = 0.98812749675847 per node
+    # (derived known answer, SURVEY.md header fact 3(ii)).  The reference test uses TruncThresh(0.0) (no device bond
+    # capacity there); here TruncBondThresh(30, 1e-13): the exact ranks of the X = 8 intermediates can exceed dmax.
+    T, k, m0 = 3, 3, 0.5
+    w = [M.HomogeneousGlauberFactor(1.0, 0.0, 1.0)] * (T + 1)
+    phi = [np.array([(1 + m0) / 2, (1 - m0) / 2]) if t == 0 else np.ones(2) for t in range(T + 1)]
+    phi[1] = np.array([0.4, 0.6])
+    phi[-1] = np.array([0.95, 0.05])
+    bp = M.mpbp_infinite_graph(k, w, 2, phi, dmax=30)
+    iters, cb = M.iterate_(bp, maxiter=150, svd_trunc=M.TruncBondThresh(30, 1e-13), tol=1e-14)
+    assert abs(M.bethe_free_energy(bp) - 0.98812749675847) < 1e-8
+
+
+def test_generic_factor_exhaustive_trace_vs_oracle():
+    # GenericFactor forces the f_bp / f_bp_dummy_neighbor path (reference test/glauber_small_tree.jl:133-169,
+    # src/bp_core.jl:18-93); on a tree with a non-binding truncation it must agree with the oracle's generic path
+    # and with brute force
+    from oracle import factors as OF, exact
+    T, N = 2, 5
+    und = [(0, 1), (1, 2), (1, 3)]
+    rng = np.random.default_rng(7)
+    h = rng.standard_normal(N)
+    go = O.BiDiGraph(N, und)
+    gd = M.IndexedBiDiGraph(N, und)
+    wo = [[OF.GenericFactor(OF.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0))] * (T + 1) for i in range(N)]
+    wd = [[M.GenericFactor(M.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0))] * (T + 1) for i in range(N)]
+    # node 4 is isolated: give it a recursive factor (the reference handles degree 0 through the recursive path)
+    wo[4] = [OF.HomogeneousGlauberFactor(1.0, float(h[4]), 1.0)] * (T + 1)
+    wd[4] = [M.HomogeneousGlauberFactor(1.0, float(h[4]), 1.0)] * (T + 1)
+    phi = [[np.array([0.75, 0.25]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][1] = np.array([1.0, 0.1])
+    phi[0][2] = np.array([0.2, 1.0])
+    bo = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
+    bd = M.mpbp(gd, wd, [2] * N, T, phi=phi, dmax=16)
+    O.iterate(bo, maxiter=4, trunc=OT.TruncThresh(0.0), tol=0.0)
+    M.iterate_(bd, maxiter=4, svd_trunc=M.TruncBondThresh(16, 0.0), tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+    p, Z, logZ = exact.exact_prob(bo)
+    assert abs(-M.bethe_free_energy(bd) - logZ) < 1e-8
+
+
 def test_isolated_node_and_leaf_vs_oracle():
     # degree-0 node (cavity of an empty neighbourhood) next to a 2-chain
     T = 3
