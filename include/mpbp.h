@@ -38,7 +38,7 @@ int mpbp_version(void);
  * Graph in the reference's IndexedBiDiGraph order: directed edge e = position in the CSC of the adjacency
  * matrix (source = column), i.e. sorted by (src,dst); out-edges of node i are colptr[i] .. colptr[i+1]-1,
  * dst[e] their destinations, rev[e] the index of the reverse edge (g.X of src/mpbp.jl:40-58).
- * dmax = capacity of every bond dimension held on the device.  device = CUDA ordinal.
+ * dmax = capacity of every bond dimension held on the device (<= 30).  device = CUDA ordinal.
  * Messages start as flat_mpem2(q_i,q_j,T; d=1) (src/mpems.jl:20), beliefs uniform, f = 0. */
 int mpbp_create(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* colptr, const int64_t* dst,
                 const int64_t* rev, int dmax, int device, mpbp_handle* out);
@@ -68,7 +68,8 @@ int mpbp_add_node_class(mpbp_handle h, int z, int q, const int32_t* qn, int nt, 
 int mpbp_set_node_classes(mpbp_handle h, const int32_t* class_of_node /* N */);
 
 /* Generic BPFactor (src/bp_core.jl:1-57): dense table per node, for t<T+1 (nt = 1 or T+1):
- *   wtab = for t : [q x qn[0] x ... x qn[z-1] x q]   w(x', x_neighbours, x).   Exhaustive-trace path. */
+ *   wtab = for t : [q x qn[0] x ... x qn[z-1] x q]   w(x', x_neighbours, x).   Exhaustive-trace path: degree 1..8, the
+ * product of the other neighbours' bond dimensions must fit dmax (it is d^(z-1), src/bp_core.jl:34). */
 int mpbp_add_generic_class(mpbp_handle h, int z, int q, const int32_t* qn, int nt, const double* wtab,
                            int32_t* class_id);
 

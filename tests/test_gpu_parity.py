@@ -337,6 +337,24 @@ def test_generic_factor_exhaustive_trace_vs_oracle():
     assert abs(-M.bethe_free_energy(bd) - logZ) < 1e-8
 
 
+def test_k4_bond16_full_size_paths_vs_oracle():
+    # complete graph K4, T=5, TruncBond(16): at the middle cuts D = 256 -> H=64 flat-tree QR, TSQR split (few ops per
+    # launch) and the subspace-iteration SVD (d~X = 96..128 > 48) all run inside a real BP iteration
+    T, N, d = 5, 4, 16
+    und = [(a, b) for a in range(N) for b in range(a + 1, N)]
+    kinds = [("glauber", (0.4, 0.05 * (i + 1), 1.0)) for i in range(N)]
+    phi = [[np.array([0.2, 0.8]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][3] = np.array([0.6, 0.3])
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=d)
+    tr = M.TruncBond(d)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0, schedule="parallel")
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule="parallel")
+    assert max(bd.get_message(0)[k].shape[0] for k in range(T + 1)) == d  # the cap is reached
+    assert bd.counters()["svd_calls"] > 0  # the subspace path ran
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
 def test_isolated_node_and_leaf_vs_oracle():
     # degree-0 node (cavity of an empty neighbourhood) next to a 2-chain
     T = 3
