@@ -100,6 +100,7 @@ struct mpbp_state {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // extra streams: op groups of one level run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   double nstreams = 4;
+  double damp = 0.0;  // set by mpbp_iterate for the duration of the call
   // options
   double arena_gb = 0;       // 0 = auto
   double qr_fill = 148;      // CTAs that fill the GPU for the QR kernel (H = 64: one per SM); fewer ops per launch -> TSQR split
@@ -174,6 +175,7 @@ int common_init(mpbp_state* h) {
     CUDA_OK(cudaFuncSetAttribute(k_qr_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_jacobi_project, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_damp, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_pair_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
   }
@@ -245,6 +247,7 @@ struct Plan {
   std::vector<std::vector<OpDesc>> levels;  // ops by level (scratch pointers filled per group)
   std::vector<std::vector<int>> capA, capB;  // bond capacities of the operands per op (1 or dmax)
   std::vector<FinJob> fin;
+  std::vector<DampJob> damp;  // one per FinJob when damp > 0 (same order)
   std::vector<BelJob> bel;
   std::vector<FJob> fj;
 };
@@ -273,6 +276,10 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
                        (size_t)d * d * q * qjm + 2 * (size_t)d * d * q + (L + 1) + (size_t)(d * q * qjm) * (d * q * qjm);
     b += (size_t)z * (fin * 8 + 8 * 256) + ((size_t)L * d * q + (size_t)d * d * q * q) * 8 + 2 * 256;
     if (h->inf_k > 0) b += (size_t)z * (h->slot * 8 + 4 * (L + 1) + 8 + 3 * 256);
+    if (h->damp > 0.0) {
+      const size_t b2 = 2 * (size_t)d, Pm = (size_t)h->qmax * h->qmax;
+      b += (size_t)z * (h->slot * 8 + 8 * ((size_t)(L + 1) * b2 * b2 + b2 * Pm * b2 + 2 * d * b2 * Pm + (d * Pm) * (d * Pm) + 2 * d * b2) + 4 * (L + 1) * 2 + 16 * 256);
+    }
     return b;
   }
   if (z > 0) b += (size_t)z * tt(d, c.ny[1]);
@@ -287,6 +294,10 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
   b += (size_t)z * (fin * 8 + 8 * 256);
   b += ((size_t)L * d * q + (size_t)d * d * q * q) * 8 + 2 * 256;
   if (h->inf_k > 0) b += (size_t)z * (h->slot * 8 + 4 * (L + 1) + 8 + 3 * 256);
+  if (h->damp > 0.0) {
+    const size_t b2 = 2 * (size_t)d, Pm = (size_t)h->qmax * h->qmax;
+    b += (size_t)z * (h->slot * 8 + 8 * ((size_t)(L + 1) * b2 * b2 + b2 * Pm * b2 + 2 * d * b2 * Pm + (d * Pm) * (d * Pm) + 2 * d * b2) + 4 * (L + 1) * 2 + 16 * 256);
+  }
   return b;
 }
 
@@ -297,6 +308,41 @@ size_t op_scratch_bytes(const mpbp_state* h, int capA, int capB, int X) {
   (void)nch;
   size_t dbl = L * D * D + mrows * D + QR_NSPLIT_MAX * D * D + d * D * X + D * d * X + (d * X) * (d * X) + 2 * d * D;
   return dbl * 8 + 4 * (L + 1) + 10 * 256;
+}
+
+// damp > 0: the finalised message goes to a scratch slot, then k_damp combines it with the old message IN PLACE on the
+// write-buffer slot (which holds the old message: same buffer for the sequential schedule, a copy for the Jacobi one)
+void add_damp_job(mpbp_state* h, Plan& P, FinJob& fj, const TTRef& dest, bool& ok) {
+  const int L = h->L, d = h->dmax;
+  const int P_ = fj.q * fj.qj;
+  TTRef scratch;
+  scratch.stride = h->sstride;
+  scratch.P = P_;
+  scratch.data = (double*)h->arena.take(sizeof(double) * h->slot);
+  scratch.bonds = (int*)h->arena.take(sizeof(int) * (L + 1));
+  scratch.ls = (double*)h->arena.take(sizeof(double));
+  ok = ok && scratch.data && scratch.bonds && scratch.ls;
+  fj.out = scratch;
+  DampJob dj;
+  memset(&dj, 0, sizeof dj);
+  dj.a = scratch;
+  dj.b = dest;
+  dj.out = dest;
+  dj.q = fj.q;
+  dj.qj = fj.qj;
+  dj.coef = h->damp / (1.0 - h->damp);
+  const size_t b2 = 2 * (size_t)d;
+  dj.lstride = (int)(b2 * b2);
+  dj.Lbuf = (double*)h->arena.take(8 * (size_t)(L + 1) * dj.lstride);
+  dj.r = (int*)h->arena.take(4 * (L + 1));
+  dj.S = (double*)h->arena.take(8 * b2 * P_ * b2);
+  dj.G = (double*)h->arena.take(8 * (size_t)d * b2 * P_);
+  dj.M2 = (double*)h->arena.take(8 * (size_t)d * P_ * b2);
+  dj.R2 = (double*)h->arena.take(8 * (size_t)(d * P_) * (d * P_));
+  dj.Pc[0] = (double*)h->arena.take(8 * (size_t)d * b2);
+  dj.Pc[1] = (double*)h->arena.take(8 * (size_t)d * b2);
+  ok = ok && dj.Lbuf && dj.r && dj.S && dj.G && dj.M2 && dj.R2 && dj.Pc[0] && dj.Pc[1];
+  P.damp.push_back(dj);
 }
 
 int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, Plan& P) {
@@ -337,6 +383,9 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
         FinJob fj;
         memset(&fj, 0, sizeof fj);
         fj.c = make_gen(j, c.gen_ny[j]);
+        fj.q = q;
+        fj.qj = qj;
+        // (damp is ignored on the generic path, exactly like src/mpbp.jl:117-138)
         if (h->inf_k > 0 && j < z - 1) {
           TTRef scratch;
           scratch.stride = h->sstride;
@@ -475,7 +524,11 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
       FinJob fj;
       memset(&fj, 0, sizeof fj);
       fj.c = dest[j];
-      if (h->inf_k > 0 && j < z - 1) {
+      fj.q = q;
+      fj.qj = qj;
+      if (h->damp > 0.0) {
+        add_damp_job(h, P, fj, msg_ref(h, h->msg[wb], eout, q * qj), ok);
+      } else if (h->inf_k > 0 && j < z - 1) {
         // only the last recomputation stays in bp.mu[1] (src/infinite_graph.jl + recursive_bp_factor.jl:154-158)
         TTRef scratch;
         scratch.stride = h->sstride;
@@ -819,6 +872,26 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
       ev_end(h, st);
       h->n_launch++;
     }
+    if (!P.damp.empty()) {
+      DampJob* d_damp;
+      if (upload_jobs(h, P.damp, &d_damp)) return 1;
+      const int P2 = qm * qm;
+      const int dvrows = std::max(64, std::min(QR_MAX_M, 2 * d * P2));
+      const int cpcap = std::max(2 * d, d * P2);
+      const size_t dfixed = (size_t)cpcap + (cpcap + 1) / 2 + 1;
+      size_t djac = std::max<size_t>((size_t)d * P2 * 2 * d, 2 * (size_t)(d + 1));
+      const size_t dqrd = qr_shared_doubles(dvrows);
+      if ((dqrd + dfixed + djac) * 8 > (size_t)h->max_smem) djac = (size_t)h->max_smem / 8 - dqrd - dfixed;
+      const size_t dsm = (dqrd + dfixed + djac) * 8;
+      if (h->inf_k > 0) {
+        // the k recomputed messages are damped one after the other against the evolving bp.mu[1] (set_msg! inside the j loop)
+        for (size_t j = 0; j < P.damp.size(); ++j) k_damp<<<1, NT, dsm, st>>>(d_damp + j, L, tr, d, dvrows, (int)djac, h->d_err);
+        h->n_launch += (double)P.damp.size();
+      } else {
+        k_damp<<<(unsigned)P.damp.size(), NT, dsm, st>>>(d_damp, L, tr, d, dvrows, (int)djac, h->d_err);
+        h->n_launch++;
+      }
+    }
     const size_t bsm = 2 * (size_t)d * qm * 8;
     ev_begin(h, F_BEL, st);
     k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
@@ -1143,7 +1216,9 @@ int mpbp_iterate(mpbp_handle h, int maxiter, int trunc_kind, int trunc_d, double
                  int schedule, const int64_t* nodes_in, int64_t n_nodes, const int64_t* order, const double* obs,
                  int* iters, double* deltas) {
   if (!h) return fail("null handle");
-  if (damp != 0.0) return fail("damp > 0 (set_msg! damping, src/recursive_bp_factor.jl:172-176) is not implemented on the device yet");
+  if (!(damp >= 0.0 && damp < 1.0)) return fail("damp must satisfy 0 <= damp < 1 (src/recursive_bp_factor.jl:169)");
+  if (h->L > DAMP_MAXL && damp > 0.0) return fail("damping supports T+1 <= %d", DAMP_MAXL);
+  h->damp = damp;
   if (trunc_kind < 0 || trunc_kind > 2) return fail("unknown truncation kind %d", trunc_kind);
   if ((trunc_kind == MPBP_TRUNC_BOND || trunc_kind == MPBP_TRUNC_BOND_THRESH) && trunc_d > h->dmax)
     return fail("TruncBond(%d) exceeds the device bond capacity dmax=%d", trunc_d, h->dmax);

@@ -992,6 +992,224 @@ __global__ void __launch_bounds__(NT) k_finalize(const FinJob* jobs, int L, Trun
 }
 
 // ------------------------------------------------------------------------------------------------
+// damping (set_msg!, src/recursive_bp_factor.jl:168-179):  mu <- normalize!(compress!(mu_new + c * mu_old; svd_trunc)),
+// c = damp/(1-damp), both operands normalised.  The sum is the block-diagonal train of bond a+b (TensorTrains._compose);
+// compress! = un-truncated R->L sweep (triangular factors only) + truncating L->R sweep, same scheme as the op.
+// One CTA per edge; `b` and `out` may be the same slot (in-place on the old message).
+// ------------------------------------------------------------------------------------------------
+struct DampJob {
+  TTRef a, b, out;
+  int q, qj;
+  double coef;
+  double* Lbuf;  // L_t at Lbuf + t*lstride, column-major bl_t x r_t
+  int lstride;
+  int* r;        // [L+1]
+  double* S;     // (r*P) x bl row-major scratch
+  double* G;     // [mt, n, p]
+  double* M2;    // column-major (dt*P) x r
+  double* R2;    // QR pre-reduction when r > dt*P
+  double* Pc[2];
+};
+constexpr int DAMP_MAXL = 192;  // static shared memory must stay below the 2 KB head-room left for it
+
+__global__ void __launch_bounds__(NT) k_damp(const DampJob* jobs, int L, Trunc tr, int dcap, int vrows, int jac_doubles, int* err) {
+  extern __shared__ double smem[];
+  __shared__ int flag, s_keep;
+  __shared__ double red[NW + 1];
+  __shared__ double s_ls;
+  __shared__ int ba[DAMP_MAXL + 1], bb[DAMP_MAXL + 1];
+  const DampJob& jb = jobs[blockIdx.x];
+  const int P = jb.q * jb.qj;
+  double* qrs = smem;
+  double* jsm = smem + qr_shared_doubles(vrows);
+  for (int i = threadIdx.x; i <= L; i += NT) {
+    ba[i] = jb.a.bonds[i];
+    bb[i] = jb.b.bonds[i];
+  }
+  __syncthreads();
+  const double fa = exp(*jb.a.ls), fb = jb.coef * exp(*jb.b.ls);
+  // element (m, n, p) of site t of the sum train
+  auto site = [&](int t, int m, int n, int p) -> double {
+    const int al = ba[t], ar = ba[t + 1], bl = bb[t], br = bb[t + 1];
+    const double* A = jb.a.data + (size_t)t * jb.a.stride;
+    const double* B = jb.b.data + (size_t)t * jb.b.stride;
+    const bool first = (t == 0), last = (t == L - 1);
+    if (first && last) return fa * A[p] + fb * B[p];
+    if (first) return n < ar ? fa * A[(size_t)al * (n + ar * p)] : fb * B[(size_t)bl * ((n - ar) + br * p)];
+    if (last) return m < al ? A[m + (size_t)al * ar * p] : B[(m - al) + (size_t)bl * br * p];
+    if (m < al && n < ar) return A[m + (size_t)al * (n + ar * p)];
+    if (m >= al && n >= ar) return B[(m - al) + (size_t)bl * ((n - ar) + br * p)];
+    return 0.0;
+  };
+  auto sbl = [&](int t) { return t == 0 ? 1 : ba[t] + bb[t]; };
+  auto sbr = [&](int t) { return t == L - 1 ? 1 : ba[t + 1] + bb[t + 1]; };
+  if (threadIdx.x == 0) {
+    jb.r[L] = 1;
+    s_ls = 0.0;
+  }
+  __syncthreads();
+  // ---------------- sweep 1 (R->L): L_t with  K_t ... K_L = L_t * (isometry) ----------------
+  for (int t = L - 1; t >= 1; --t) {
+    const int bl = sbl(t), br = sbr(t), rn = jb.r[t + 1];
+    const double* Ln = jb.Lbuf + (size_t)(t + 1) * jb.lstride;  // br x rn (unused for t = L-1)
+    const int rows = rn * P;
+    for (int idx = threadIdx.x; idx < rows * bl; idx += NT) {
+      const int m = idx % bl, row = idx / bl, rr = row % rn, p = row / rn;
+      double acc = 0.0;
+      if (t == L - 1) acc = site(t, m, 0, p);
+      else
+        for (int n = 0; n < br; ++n) acc += site(t, m, n, p) * Ln[n + (size_t)br * rr];
+      jb.S[idx] = acc;
+    }
+    __syncthreads();
+    double* Lt = jb.Lbuf + (size_t)t * jb.lstride;
+    qr_r_cta(jb.S, rows, bl, bl, Lt, bl, true, qrs, vrows);
+    if (threadIdx.x == 0) jb.r[t] = min(rows, bl);
+    __syncthreads();
+  }
+  // ---------------- sweep 2 (L->R): truncating ----------------
+  if (threadIdx.x == 0) jb.out.bonds[0] = 1;
+  __syncthreads();
+  int dt = 1;
+  for (int t = 0; t < L; ++t) {
+    const int bl = sbl(t), br = sbr(t);
+    const double* Pc = (t == 0) ? nullptr : jb.Pc[(t - 1) & 1];  // dt x bl
+    for (int idx = threadIdx.x; idx < dt * br * P; idx += NT) {
+      const int mt = idx % dt, n = (idx / dt) % br, p = idx / (dt * br);
+      double acc = 0.0;
+      if (!Pc) acc = site(t, 0, n, p);
+      else
+        for (int m = 0; m < bl; ++m) acc += Pc[mt + (size_t)dt * m] * site(t, m, n, p);
+      jb.G[idx] = acc;
+    }
+    __syncthreads();
+    double* O = jb.out.data + (size_t)t * jb.out.stride;
+    if (t == L - 1) {
+      double mx = 0.0;
+      for (int idx = threadIdx.x; idx < dt * P; idx += NT) mx = fmax(mx, fabs(jb.G[idx]));
+      mx = block_max(mx, red);
+      const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+      for (int idx = threadIdx.x; idx < dt * P; idx += NT) O[idx] = jb.G[idx] * f;
+      if (threadIdx.x == 0) {
+        jb.out.bonds[L] = 1;
+        if (f != 1.0) s_ls += log(mx);
+      }
+      __syncthreads();
+      break;
+    }
+    const int rn = jb.r[t + 1];
+    const double* Ln = jb.Lbuf + (size_t)(t + 1) * jb.lstride;  // br x rn
+    const int p_rows = dt * P;
+    for (int idx = threadIdx.x; idx < p_rows * rn; idx += NT) {
+      const int a = idx % p_rows, rr = idx / p_rows, mt = a % dt, p = a / dt;
+      double acc = 0.0;
+      for (int n = 0; n < br; ++n) acc += jb.G[mt + (size_t)dt * (n + (size_t)br * p)] * Ln[n + (size_t)br * rr];
+      jb.M2[idx] = acc;
+    }
+    __syncthreads();
+    int c = rn;
+    double* A = jb.M2;
+    if (c > p_rows) {
+      qr_r_cta(jb.M2, c, p_rows, p_rows, jb.R2, p_rows, false, qrs, vrows);
+      A = jb.R2;
+      c = p_rows;
+    }
+    const int cp = max(c, p_rows);
+    double* sig = jsm;
+    int* order = reinterpret_cast<int*>(jsm + cp);
+    double* cache = jsm + cp + (cp + 1) / 2 + 1;
+    if ((long long)p_rows * c <= jac_doubles) {
+      for (int idx = threadIdx.x; idx < p_rows * c; idx += NT) cache[idx] = A[idx];
+      A = cache;
+      __syncthreads();
+    }
+    const int sweeps = jacobi_cols(A, p_rows, c, p_rows, &flag);
+    if (sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
+    jacobi_sort(A, p_rows, c, p_rows, sig, order);
+    if (threadIdx.x == 0) {
+      double nrm2 = 0.0;
+      for (int i = 0; i < c; ++i) nrm2 += sig[i] * sig[i];
+      int kk = c;
+      if (tr.kind == 1 || tr.kind == 2) {
+        const double lim = fmax(tr.eps * sqrt(nrm2), 2.0 * JACOBI_ZERO * sig[order[0]]);
+        int last = 0;
+        for (int i = 0; i < c; ++i)
+          if (sig[order[i]] > lim) last = i + 1;
+        kk = last > 0 ? last : 1;
+      }
+      if (tr.kind == 0 || tr.kind == 2) kk = min(kk, tr.d);
+      if (kk > dcap) {
+        atomicOr(err, ERR_BOND_OVERFLOW);
+        kk = dcap;
+      }
+      if (!(nrm2 == nrm2)) atomicOr(err, ERR_NAN);
+      s_keep = kk;
+      jb.out.bonds[t + 1] = kk;
+    }
+    __syncthreads();
+    const int keep = s_keep;
+    normalize_cols(A, p_rows, c, sig);
+    for (int idx = threadIdx.x; idx < dt * keep * P; idx += NT) {
+      const int mt = idx % dt, kk = (idx / dt) % keep, p = idx / (dt * keep);
+      O[idx] = A[(mt + dt * p) + (size_t)order[kk] * p_rows];
+    }
+    double* Pn = jb.Pc[t & 1];
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < keep * br; idx += NT) {
+      const int kk = idx % keep, n = idx / keep;
+      const double* u = A + (size_t)order[kk] * p_rows;
+      double acc = 0.0;
+      for (int p = 0; p < P; ++p)
+        for (int mt = 0; mt < dt; ++mt) acc += u[mt + dt * p] * jb.G[mt + (size_t)dt * (n + (size_t)br * p)];
+      Pn[idx] = acc;
+      mx = fmax(mx, fabs(acc));
+    }
+    mx = block_max(mx, red);
+    if (mx > 0.0 && isfinite(mx)) {
+      const double f = 1.0 / mx;
+      for (int idx = threadIdx.x; idx < keep * br; idx += NT) Pn[idx] *= f;
+      if (threadIdx.x == 0) s_ls += log(mx);
+    }
+    __syncthreads();
+    dt = keep;
+  }
+  // ---------------- normalize! ----------------
+  {
+    double* l0 = jsm;
+    double* l1 = jsm + dcap + 1;
+    if (threadIdx.x == 0) l0[0] = 1.0;
+    __syncthreads();
+    double logZ = 0.0;
+    for (int t = 0; t < L; ++t) {
+      const int bl = jb.out.bonds[t], br = jb.out.bonds[t + 1];
+      const double* O = jb.out.data + (size_t)t * jb.out.stride;
+      double mx = 0.0;
+      for (int n = threadIdx.x; n < br; n += NT) {
+        double acc = 0.0;
+        for (int pp = 0; pp < P; ++pp)
+          for (int m = 0; m < bl; ++m) acc += l0[m] * O[m + (size_t)bl * (n + br * pp)];
+        l1[n] = acc;
+        mx = fmax(mx, fabs(acc));
+      }
+      mx = block_max(mx, red);
+      const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+      for (int n = threadIdx.x; n < br; n += NT) l1[n] *= f;
+      if (f != 1.0) logZ += log(mx);
+      __syncthreads();
+      double* tmp = l0;
+      l0 = l1;
+      l1 = tmp;
+    }
+    if (threadIdx.x == 0) {
+      const double z = l0[0];
+      logZ += log(fabs(z));
+      *jb.out.ls = -logZ;
+      if (!(logZ == logZ) || !(z > 0.0)) atomicOr(err, ERR_NAN);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // belief of node i from `full`: marginals + log z_i, one CTA per node
 // ------------------------------------------------------------------------------------------------
 struct BelJob {

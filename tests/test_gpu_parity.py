@@ -355,6 +355,39 @@ def test_k4_bond16_full_size_paths_vs_oracle():
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
 
 
+@pytest.mark.parametrize("schedule", ["sequential", "parallel"])
+def test_damping_vs_oracle(schedule):
+    # set_msg! with damp > 0 (src/recursive_bp_factor.jl:168-179): TT sum of new and old message + compress! + normalize!
+    T = 4
+    und = [(0, 1), (0, 2), (1, 2), (2, 3), (3, 4)]
+    N = 5
+    kinds = [("sis", (0.2 + 0.02 * i, 0.12, 0.01)) for i in range(N)]
+    phi = [[np.array([0.87, 0.13]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][3] = np.array([0.2, 1.0])
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=4)
+    tr = M.TruncBond(3)
+    O.iterate(bo, maxiter=4, trunc=otrunc(tr), tol=0.0, damp=0.3, schedule=schedule)
+    M.iterate_(bd, maxiter=4, svd_trunc=tr, tol=0.0, damp=0.3, shuffle_nodes=False, schedule=schedule)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_damping_infinite_graph_vs_oracle():
+    # reference test/glauber_infinite_graph.jl:22 iterates the infinite graph with damp = 0.1: the k recomputed messages
+    # are damped one after the other against the evolving bp.mu[1]
+    from oracle import factors as OF
+    T, k, m0 = 3, 3, 0.5
+    phi = [np.array([(1 + m0) / 2, (1 - m0) / 2]) if t == 0 else np.ones(2) for t in range(T + 1)]
+    phi[1] = np.array([0.4, 0.6])
+    phi[-1] = np.array([0.95, 0.05])
+    bo = O.mpbp_infinite_graph(k, [OF.HomogeneousGlauberFactor(1.0, 0.1, 1.0)] * (T + 1), 2, [p.copy() for p in phi])
+    bd = M.mpbp_infinite_graph(k, [M.HomogeneousGlauberFactor(1.0, 0.1, 1.0)] * (T + 1), 2, phi, dmax=6)
+    O.iterate(bo, maxiter=5, trunc=OT.TruncBond(6), tol=0.0, damp=0.1)
+    M.iterate_(bd, maxiter=5, svd_trunc=M.TruncBond(6), tol=0.0, damp=0.1)
+    assert np.max(np.abs(np.array(O.beliefs(bo)[0]) - M.beliefs(bd)[0])) < TOL
+    assert abs(O.bethe_free_energy(bo) - M.bethe_free_energy(bd)) < TOL
+
+
 def test_isolated_node_and_leaf_vs_oracle():
     # degree-0 node (cavity of an empty neighbourhood) next to a 2-chain
     T = 3
@@ -401,4 +434,4 @@ def test_errors_are_loud():
     with pytest.raises(M.MPBPError):
         M.iterate_(bp, maxiter=1, svd_trunc=M.TruncBond(5))  # exceeds dmax
     with pytest.raises(M.MPBPError):
-        M.iterate_(bp, maxiter=1, svd_trunc=M.TruncBond(2), damp=0.5)  # not implemented -> loud
+        M.iterate_(bp, maxiter=1, svd_trunc=M.TruncBond(2), damp=1.5)  # invalid damping -> loud
