@@ -304,8 +304,6 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
 size_t op_scratch_bytes(const mpbp_state* h, int capA, int capB, int X) {
   const size_t D = (size_t)capA * capB, d = h->dmax, L = h->L;
   const size_t mrows = D * X;
-  const size_t nch = (mrows + QR_MAX_M - 1) / QR_MAX_M;
-  (void)nch;
   size_t dbl = L * D * D + mrows * D + QR_NSPLIT_MAX * D * D + d * D * X + D * d * X + (d * X) * (d * X) + 2 * d * D;
   return dbl * 8 + 4 * (L + 1) + 10 * 256;
 }
@@ -774,7 +772,6 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     while (i0 < ops.size()) {
       h->arena.used = persistent;
       size_t i1 = i0;
-      int maxD = 1, maxX = 1, maxNy = 1, maxq = 1;
       // reserve room for the descriptor array first
       OpDesc* d_ops = (OpDesc*)h->arena.take(sizeof(OpDesc) * (ops.size() - i0));
       if (!d_ops) return fail("arena exhausted (op descriptors)");
@@ -786,12 +783,10 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         if (h->arena.used + need > h->arena.cap) break;
         const size_t D = (size_t)ca * cb;
         const size_t mrows = D * X;
-        const size_t nch = (mrows + QR_MAX_M - 1) / QR_MAX_M;
         op.r = (int*)h->arena.take(4 * (L + 1));
         op.Lstride = (long long)(D * D);
         op.Lbuf = (double*)h->arena.take(8 * (size_t)L * D * D);
         op.M = (double*)h->arena.take(8 * mrows * D);
-        (void)nch;
         op.Ms = (double*)h->arena.take(8 * (size_t)QR_NSPLIT_MAX * D * D);
         op.G = (double*)h->arena.take(8 * (size_t)d * D * X);
         op.M2T = (double*)h->arena.take(8 * D * (size_t)d * X);
@@ -799,10 +794,6 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         op.Pc[0] = (double*)h->arena.take(8 * (size_t)d * D);
         op.Pc[1] = (double*)h->arena.take(8 * (size_t)d * D);
         if (!op.r || !op.Lbuf || !op.M || !op.Ms || !op.G || !op.M2T || !op.R2 || !op.Pc[0] || !op.Pc[1]) break;
-        maxD = std::max(maxD, (int)D);
-        maxX = std::max(maxX, X);
-        maxNy = std::max(maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
-        maxq = std::max(maxq, op.q);
         ++i1;
       }
       if (i1 == i0) return fail("arena too small for a single op (need %.1f MB)", op_scratch_bytes(h, d, d, ops[i0].nyo * ops[i0].q) / 1e6);
@@ -1502,10 +1493,12 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
 }
 
 // ---- test hooks (unit tests of the two numerical kernels through the C ABI) ----
+}  // extern "C"
 __global__ void __launch_bounds__(NT) k_test_qr(double* A, int m, int n, double* R, int vrows) {
   extern __shared__ double smem[];
   qr_r_cta(A + (size_t)blockIdx.x * m * n, m, n, n, R + (size_t)blockIdx.x * min(m, n) * n, n, false, smem, vrows);
 }
+extern "C" {
 int mpbp_test_qr(const double* A, int batch, int m, int n, double* R) {
   if (m > QR_MAX_M || n > NT * QR_MAX_CPT + QB) return fail("test_qr: size out of range");
   double *dA, *dR;
@@ -1574,7 +1567,8 @@ int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, 
 }
 __global__ void __launch_bounds__(NT) k_test_svd(const double* M, int p, int n, Trunc tr, int jac_doubles, double* scratch,
                                                  size_t scratch_per, double* U, double* S, int* err, double* stats) {
-  extern __shared__ double smem[];
+  extern __shared__ double smem_tsvd[];
+  double* smem = smem_tsvd;
   __shared__ int flag, s_done;
   __shared__ double red[NW + 1];
   const double* Mb = M + (size_t)blockIdx.x * p * n;
@@ -1652,7 +1646,8 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
 }
 __global__ void __launch_bounds__(NT) k_test_jacobi(double* A, int p, int c, double* sig, int* order) {
   __shared__ int flag;
-  extern __shared__ double smem[];
+  extern __shared__ double smem_tjac[];
+  double* smem = smem_tjac;
   double* a = A + (size_t)blockIdx.x * p * c;
   jacobi_cols(a, p, c, p, &flag);
   double* s = smem;
