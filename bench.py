@@ -146,7 +146,7 @@ def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     import mpbp_b200 as M
     from mpbp_b200 import _lib
-    from mpbp_b200.dist import CudaBackend, DistMPBP, LocalProblem, partition_contiguous
+    from mpbp_b200.dist import CudaBackend, DistMPBP, LocalProblem, partition_balanced
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -154,7 +154,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     T, d = args.T, args.d
     ntot, und = make_workload(args.nodes_per_gpu * world)
-    owner = partition_contiguous(ntot, world)
+    owner = partition_balanced(ntot, und, world)
     lp = LocalProblem(ntot, und, owner, rank)
     g = M.IndexedBiDiGraph(len(lp.nodes), lp.local_und)
     lp.build_exchange(g.src, g.dst, world)
@@ -171,6 +171,9 @@ def run_gpu(args, rank, world, local_rank):
     bp.set_stream(stream.cuda_stream)
     if args.arena_gb > 0:
         bp.set_option("arena_gb", args.arena_gb)
+    for kv in args.set:  # engine tuning knobs (mpbp_set_option), e.g. --set level_balance=0
+        k, v = kv.split("=")
+        bp.set_option(k, float(v))
     backend = CudaBackend(bp, lp.owned_local, M.TruncBond(d))
     drv = DistMPBP(lp, backend, dist if world > 1 else None, device=f"cuda:{local_rank}")
     degs_owned = np.array([g.degree(int(i)) for i in lp.owned_local])
@@ -268,7 +271,7 @@ def run_gpu(args, rank, world, local_rank):
                                          "configs[2]'s N=1e5 does not fit one GPU (261 GB of messages) nor the time budget",
                                 nodes_per_gpu=args.nodes_per_gpu, schedule="parallel (Jacobi), one halo exchange per step",
                                 l2="working set per step >> L2 (126 MB): every heavy op streams ~70 MB of scratch",
-                                parallelism=f"node partition x{world}"),
+                                parallelism=f"node partition x{world} (cost-balanced by degree)"),
                     clocks=clocks,
                     e2e=dict(value=edges_total / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=launches,
@@ -297,6 +300,7 @@ def main():
     ap.add_argument("--d", type=int, default=20)
     ap.add_argument("--arena-gb", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--set", action="append", default=[], metavar="OPTION=VALUE")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -100,6 +100,7 @@ struct mpbp_state {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // extra streams: op groups of one level run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   double nstreams = 4;
+  double level_balance = 1;  // stagger the cavity levels of the nodes of a chunk so that every round carries similar work
   double damp = 0.0;  // set by mpbp_iterate for the duration of the call
   // options
   double arena_gb = 0;       // 0 = auto
@@ -343,10 +344,68 @@ void add_damp_job(mpbp_state* h, Plan& P, FinJob& fj, const TTRef& dest, bool& o
   P.damp.push_back(dj);
 }
 
+// Work (~ D^2 X, the QR and SVD cost of an op up to a constant) that a degree-z node of class c puts on each
+// level of its cavity DAG; mirrors the level assignment of build_plan below.
+std::vector<double> node_level_cost(const NodeClass& c, int d) {
+  const int z = c.z, q = c.q;
+  std::vector<double> w(z + 1, 0.0);
+  auto cost = [&](int ca, int cb, int ny) { return (double)ca * cb * ca * cb * ny * q; };
+  if (z == 1) w[1] += cost(d, 1, c.ny[1]);
+  if (z < 2) return w;
+  for (int k = 1; k < z; ++k) w[k] += cost(d, d, c.ny[k + 1]);
+  w[z] += cost(d, 1, c.ny[z]);
+  for (int k = z - 1; k >= 1; --k) w[z - k] += cost(d, k == z - 1 ? 1 : d, c.ny[z - k]);
+  for (int k = 1; k < z; ++k) w[std::max(k - 1, z - k - 1) + 1] += cost(d, k == z - 1 ? 1 : d, c.ny[z - 1]);
+  return w;
+}
+
+// Level offsets: the cavity DAG of a degree-z node has z levels, and the nodes of a chunk are independent, so node i
+// may run its level l in round l + off[i] for any 0 <= off[i] <= zmax - z_i.  Greedy, deepest nodes first: each node
+// takes the offset where its work overlaps least with the work already placed, so that the deep levels of the few
+// high-degree nodes share their rounds with the bulk of the low-degree ones instead of running alone on an
+// under-filled GPU.  The per-node order of operations (hence the result) is unchanged.
+std::vector<int> plan_level_offsets(const mpbp_state* h, const std::vector<int64_t>& nodes) {
+  std::vector<int> off(nodes.size(), 0);
+  if (h->level_balance <= 0 || nodes.size() < 2) return off;
+  int zmax = 0;
+  std::vector<size_t> order;
+  for (size_t k = 0; k < nodes.size(); ++k) {
+    const int ci = h->class_of_node[nodes[k]];
+    if (ci < 0 || ci >= (int)h->classes.size() || h->classes[ci].generic) continue;
+    zmax = std::max(zmax, h->classes[ci].z);
+    order.push_back(k);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+    return h->classes[h->class_of_node[nodes[a]]].z > h->classes[h->class_of_node[nodes[b]]].z;
+  });
+  std::vector<double> load(zmax + 1, 0.0);
+  std::map<int, std::vector<double>> wcache;
+  for (size_t k : order) {
+    const int ci = h->class_of_node[nodes[k]];
+    const NodeClass& c = h->classes[ci];
+    auto it = wcache.find(ci);
+    if (it == wcache.end()) it = wcache.emplace(ci, node_level_cost(c, h->dmax)).first;
+    const std::vector<double>& w = it->second;
+    int best = 0;
+    double bestv = -1.0;
+    for (int o = 0; o + c.z <= zmax; ++o) {
+      double v = 0.0;
+      for (int l = 1; l <= c.z; ++l) v += load[l + o] * w[l];
+      if (bestv < 0.0 || v < bestv) { bestv = v; best = o; }
+    }
+    off[k] = best;
+    for (int l = 1; l <= c.z; ++l) load[l + best] += w[l];
+  }
+  return off;
+}
+
 int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, Plan& P) {
   const int L = h->L, d = h->dmax;
   bool ok = true;
-  for (int64_t i : nodes) {
+  const std::vector<int> lev_off = plan_level_offsets(h, nodes);
+  for (size_t inode = 0; inode < nodes.size(); ++inode) {
+    const int64_t i = nodes[inode];
+    const int loff = lev_off[inode];
     const int ci = h->class_of_node[i];
     if (ci < 0 || ci >= (int)h->classes.size()) return fail("node %lld has no factor class", (long long)i);
     const NodeClass& c = h->classes[ci];
@@ -470,6 +529,7 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
     P.init.push_back(ij);
     const TTRef init = ij.out;
     auto add_op = [&](int level, const TTRef& a, int da, const TTRef& b, int db, int ca, int cb, TTRef& out) -> int {
+      level += loff;
       auto it = c.pyy.find({da, db});
       if (it == c.pyy.end()) return fail("class %d lacks the prob_yy table for (d1,d2)=(%d,%d)", ci, da, db);
       OpDesc op;
@@ -1488,6 +1548,7 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "profile") h->profile = (int)value;
   else if (n == "qr_fill") h->qr_fill = value;
   else if (n == "nstreams") h->nstreams = std::max(1.0, std::min(4.0, value));
+  else if (n == "level_balance") h->level_balance = value;
   else return fail("unknown option %s", name);
   return 0;
 }
