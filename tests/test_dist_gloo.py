@@ -70,14 +70,15 @@ class OracleBackend:
             self.bp.mu[int(e)] = OT.TT(tens, float(buf[k, -1]))
 
 
-def _worker(rank, world, port, iters, out):
+def _worker(rank, world, port, iters, out, balanced=False):
     import torch.distributed as dist
     from mpbp_b200.dist import DistMPBP, LocalProblem, partition_contiguous
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     w, phi = _problem()
-    owner = partition_contiguous(N, world)
+    from mpbp_b200.dist import partition_balanced
+    owner = partition_balanced(N, UND, world) if balanced else partition_contiguous(N, world)
     lp = LocalProblem(N, UND, owner, rank)
     g = O.BiDiGraph(len(lp.nodes), lp.local_und)
     lp.build_exchange(np.array(g.src), np.array(g.dst), world)
@@ -95,7 +96,8 @@ def _worker(rank, world, port, iters, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_halo_exchange_matches_single_process():
+@pytest.mark.parametrize("balanced", [False, True])
+def test_two_rank_halo_exchange_matches_single_process(balanced):
     import torch.multiprocessing as mp
     iters = 3
     w, phi = _problem()
@@ -108,7 +110,7 @@ def test_two_rank_halo_exchange_matches_single_process():
     s.close()
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, iters, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, iters, out, balanced)) for r in range(2)]
     for p in procs:
         p.start()
     gathered = out.get(timeout=240)
@@ -147,3 +149,28 @@ def test_partition_and_exchange_lists_are_consistent():
     cut = sum(len(v) for v in sends.values())
     gfull = M.IndexedBiDiGraph(N, UND)
     assert cut == int(np.sum(owner[gfull.src] != owner[gfull.dst]))
+
+
+def test_balanced_partition_covers_all_nodes_and_balances_cost():
+    from mpbp_b200.dist import LocalProblem, node_update_cost, partition_balanced, partition_contiguous
+    import networkx as nx
+    n = 300
+    G = nx.fast_gnp_random_graph(n, 4.0 / n, seed=1)
+    und = [(int(a), int(b)) for a, b in G.edges()]
+    deg = np.bincount(np.array(und).reshape(-1), minlength=n)
+    cost = np.array([node_update_cost(z) for z in deg])
+    for world in (2, 3, 8):
+        owner = partition_balanced(n, und, world)
+        assert owner.shape == (n,) and owner.min() == 0 and owner.max() == world - 1
+        load = np.array([cost[owner == r].sum() for r in range(world)])
+        lc = np.array([cost[partition_contiguous(n, world) == r].sum() for r in range(world)])
+        assert load.max() / load.mean() < 1.01 and load.max() <= lc.max() + 1e-9
+        # the local problems built from it are consistent: owned sets partition the nodes, neighbour order preserved
+        seen = []
+        for r in range(world):
+            lp = LocalProblem(n, und, owner, r)
+            seen.extend(int(x) for x in lp.nodes[lp.owned_local])
+            assert np.all(np.diff(lp.nodes) > 0)
+        assert sorted(seen) == list(range(n))
+    # monotone in the degree, light nodes cost one unit
+    assert node_update_cost(0) == 1.0 and all(node_update_cost(z + 1) > node_update_cost(z) for z in range(1, 12))

@@ -216,6 +216,28 @@ def test_glauber_degree5_star_truncated_vs_oracle():
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
 
 
+@pytest.mark.parametrize("schedule", ["sequential", "parallel"])
+def test_mixed_degrees_level_staggering_is_invisible(schedule):
+    # hub of degree 6, nodes of degree 1..4 and a cycle: the engine staggers the cavity levels of independent nodes
+    # (option level_balance) to fill the GPU; the results must not depend on it, bit for bit, and match the oracle
+    T = 3
+    und = [(0, k) for k in range(1, 7)] + [(1, 2), (2, 3), (3, 4), (4, 7), (7, 8), (8, 4), (5, 8)]
+    N = 9
+    kinds = [("glauber", (0.3 + 0.05 * i, 0.1 * (i - 4), 1.0)) for i in range(N)]
+    phi = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    tr = M.TruncBond(4)
+    res = []
+    for lb in (1.0, 0.0):
+        bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=4)
+        bd.set_option("level_balance", lb)
+        M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule=schedule)
+        res.append((np.concatenate([np.array(b).ravel() for b in M.beliefs(bd)]), M.api.free_energy_contributions(bd).copy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0, schedule=schedule)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
 def test_glauber_4regular_bond10_subspace_svd_vs_oracle():
     # D = 100, d~X up to 100 > 64: the truncating SVDs take the blocked subspace-iteration path
     import networkx as nx
