@@ -16,12 +16,12 @@ import numpy as np
 
 from . import _lib
 from .factors import (BPFactor, DampedFactor, GenericFactor, GenericGlauberFactor, HomogeneousGlauberFactor, IntegerGlauberFactor,
-                      PMJGlauberFactor, RecursiveBPFactor, SIRSFactor, SISFactor, tabulate_class)
+                      PMJGlauberFactor, RecursiveBPFactor, SIRSFactor, SIS_heterogeneousFactor, SISFactor, tabulate_class)
 from .truncations import SVDTrunc, TruncBond, TruncBondMax, TruncBondThresh, TruncThresh
 
 __all__ = [
     "BPFactor", "RecursiveBPFactor", "HomogeneousGlauberFactor", "PMJGlauberFactor", "IntegerGlauberFactor",
-    "GenericGlauberFactor", "SISFactor", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
+    "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
     "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
     "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "pair_beliefs", "bethe_free_energy", "means",
     "reset_messages_", "glauber_factors", "MPBPError",
@@ -127,6 +127,27 @@ class SIS:
         gam = np.broadcast_to(np.asarray(gamma, dtype=float), (g.N,))
         self.phi = [[np.array([1 - gam[i], gam[i]]) if t == 0 else np.ones(2) for t in range(T + 1)] for i in range(g.N)] if phi is None else phi
         self.psi = psi  # per directed edge
+
+
+class SIS_heterogeneous:
+    """src/Models/epidemics/sis_heterogeneous.jl:1-49.  `lam` is an N x N matrix (dense or scipy sparse) whose entry
+    [j, i] is the probability that j infects i; node i's factor takes column i restricted to its neighbours, in
+    ascending neighbour order (`sis_heterogeneous_factors`, :51-53).  `rho`, `alpha`: per-node vectors."""
+
+    def __init__(self, g: IndexedBiDiGraph, lam, rho, T, alpha=None, gamma=0.5, phi=None, psi=None):
+        lam = np.asarray(lam.todense() if hasattr(lam, "todense") else lam, dtype=float)
+        assert lam.shape == (g.N, g.N)
+        self.g, self.lam, self.T = g, lam, int(T)
+        self.rho = np.broadcast_to(np.asarray(rho, dtype=float), (g.N,))
+        self.alpha = np.zeros(g.N) if alpha is None else np.broadcast_to(np.asarray(alpha, dtype=float), (g.N,))
+        gam = np.broadcast_to(np.asarray(gamma, dtype=float), (g.N,))
+        self.phi = [[np.array([1 - gam[i], gam[i]]) if t == 0 else np.ones(2) for t in range(T + 1)] for i in range(g.N)] if phi is None else phi
+        self.psi = psi  # per directed edge
+
+    def factors(self):
+        g = self.g
+        return [[SIS_heterogeneousFactor([self.lam[int(j), i] for j in g.neighbors(i)], self.rho[i], self.alpha[i])] * (self.T + 1)
+                for i in range(g.N)]
 
 
 class SIRS:
@@ -343,6 +364,8 @@ def mpbp(*args, **kw):
         if isinstance(m, SIS):
             w = [[SISFactor(m.lam, m.rho, m.alpha)] * (m.T + 1)] * m.g.N
             return MPBP(m.g, w, [2] * m.g.N, m.T, phi=m.phi, psi=m.psi, **kw)
+        if isinstance(m, SIS_heterogeneous):
+            return MPBP(m.g, m.factors(), [2] * m.g.N, m.T, phi=m.phi, psi=m.psi, **kw)
         if isinstance(m, SIRS):
             w = [[SIRSFactor(m.lam, m.rho, m.sigma, m.alpha)] * (m.T + 1)] * m.g.N
             return MPBP(m.g, w, [3] * m.g.N, m.T, phi=m.phi, psi=m.psi, **kw)

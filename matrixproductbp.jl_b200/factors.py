@@ -203,6 +203,32 @@ class SISFactor(RecursiveBPFactor):
         return p if xnext == SUSCEPTIBLE else 1 - p
 
 
+class SIS_heterogeneousFactor(SISFactor):
+    """SIS with per-neighbour incoming infection probabilities lam[k], k = position of the neighbour in the node's
+    (ascending) neighbour list (src/Models/epidemics/sis_heterogeneous_bp.jl:4-15, prob_xy :69-72)."""
+
+    def __init__(self, lam, rho, alpha=0.0):
+        lam = [float(v) for v in lam]
+        for v in lam + [rho, alpha]:
+            assert 0 <= v <= 1
+        self.lam, self.rho, self.alpha = lam, float(rho), float(alpha)
+
+    def key(self):
+        return ("SIShet", tuple(self.lam), self.rho, self.alpha)
+
+    def prob_xy(self, yk, xk, xi, k=None):
+        lam, inf = self.lam[k - 1], xk == INFECTIOUS
+        return (yk == INFECTIOUS) * lam * inf + (yk == SUSCEPTIBLE) * (1 - lam * inf)
+
+    def __call__(self, xnext, xneigh, x):
+        if x == INFECTIOUS:
+            return self.rho if xnext == SUSCEPTIBLE else 1 - self.rho
+        p = 1 - self.alpha
+        for v, lam in zip(xneigh, self.lam):
+            p *= 1 - lam * (v == INFECTIOUS)
+        return p if xnext == SUSCEPTIBLE else 1 - p
+
+
 class SIRSFactor(RecursiveBPFactor):
     def __init__(self, lam, rho, sigma, alpha=0.0):
         for v in (lam, rho, sigma, alpha):

@@ -197,6 +197,25 @@ class SISFactor(RecursiveBPFactor):
         return p if xnext == SUSCEPTIBLE else 1 - p
 
 
+class SIS_heterogeneousFactor(SISFactor):
+    """per-neighbour infection probabilities lam[k] (src/Models/epidemics/sis_heterogeneous_bp.jl:4-15,52-72)."""
+
+    def __init__(self, lam, rho, alpha=0.0):
+        self.lam, self.rho, self.alpha = [float(v) for v in lam], rho, alpha
+
+    def prob_xy(self, yk, xk, xi, k=None):
+        lam = self.lam[k - 1]
+        return (yk == INFECTIOUS) * lam * (xk == INFECTIOUS) + (yk == SUSCEPTIBLE) * (1 - lam * (xk == INFECTIOUS))
+
+    def __call__(self, xnext, xneigh, x):
+        if x == INFECTIOUS:
+            return self.rho if xnext == SUSCEPTIBLE else 1 - self.rho
+        p = 1 - self.alpha
+        for v, lam in zip(xneigh, self.lam):
+            p *= 1 - lam * (v == INFECTIOUS)
+        return p if xnext == SUSCEPTIBLE else 1 - p
+
+
 class SIRSFactor(RecursiveBPFactor):
     def __init__(self, lam, rho, sigma, alpha=0.0):
         self.lam, self.rho, self.sigma, self.alpha = lam, rho, sigma, alpha

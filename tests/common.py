@@ -12,6 +12,7 @@ def make_factor(kind, params, both=True):
         "pmj": (OF.PMJGlauberFactor, M.PMJGlauberFactor),
         "intglauber": (OF.IntegerGlauberFactor, M.IntegerGlauberFactor),
         "sis": (OF.SISFactor, M.SISFactor),
+        "sishet": (OF.SIS_heterogeneousFactor, M.SIS_heterogeneousFactor),
         "sirs": (OF.SIRSFactor, M.SIRSFactor),
     }
     a, b = table[kind]

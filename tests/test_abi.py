@@ -52,6 +52,7 @@ def test_host_tabulation_matches_oracle_factors():
     pairs = [
         (OF.HomogeneousGlauberFactor(0.7, -0.2, 1.3), M.HomogeneousGlauberFactor(0.7, -0.2, 1.3), 2),
         (OF.SISFactor(0.3, 0.2, 0.05), M.SISFactor(0.3, 0.2, 0.05), 2),
+        (OF.SIS_heterogeneousFactor([0.3, 0.6, 0.1], 0.2, 0.05), M.SIS_heterogeneousFactor([0.3, 0.6, 0.1], 0.2, 0.05), 2),
         (OF.SIRSFactor(0.3, 0.2, 0.1, 0.05), M.SIRSFactor(0.3, 0.2, 0.1, 0.05), 3),
         (OF.PMJGlauberFactor([1, -1, 1], 0.5, 0.1, 1.0), M.PMJGlauberFactor([1, -1, 1], 0.5, 0.1, 1.0), 2),
         (OF.IntegerGlauberFactor([1, -2, 1], 0.1, 0.8), M.IntegerGlauberFactor([1, -2, 1], 0.1, 0.8), 2),

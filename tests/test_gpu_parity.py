@@ -316,6 +316,38 @@ def test_nodes_subset_and_visiting_order_vs_oracle():
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
 
 
+def test_sis_heterogeneous_star_and_model_vs_oracle():
+    # per-neighbour infection probabilities (src/Models/epidemics/sis_heterogeneous_bp.jl:69-72): the Pxy tables are per
+    # (node class, neighbour); star of test/sis_heterogeneous.jl plus a loopy edge, truncation active
+    T, N = 3, 5
+    rng = np.random.default_rng(3)
+    und = [(0, 1), (0, 2), (0, 3), (1, 2), (3, 4)]
+    gd = M.IndexedBiDiGraph(N, und)
+    lam = np.zeros((N, N))
+    for a, b in und:
+        lam[a, b], lam[b, a] = rng.random(), rng.random()
+    rho, alpha = rng.random(N), 0.2 * rng.random(N)
+    kinds = [("sishet", ([lam[int(j), i] for j in gd.neighbors(i)], float(rho[i]), float(alpha[i]))) for i in range(N)]
+    phi = [[np.array([0.6, 0.4]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][T] = np.array([0.1, 1.0])
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=4)
+    tr = M.TruncBond(3)
+    O.iterate(bo, maxiter=4, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=4, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+    # the model constructor builds the same factors (sis_heterogeneous_factors, sis_heterogeneous.jl:51-53)
+    bm = M.mpbp(M.SIS_heterogeneous(gd, lam, rho, T, alpha=alpha, phi=phi), dmax=4)
+    M.iterate_(bm, maxiter=4, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    assert np.array_equal(np.array(M.beliefs(bm)), np.array(M.beliefs(bd)))
+    # uniform rates reproduce the homogeneous model (test/sis_heterogeneous_compare_homogeneous.jl:12-35)
+    bu = M.mpbp(M.SIS(gd, 0.15, 0.12, T, gamma=0.13), dmax=4)
+    bh = M.mpbp(M.SIS_heterogeneous(gd, 0.15 * (lam > 0), 0.12, T, gamma=0.13), dmax=4)
+    for b in (bu, bh):
+        M.iterate_(b, maxiter=30, svd_trunc=tr, tol=1e-12, shuffle_nodes=False)
+    assert np.allclose(np.array(M.beliefs(bu)), np.array(M.beliefs(bh)), atol=1e-12)
+
+
 def test_glauber_infinite_graph_free_energy_known_answer():
     # /root/reference/test/glauber_infinite_graph.jl:7-18 inputs, run without damping: f = 0.98812749675847 per node
     # (derived known answer, SURVEY.md header fact 3(ii)).  The reference test uses TruncThresh(0.0) (no device bond
@@ -357,6 +389,78 @@ def test_generic_factor_exhaustive_trace_vs_oracle():
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
     p, Z, logZ = exact.exact_prob(bo)
     assert abs(-M.bethe_free_energy(bd) - logZ) < 1e-8
+
+
+def test_pair_observations_generic_glauber_vs_oracle_and_exact():
+    # test/pair_observations.jl:62-112: random couplings (GenericGlauberFactor -> exhaustive trace) with psi on four
+    # (edge, time) pairs on a tree; device vs oracle vs brute force
+    from oracle import factors as OF, exact
+    T, N = 2, 5
+    rng = np.random.default_rng(11)
+    und = [(0, 1), (1, 2), (2, 3), (2, 4)]
+    go = O.BiDiGraph(N, und)
+    gd = M.IndexedBiDiGraph(N, und)
+    obs = [(0, 1, 1, np.array([[0.1, 0.9], [0.3, 0.4]])), (2, 3, 2, np.array([[0.4, 0.6], [0.5, 0.9]])),
+           (2, 4, 2, rng.random((2, 2))), (1, 2, T, rng.random((2, 2)))]
+    psi = [[np.ones((2, 2)) for _ in range(T + 1)] for _ in range(go.ne)]
+    for (i, j, t, m) in obs:
+        for e in range(go.ne):
+            if go.src[e] == i and go.dst[e] == j:
+                psi[e][t] = psi[e][t] * m
+            if go.src[e] == j and go.dst[e] == i:
+                psi[e][t] = psi[e][t] * m.T
+    h = rng.standard_normal(N)
+    J = {frozenset(e): float(rng.standard_normal()) for e in und}
+    wo, wd = [], []
+    for i in range(N):
+        Ji = [J[frozenset((i, int(j)))] for j in gd.neighbors(i)]
+        wo.append([OF.GenericGlauberFactor(Ji, float(h[i]), 1.0)] * (T + 1))
+        wd.append([M.GenericGlauberFactor(Ji, float(h[i]), 1.0)] * (T + 1))
+    phi = [[np.array([0.15, 0.85]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[3][1] = np.array([1.0, 0.05])
+    bo = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi], psi=[[m.copy() for m in ps] for ps in psi])
+    bd = M.mpbp(gd, wd, [2] * N, T, phi=phi, psi=psi, dmax=16)
+    O.iterate(bo, maxiter=5, trunc=OT.TruncThresh(0.0), tol=0.0)
+    M.iterate_(bd, maxiter=5, svd_trunc=M.TruncBondThresh(16, 0.0), tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+    p, Z, logZ = exact.exact_prob(bo)
+    assert abs(-M.bethe_free_energy(bd) - logZ) < 1e-8
+    assert np.allclose(np.array(M.beliefs(bd)), np.array(exact.exact_marginals(bo, p)), atol=1e-8)
+
+
+@pytest.mark.parametrize("schedule", ["sequential", "parallel"])
+def test_sirs_loopy_truncated_vs_oracle(schedule):
+    # q = 3 on a loopy graph with an active bond cap: 3x3 message blocks through every kernel of the recursion
+    T = 3
+    und = [(0, 1), (1, 2), (0, 2), (2, 3)]
+    N = 4
+    kinds = [("sirs", (0.3 + 0.05 * i, 0.15, 0.2, 0.02)) for i in range(N)]
+    phi = [[np.array([0.7, 0.25, 0.05]) if t == 0 else np.ones(3) for t in range(T + 1)] for _ in range(N)]
+    phi[1][2] = np.array([0.1, 1.0, 0.3])
+    bo, bd = build_pair(N, und, T, kinds, [3] * N, phi, dmax=5)
+    tr = M.TruncBond(5)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0, schedule=schedule)
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule=schedule)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_trunc_bond_thresh_loopy_vs_oracle():
+    # TruncBondThresh(d, eps): both the cap and the relative threshold bind at different sites
+    T = 4
+    und = [(0, 1), (0, 2), (1, 2), (2, 3), (3, 4), (4, 0)]
+    N = 5
+    kinds = [("glauber", (0.35, 0.05 * (i - 2), 1.0)) for i in range(N)]
+    phi = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=6)
+    tr = M.TruncBondThresh(5, 1e-3)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    bonds = [bd.get_message(e)[k].shape[0] for e in range(bd.E2) for k in range(T + 1)]
+    assert max(bonds) == 5 and any(1 < b < 4 for b in bonds[2:])
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
 
 
 def test_k4_bond16_full_size_paths_vs_oracle():

@@ -112,6 +112,102 @@ def test_sis_small_tree_vs_exact():
     assert np.allclose(np.array(pb), np.array(exact.exact_pair_marginals(bp, p)), atol=1e-10)
 
 
+def test_sis_heterogeneous_small_tree_vs_exact():
+    # /root/reference/test/sis_heterogeneous.jl:1-47 structure: star, T=3, per-edge lambda, per-node rho/alpha, cap 8 exact
+    T, N = 3, 4
+    rng = np.random.default_rng(0)
+    und = [(0, 1), (0, 2), (0, 3)]
+    g = O.BiDiGraph(N, und)
+    lam = np.zeros((N, N))
+    for a, b in und:
+        lam[a, b], lam[b, a] = rng.random(), rng.random()
+    rho, alpha, gamma = rng.random(N), rng.random(N), 0.5
+    w = []
+    for i in range(N):
+        nb = [g.dst[e] for e in range(len(g.src)) if g.src[e] == i]
+        assert nb == sorted(nb)
+        w.append([F.SIS_heterogeneousFactor([lam[j, i] for j in nb], rho[i], alpha[i])] * (T + 1))
+    phi = [[np.array([1 - gamma, gamma]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    for i in range(N):
+        o = np.full(2, 0.1)
+        o[rng.integers(2)] = 1.0
+        phi[i][T] = phi[i][T] * o
+    bp = O.MPBP(g, w, [2] * N, T, phi=phi)
+    O.iterate(bp, maxiter=10, trunc=tt.TruncBondMax(8), tol=0.0)
+    p, Z, _ = exact.exact_prob(bp)
+    assert abs(np.exp(-O.bethe_free_energy(bp)) - Z) < 1e-9 * Z
+    assert np.allclose(np.array(O.beliefs(bp)), np.array(exact.exact_marginals(bp, p)), atol=1e-10)
+    pb, _ = O.pair_beliefs(bp)
+    assert np.allclose(np.array(pb), np.array(exact.exact_pair_marginals(bp, p)), atol=1e-10)
+    # the recursive interface reproduces the factor itself (what the reference checks with RestrictedRecursiveBPFactor, :49-60)
+    f = w[0][0]
+    for xn in (1, 2):
+        for x in (1, 2):
+            for xs in np.ndindex(2, 2, 2):
+                xs = [v + 1 for v in xs]
+                assert abs(F.RecursiveBPFactor.__call__(f, xn, xs, x) - f(xn, xs, x)) < 1e-14
+
+
+def test_sis_heterogeneous_with_uniform_rates_equals_homogeneous():
+    # /root/reference/test/sis_heterogeneous_compare_homogeneous.jl:1-35: loopy 5-node graph, TruncBond(3), tol=1e-12
+    T, N = 3, 5
+    A = np.array([[0, 1, 1, 0, 0], [1, 0, 1, 0, 0], [1, 1, 0, 1, 0], [0, 0, 1, 0, 1], [0, 0, 0, 1, 0]])
+    und = [(i, j) for i in range(N) for j in range(i + 1, N) if A[i, j]]
+    lam, rho, gamma = 0.15, 0.12, 0.13
+    g = O.BiDiGraph(N, und)
+    phi = [[np.array([1 - gamma, gamma]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    wu = [[F.SISFactor(lam, rho)] * (T + 1) for _ in range(N)]
+    wh = [[F.SIS_heterogeneousFactor([lam] * int(A[i].sum()), rho)] * (T + 1) for i in range(N)]
+    res = []
+    for w in (wu, wh):
+        bp = O.MPBP(g, w, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
+        O.iterate(bp, maxiter=200, trunc=tt.TruncBond(3), tol=1e-12)
+        res.append(np.array(O.beliefs(bp)))
+    assert np.allclose(res[0], res[1], atol=1e-12)
+
+
+def test_pair_observations_tree_vs_exact():
+    # /root/reference/test/pair_observations.jl:1-60: Glauber on a 5-node tree, T=2, psi on four (edge, time) pairs,
+    # TruncThresh(0.0); recursive and generic (random couplings) factors
+    T, N = 2, 5
+    rng = np.random.default_rng(111)
+    und = [(0, 1), (1, 2), (2, 3), (2, 4)]
+    g = O.BiDiGraph(N, und)
+    obs = [(0, 1, 1, np.array([[0.1, 0.9], [0.3, 0.4]])), (2, 3, 2, np.array([[0.4, 0.6], [0.5, 0.9]])),
+           (2, 4, 2, rng.random((2, 2))), (1, 2, T, rng.random((2, 2)))]
+    E2 = len(g.src)
+    psi = [[np.ones((2, 2)) for _ in range(T + 1)] for _ in range(E2)]
+    for (i, j, t, m) in obs:  # pair_observations_nondirected: psi_{i->j}[t][x_i, x_j] = m, psi_{j->i} = m^T
+        for e in range(E2):
+            if g.src[e] == i and g.dst[e] == j:
+                psi[e][t] = psi[e][t] * m
+            if g.src[e] == j and g.dst[e] == i:
+                psi[e][t] = psi[e][t] * m.T
+    h = rng.standard_normal(N)
+    for generic in (False, True):
+        if generic:
+            J = {frozenset(e): rng.standard_normal() for e in und}
+            w = []
+            for i in range(N):
+                nb = [g.dst[e] for e in range(E2) if g.src[e] == i]
+                w.append([F.GenericGlauberFactor([J[frozenset((i, j))] for j in nb], h[i], 1.0)] * (T + 1))
+        else:
+            w = [[F.HomogeneousGlauberFactor(1.0, h[i], 1.0)] * (T + 1) for i in range(N)]
+        phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(N)]
+        for _ in range(N):
+            i, t = rng.integers(N), rng.integers(1, T + 1)
+            o = np.full(2, 1e-2)
+            o[rng.integers(2)] = 1.0
+            phi[i][t] = phi[i][t] * o
+        bp = O.MPBP(g, w, [2] * N, T, phi=phi, psi=[[m.copy() for m in ps] for ps in psi])
+        O.iterate(bp, maxiter=10, trunc=tt.TruncThresh(0.0), tol=0.0)
+        p, Z, _ = exact.exact_prob(bp)
+        assert abs(np.exp(-O.bethe_free_energy(bp)) - Z) < 1e-9 * Z
+        assert np.allclose(np.array(O.beliefs(bp)), np.array(exact.exact_marginals(bp, p)), atol=1e-10)
+        pb, _ = O.pair_beliefs(bp)
+        assert np.allclose(np.array(pb), np.array(exact.exact_pair_marginals(bp, p)), atol=1e-10)
+
+
 def test_sirs_small_tree_vs_exact():
     # /root/reference/test/sirs_small_tree.jl structure (q=3, TruncThresh(0.0))
     T = 2
