@@ -62,3 +62,38 @@ def exact_pair_marginals(bp, p):
             row.append(m if a < b else m.T)
         out.append(row)
     return out
+
+
+def onesample(bp, rng):
+    """forward sample of the prior dynamics: x_i^0 ~ phi_i^0 (normalised), x_i^{t+1} ~ w_i^t(. | x_neigh^t, x_i^t)
+    (the prior part of /root/reference/src/sampling.jl onesample; reweightings at t > 0 are NOT applied).  1-based states."""
+    g, w, q = bp.g, bp.w, bp.q
+    N, L = g.N, bp.T + 1
+    neigh = [[g.dst[e] for e in g.out_edges[i]] for i in range(N)]
+    X = np.zeros((N, L), dtype=int)
+    for i in range(N):
+        p0 = np.asarray(bp.phi[i][0], dtype=float)
+        X[i, 0] = 1 + rng.choice(q[i], p=p0 / p0.sum())
+    for t in range(L - 1):
+        for i in range(N):
+            pr = np.array([w[i][t](xn, [X[k, t] for k in neigh[i]], X[i, t]) for xn in range(1, q[i] + 1)])
+            X[i, t + 1] = 1 + rng.choice(q[i], p=pr / pr.sum())
+    return X
+
+
+def logprob(bp, X):
+    """log of the un-normalised weight of trajectory X (N x (T+1), 1-based): /root/reference/src/mpbp.jl:301-323."""
+    g, w, phi, psi = bp.g, bp.w, bp.phi, bp.psi
+    N, L = g.N, bp.T + 1
+    neigh = [[g.dst[e] for e in g.out_edges[i]] for i in range(N)]
+    lp = 0.0
+    for i in range(N):
+        lp += np.log(phi[i][0][X[i, 0] - 1])
+    for t in range(L - 1):
+        for i in range(N):
+            lp += np.log(w[i][t](X[i, t + 1], [X[k, t] for k in neigh[i]], X[i, t]))
+            lp += np.log(phi[i][t + 1][X[i, t + 1] - 1])
+    for t in range(L):
+        for e in range(g.ne):
+            lp += 0.5 * np.log(np.asarray(psi[e][t])[X[g.src[e], t] - 1, X[g.dst[e], t] - 1])
+    return float(lp)

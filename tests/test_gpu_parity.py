@@ -463,6 +463,61 @@ def test_trunc_bond_thresh_loopy_vs_oracle():
     assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
 
 
+def test_observe_everything_free_energy_is_logprob_on_device():
+    # test/glauber_small_tree.jl:74-86: every (i, t) observed with hard one-hot reweightings (exact zeros in phi): the
+    # messages have zero blocks everywhere, -f_bethe must equal logprob(X) and the beliefs are the observed trajectory
+    from oracle import factors as OF, exact
+    T, N = 3, 5
+    und = [(0, 1), (1, 2), (1, 3)]  # node 4 isolated
+    rng = np.random.default_rng(5)
+    h = rng.standard_normal(N)
+    go = O.BiDiGraph(N, und)
+    gd = M.IndexedBiDiGraph(N, und)
+    wo = [[OF.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0)] * (T + 1) for i in range(N)]
+    wd = [[M.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0)] * (T + 1) for i in range(N)]
+    phi = [[np.array([0.75, 0.25]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    bo = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
+    X = exact.onesample(bo, rng)
+    for i in range(N):
+        for t in range(T + 1):
+            bo.phi[i][t] = bo.phi[i][t] * (np.arange(1, 3) == X[i, t])
+    bd = M.mpbp(gd, wd, [2] * N, T, phi=[[p.copy() for p in ph] for ph in bo.phi], dmax=10)
+    tr = M.TruncBondThresh(10, 0.0)
+    O.iterate(bo, maxiter=6, trunc=OT.TruncBondThresh(10), tol=0.0)
+    M.iterate_(bd, maxiter=6, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    lp = exact.logprob(bo, X)
+    assert abs(-M.bethe_free_energy(bd) - lp) < 1e-8 and abs(-O.bethe_free_energy(bo) - lp) < 1e-8
+    b = np.array(M.beliefs(bd))
+    assert np.allclose(b, (np.arange(1, 3)[None, None, :] == X[:, :, None]), atol=1e-10)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_damped_factor_vs_oracle_and_exact():
+    # DampedFactor(w, p) (src/recursive_bp_factor.jl:183-206, test/glauber_small_tree.jl:88-131)
+    from oracle import factors as OF, exact
+    T, N = 2, 5
+    und = [(0, 1), (1, 2), (1, 3), (3, 4)]
+    rng = np.random.default_rng(9)
+    h = rng.standard_normal(N)
+    go = O.BiDiGraph(N, und)
+    gd = M.IndexedBiDiGraph(N, und)
+    wo = [[OF.DampedFactor(OF.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0), 0.2)] * (T + 1) for i in range(N)]
+    wd = [[M.DampedFactor(M.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0), 0.2)] * (T + 1) for i in range(N)]
+    phi = [[np.array([0.75, 0.25]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][1] = np.array([1.0, 1e-3])
+    phi[4][2] = np.array([1e-3, 1.0])
+    bo = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
+    bd = M.mpbp(gd, wd, [2] * N, T, phi=phi, dmax=10)
+    O.iterate(bo, maxiter=8, trunc=OT.TruncBondThresh(10), tol=0.0)
+    M.iterate_(bd, maxiter=8, svd_trunc=M.TruncBondThresh(10, 0.0), tol=0.0, shuffle_nodes=False)
+    eb, ef, ep = compare(bo, bd)
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+    p, Z, logZ = exact.exact_prob(bo)
+    assert abs(-M.bethe_free_energy(bd) - logZ) < 1e-8
+    assert np.allclose(np.array(M.beliefs(bd)), np.array(exact.exact_marginals(bo, p)), atol=1e-8)
+
+
 def test_k4_bond16_full_size_paths_vs_oracle():
     # complete graph K4, T=5, TruncBond(16): at the middle cuts D = 256 -> H=64 flat-tree QR, TSQR split (few ops per
     # launch) and the subspace-iteration SVD (d~X = 96..128 > 48) all run inside a real BP iteration

@@ -208,6 +208,41 @@ def test_pair_observations_tree_vs_exact():
         assert np.allclose(np.array(pb), np.array(exact.exact_pair_marginals(bp, p)), atol=1e-10)
 
 
+def test_glauber_observe_everything_free_energy_is_logprob():
+    # /root/reference/test/glauber_small_tree.jl:74-86: with every (i, t) observed (hard, zeros in phi) the Bethe free
+    # energy is minus the log-probability of the observed trajectory
+    rng = np.random.default_rng(111)
+    T = 2
+    g, w, phi = _small_tree(rng, T)
+    phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(g.N)]
+    for i in range(g.N):
+        phi[i][0] = np.array([0.75, 0.25])
+    bp = O.MPBP(g, w, [2] * g.N, T, phi=phi)
+    X = exact.onesample(bp, rng)
+    for i in range(g.N):
+        for t in range(T + 1):
+            bp.phi[i][t] = bp.phi[i][t] * (np.arange(1, 3) == X[i, t])
+    O.iterate(bp, maxiter=10, trunc=tt.TruncBondThresh(10), tol=0.0)
+    assert abs(-O.bethe_free_energy(bp) - exact.logprob(bp, X)) < 1e-10
+    for i in range(g.N):
+        assert np.allclose(np.array(O.beliefs(bp)[i]), (np.arange(1, 3)[None, :] == X[i][:, None]), atol=1e-12)
+
+
+def test_damped_factor_small_tree_vs_exact():
+    # /root/reference/test/glauber_small_tree.jl:88-131: DampedFactor(w, 0.2) on the same tree, TruncBondThresh(10)
+    rng = np.random.default_rng(111)
+    T = 2
+    g, w, phi = _small_tree(rng, T)
+    w = [[F.DampedFactor(x, 0.2) for x in wi] for wi in w]
+    bp = O.MPBP(g, w, [2] * g.N, T, phi=phi)
+    O.iterate(bp, maxiter=20, trunc=tt.TruncBondThresh(10), tol=0.0)
+    p, Z, _ = exact.exact_prob(bp)
+    assert abs(np.exp(-O.bethe_free_energy(bp)) - Z) < 1e-9 * Z
+    assert np.allclose(np.array(O.beliefs(bp)), np.array(exact.exact_marginals(bp, p)), atol=1e-10)
+    pb, _ = O.pair_beliefs(bp)
+    assert np.allclose(np.array(pb), np.array(exact.exact_pair_marginals(bp, p)), atol=1e-10)
+
+
 def test_sirs_small_tree_vs_exact():
     # /root/reference/test/sirs_small_tree.jl structure (q=3, TruncThresh(0.0))
     T = 2
