@@ -115,6 +115,10 @@ int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, con
  * sweeps, [2] executed FLOPs of all kernels (model), [3] device ms in QR kernels (CUDA events, only when
  * profiling is on), [4] heavy ops run, [5] edge updates. */
 int mpbp_counters(mpbp_handle h, double* out8, int reset);
+/* engine tuning knobs (none changes a result bit): "arena_gb" scratch arena size, "max_group_ops" ops per launch group,
+ * "nstreams" (1..4) concurrent streams per cavity round, "qr_fill" CTAs below which tall QRs are TSQR-split,
+ * "level_balance" (default 1) stagger the cavity levels of independent nodes so that every round carries similar
+ * work, "profile" (0/1) per-kernel-family CUDA-event timing. */
 int mpbp_set_option(mpbp_handle h, const char* name, double value);
 /* device ms per kernel family since the last reset (option "profile" = 1): [0] sweep-1 QR, [1] kron_carry,
  * [2] kron_proj, [3] gemm_m2t, [4] qr_small, [5] jacobi_project, [6] finalize, [7] belief */
