@@ -103,6 +103,12 @@ int mpbp_beliefs(mpbp_handle h, double* out);
 int mpbp_pair_beliefs(mpbp_handle h, double* out, double* logz);
 int mpbp_free_energy(mpbp_handle h, double* f);
 
+/* two-time marginals b_i(x^t, x^u) of every node's belief (reference: beliefs_tu / twovar_marginals.(bp.b),
+ * src/mpbp.jl:239; feeds autocorrelations / autocovariances :245-255,289-296).  Computed together with the beliefs
+ * once mpbp_set_option(h, "twovar", maxdist) is set (maxdist >= 1; T = all pairs).
+ * out[((i*L + t)*L + u)*Q + x_t + q_i*x_u], L = T+1, Q = qmax*qmax; entries with t >= u or u - t > maxdist are 0. */
+int mpbp_twovar_marginals(mpbp_handle h, double* out);
+
 /* ---- multi-GPU plumbing (no reference counterpart; see DESIGN.md "multi-GPU") ----
  * pack/unpack the fixed-capacity device slots of `n` messages into/from one contiguous DEVICE buffer so that
  * the host layer can exchange cut-edge messages with one collective.  slot size from mpbp_message_slot_bytes. */
@@ -118,7 +124,8 @@ int mpbp_counters(mpbp_handle h, double* out8, int reset);
 /* engine tuning knobs (none changes a result bit): "arena_gb" scratch arena size, "max_group_ops" ops per launch group,
  * "nstreams" (1..4) concurrent streams per cavity round, "qr_fill" CTAs below which tall QRs are TSQR-split,
  * "level_balance" (default 1) stagger the cavity levels of independent nodes so that every round carries similar
- * work, "profile" (0/1) per-kernel-family CUDA-event timing. */
+ * work, "profile" (0/1) per-kernel-family CUDA-event timing, "twovar" (maxdist, 0 = off) also compute the two-time
+ * marginals read by mpbp_twovar_marginals. */
 int mpbp_set_option(mpbp_handle h, const char* name, double value);
 /* device ms per kernel family since the last reset (option "profile" = 1): [0] sweep-1 QR, [1] kron_carry,
  * [2] kron_proj, [3] gemm_m2t, [4] qr_small, [5] jacobi_project, [6] finalize, [7] belief */

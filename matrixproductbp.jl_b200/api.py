@@ -23,7 +23,7 @@ __all__ = [
     "BPFactor", "RecursiveBPFactor", "HomogeneousGlauberFactor", "PMJGlauberFactor", "IntegerGlauberFactor",
     "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
     "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
-    "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "pair_beliefs", "bethe_free_energy", "means",
+    "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "pair_beliefs", "bethe_free_energy", "means",
     "reset_messages_", "glauber_factors", "MPBPError",
 ]
 
@@ -426,6 +426,49 @@ def beliefs(bp: MPBP):
 
 def means(f, bp: MPBP):
     return [[sum(f(x + 1, i) * p[x] for x in range(len(p))) for p in b] for i, b in enumerate(beliefs(bp))]
+
+
+def beliefs_tu(bp: MPBP):
+    """beliefs_tu(bp)[i][t][u] = b_i(x^t, x^u) as a q x q array for t < u <= t + maxdist (src/mpbp.jl:239), None
+    elsewhere.  The two-time marginals are computed together with the beliefs during `iterate_`, so they must be
+    switched on first: ``bp.set_option("twovar", maxdist)`` (maxdist = bp.T for all pairs)."""
+    L, qm = bp.T + 1, int(np.max(bp.q))
+    out = np.zeros(bp.N * L * L * qm * qm)
+    _lib.check(_lib.lib().mpbp_twovar_marginals(bp._h, _p(out, _lib.c_dp)))
+    out = out.reshape(bp.N, L, L, qm * qm)
+    res = []
+    for i in range(bp.N):
+        qi = int(bp.q[i])
+        row = [[None] * L for _ in range(L)]
+        for t in range(L):
+            for u in range(t + 1, L):
+                blk = out[i, t, u, :qi * qi]
+                if blk.any():
+                    row[t][u] = blk.reshape(qi, qi, order="F").copy()
+        res.append(row)
+    return res
+
+
+def autocorrelations(f, bp: MPBP):
+    """autocorrelations(f, bp)[i][t, u] = <f(x_i^t, i) f(x_i^u, i)> for t < u, zero elsewhere (src/mpbp.jl:245-255);
+    states are numbered from 1 as in the reference."""
+    res = []
+    for i, tv in enumerate(beliefs_tu(bp)):
+        L, qi = bp.T + 1, int(bp.q[i])
+        fx = np.array([f(x + 1, i) for x in range(qi)], dtype=float)
+        r = np.zeros((L, L))
+        for t in range(L):
+            for u in range(t + 1, L):
+                if tv[t][u] is not None:
+                    r[t, u] = fx @ tv[t][u] @ fx
+        res.append(r)
+    return res
+
+
+def autocovariances(f, bp: MPBP):
+    """covariance.(r, mu) = r - mu mu' on the whole matrix (src/mpbp.jl:287-296)"""
+    mu = means(f, bp)
+    return [r - np.outer(m, m) for r, m in zip(autocorrelations(f, bp), mu)]
 
 
 def pair_beliefs(bp: MPBP):

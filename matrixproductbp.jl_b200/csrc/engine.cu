@@ -100,6 +100,8 @@ struct mpbp_state {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // extra streams: op groups of one level run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   double nstreams = 4;
+  int twovar = 0;            // > 0: maxdist of the two-time marginals computed with every belief (option "twovar")
+  double* d_tv = nullptr;    // [N][L][L][qmax*qmax]
   double level_balance = 1;  // stagger the cavity levels of the nodes of a chunk so that every round carries similar work
   double damp = 0.0;  // set by mpbp_iterate for the duration of the call
   // options
@@ -270,6 +272,7 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
   const int z = c.z, q = c.q, d = h->dmax, L = h->L;
   auto tt = [&](int cap, int ny) { return (size_t)L * cap * cap * ny * q * 8 + 4 * (L + 1) + 8 + 3 * 256; };
   size_t b = 0;
+  if (h->twovar > 0) b += 8 * ((size_t)L * d * d * q * q + (size_t)L * d * q) + 2 * 256;
   if (c.generic) {
     for (int j = 0; j <= z; ++j) b += tt(d, c.gen_ny[j]);
     const int qjm = h->qmax;
@@ -488,6 +491,12 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
       bj.bw = (double*)h->arena.take(8 * (size_t)L * d * q);
       bj.Bt = (double*)h->arena.take(8 * (size_t)d * d * q * q);
       ok = ok && bj.bw && bj.Bt;
+      if (h->twovar > 0) {
+        bj.tv = h->d_tv + (size_t)i * L * L * h->qmax * h->qmax;
+        bj.Btall = (double*)h->arena.take(8 * (size_t)(L - 1 > 0 ? L - 1 : 1) * d * d * q * q);
+        bj.fwall = (double*)h->arena.take(8 * (size_t)L * d * q);
+        ok = ok && bj.Btall && bj.fwall;
+      }
       P.bel.push_back(bj);
       FJob f;
       f.logzi = h->d_logzi + i;
@@ -632,6 +641,12 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
     bj.bw = (double*)h->arena.take(8 * (size_t)L * d * q);
     bj.Bt = (double*)h->arena.take(8 * (size_t)d * d * q * q);
     ok = ok && bj.bw && bj.Bt;
+    if (h->twovar > 0) {
+      bj.tv = h->d_tv + (size_t)i * L * L * h->qmax * h->qmax;
+      bj.Btall = (double*)h->arena.take(8 * (size_t)(L - 1 > 0 ? L - 1 : 1) * d * d * q * q);
+      bj.fwall = (double*)h->arena.take(8 * (size_t)L * d * q);
+      ok = ok && bj.Btall && bj.fwall;
+    }
     P.bel.push_back(bj);
     FJob f;
     f.logzi = h->d_logzi + i;
@@ -947,6 +962,11 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     ev_begin(h, F_BEL, st);
     k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
     ev_end(h, st);
+    if (h->twovar > 0) {
+      const size_t tsm = 2 * (size_t)qm * d * qm * 8;
+      k_twovar<<<(unsigned)P.bel.size(), NT, tsm, st>>>(d_bel, L, d, h->twovar, qm * qm);
+      h->n_launch++;
+    }
     k_free_energy<<<(unsigned)(P.fj.size() + 127) / 128, 128, 0, st>>>(d_fj, (int)P.fj.size());
     h->n_launch += 2;
   }
@@ -1069,7 +1089,7 @@ int mpbp_destroy(mpbp_handle h) {
   for (int b = 0; b < 2; ++b) { cudaFree(h->msg[b].data); cudaFree(h->msg[b].bonds); cudaFree(h->msg[b].ls); }
   cudaFree(h->d_phi); cudaFree(h->d_psi); cudaFree(h->d_qprod); cudaFree(h->d_marg); cudaFree(h->d_logzi);
   cudaFree(h->d_logzij); cudaFree(h->d_f); cudaFree(h->d_means); cudaFree(h->d_marg_off); cudaFree(h->d_q);
-  cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->arena.base);
+  cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->arena.base); cudaFree(h->d_tv);
   for (auto& e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (h->own_stream) cudaStreamDestroy(h->st);
   for (int k = 0; k < 3; ++k) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
@@ -1346,6 +1366,14 @@ int mpbp_beliefs(mpbp_handle h, double* out) {
   return 0;
 }
 
+int mpbp_twovar_marginals(mpbp_handle h, double* out) {
+  if (!h || !out) return fail("null argument");
+  if (h->twovar <= 0 || !h->d_tv) return fail("two-time marginals are off: mpbp_set_option(h, \"twovar\", maxdist) before iterating");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpy(out, h->d_tv, sizeof(double) * (size_t)h->N * h->L * h->L * h->qmax * h->qmax, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int mpbp_free_energy(mpbp_handle h, double* f) {
   if (!h || !f) return fail("null argument");
   CUDA_OK(cudaSetDevice(h->device));
@@ -1549,6 +1577,16 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "qr_fill") h->qr_fill = value;
   else if (n == "nstreams") h->nstreams = std::max(1.0, std::min(4.0, value));
   else if (n == "level_balance") h->level_balance = value;
+  else if (n == "twovar") {
+    // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
+    h->twovar = value > 0 ? (int)std::min<double>(value, h->L) : 0;
+    if (h->twovar > 0 && !h->d_tv) {
+      const size_t nb = sizeof(double) * (size_t)h->N * h->L * h->L * h->qmax * h->qmax;
+      CUDA_OK(cudaSetDevice(h->device));
+      CUDA_OK(cudaMalloc((void**)&h->d_tv, nb));
+      CUDA_OK(cudaMemset(h->d_tv, 0, nb));
+    }
+  }
   else return fail("unknown option %s", name);
   return 0;
 }

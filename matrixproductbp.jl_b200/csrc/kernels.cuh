@@ -1222,6 +1222,10 @@ struct BelJob {
   double* logz;   // output scalar
   double* bw;     // scratch [L][dcap*q]
   double* Bt;     // scratch [m,n,x,x']
+  // two-time marginals (option "twovar"; nullptr = off)
+  double* tv;     // output [t][u][x_t + q*x_u], (t,u) stride q2cap, zero unless t < u <= t + maxdist
+  double* Btall;  // scratch [L-1][dcap*dcap*q*q]
+  double* fwall;  // scratch [L][dcap*q]
 };
 
 __global__ void __launch_bounds__(NT) k_belief(const BelJob* jobs, int L, int dcap, int* err) {
@@ -1332,6 +1336,108 @@ __global__ void __launch_bounds__(NT) k_belief(const BelJob* jobs, int L, int dc
     double* tmp = fw0;
     fw0 = fw1;
     fw1 = tmp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// two-time marginals of the belief, b_i(x^t, x^u) for t < u <= t + maxdist: what TensorTrains.twovar_marginals
+// returns for bp.b[i] (beliefs_tu / autocorrelations / autocovariances, src/mpbp.jl:239-255,289-296).  Same transfer
+// formulation as k_belief (the belief MPEM is never built): with B_s[m,n,x,x'] the site tensors of
+// f_bp_partial_i(full), F_t[m,x] the forward and G_u[n,y] the backward vectors (jb.bw, left there by k_belief),
+//   p_tu[x0,y] ~ sum_n ( [F_t delta_{x0,x}] B_t ... B_{u-1} )[x0; n,y] G_u[n,y].
+// One CTA per node, launched right after k_belief on the same jobs.  dyn smem: 2 * q*dcap*q doubles.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_twovar(const BelJob* jobs, int L, int dcap, int maxdist, int q2cap) {
+  __shared__ double red[NW + 1];
+  __shared__ double pbuf[64];
+  extern __shared__ double smem[];
+  const BelJob& jb = jobs[blockIdx.x];
+  if (!jb.tv) return;
+  const int q = jb.q, ny = jb.ny;
+  const int bst = dcap * dcap * q * q, fst = dcap * q;
+  const int* bonds = jb.full.bonds;
+  for (int idx = threadIdx.x; idx < L * L * q2cap; idx += NT) jb.tv[idx] = 0.0;
+  // site tensors
+  for (int t = 0; t < L - 1; ++t) {
+    const int bl = bonds[t], br = bonds[t + 1], mn = bl * br;
+    const double* C = jb.full.data + (size_t)t * jb.full.stride;
+    const double* phi = jb.phi + (size_t)t * q;
+    const double* W = jb.Wd + (size_t)t * jb.w_tstride;
+    double* B = jb.Btall + (size_t)t * bst;
+    for (int idx = threadIdx.x; idx < mn * q * q; idx += NT) {
+      const int e = idx % mn, x = (idx / mn) % q, xn = idx / (mn * q);
+      double acc = 0.0;
+      for (int y = 0; y < ny; ++y) acc += W[xn + q * (x + q * y)] * C[e + mn * (y + ny * x)];
+      B[idx] = acc * phi[x];
+    }
+  }
+  for (int idx = threadIdx.x; idx < q; idx += NT) jb.fwall[idx] = 1.0;  // bonds[0] = 1
+  __syncthreads();
+  // forward vectors F_{t+1}[n,x'] = sum_{m,x} F_t[m,x] B_t[m,n,x,x'], each rescaled by its max-abs
+  for (int t = 0; t < L - 1; ++t) {
+    const int bl = bonds[t], br = bonds[t + 1];
+    const double* F = jb.fwall + (size_t)t * fst;
+    double* Fn = jb.fwall + (size_t)(t + 1) * fst;
+    const double* B = jb.Btall + (size_t)t * bst;
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < br * q; idx += NT) {
+      const int n = idx % br, xn = idx / br;
+      double acc = 0.0;
+      for (int x = 0; x < q; ++x)
+        for (int m = 0; m < bl; ++m) acc += F[m + bl * x] * B[m + bl * (n + br * (x + q * xn))];
+      Fn[idx] = acc;
+      mx = fmax(mx, fabs(acc));
+    }
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < br * q; idx += NT) Fn[idx] *= f;
+    __syncthreads();
+  }
+  double* M0 = smem;
+  double* M1 = smem + (size_t)q * fst;
+  for (int t = 0; t < L - 1; ++t) {
+    const int bt = bonds[t];
+    const double* F = jb.fwall + (size_t)t * fst;
+    for (int idx = threadIdx.x; idx < q * bt * q; idx += NT) {
+      const int x0 = idx % q, r = idx / q, x = r / bt;
+      M0[idx] = (x0 == x) ? F[r] : 0.0;
+    }
+    __syncthreads();
+    const int umax = min(L - 1, t + maxdist);
+    for (int u = t + 1; u <= umax; ++u) {
+      const int bl = bonds[u - 1], br = bonds[u];
+      const double* B = jb.Btall + (size_t)(u - 1) * bst;
+      const double* G = jb.bw + (size_t)u * fst;  // [n + br*y], includes site u
+      double mx = 0.0;
+      for (int idx = threadIdx.x; idx < q * br * q; idx += NT) {
+        const int x0 = idx % q, r = idx / q, n = r % br, y = r / br;
+        double acc = 0.0;
+        for (int x = 0; x < q; ++x)
+          for (int m = 0; m < bl; ++m) acc += M0[x0 + q * (m + bl * x)] * B[m + bl * (n + br * (x + q * y))];
+        M1[idx] = acc;
+        mx = fmax(mx, fabs(acc));
+      }
+      mx = block_max(mx, red);
+      if (threadIdx.x < q * q) {
+        const int x0 = threadIdx.x % q, y = threadIdx.x / q;
+        double acc = 0.0;
+        for (int n = 0; n < br; ++n) acc += M1[x0 + q * (n + br * y)] * G[n + br * y];
+        pbuf[threadIdx.x] = acc;
+      }
+      __syncthreads();
+      if (threadIdx.x < q * q) {
+        double sum = 0.0;
+        for (int k = 0; k < q * q; ++k) sum += pbuf[k];
+        jb.tv[((size_t)t * L + u) * q2cap + threadIdx.x] = pbuf[threadIdx.x] / sum;
+      }
+      const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+      for (int idx = threadIdx.x; idx < q * br * q; idx += NT) M1[idx] *= f;
+      __syncthreads();
+      double* tmp = M0;
+      M0 = M1;
+      M1 = tmp;
+    }
+    __syncthreads();
   }
 }
 

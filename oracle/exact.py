@@ -64,6 +64,22 @@ def exact_pair_marginals(bp, p):
     return out
 
 
+def exact_autocorrelations(bp, p, f=lambda x, i: x):
+    """<f(x_i^t) f(x_i^u)> for t < u from the joint distribution (exact_autocorrelations of the reference's src/exact.jl,
+    as used by test/glauber_small_tree.jl:46-50); zero elsewhere."""
+    N, L = bp.g.N, bp.T + 1
+    out = []
+    for i in range(N):
+        fx = np.array([f(x + 1, i) for x in range(bp.q[i])], dtype=float)
+        r = np.zeros((L, L))
+        for t in range(L):
+            for u in range(t + 1, L):
+                m = p.sum(axis=tuple(c for c in range(N * L) if c not in (i * L + t, i * L + u)))
+                r[t, u] = fx @ m @ fx
+        out.append(r)
+    return out
+
+
 def onesample(bp, rng):
     """forward sample of the prior dynamics: x_i^0 ~ phi_i^0 (normalised), x_i^{t+1} ~ w_i^t(. | x_neigh^t, x_i^t)
     (the prior part of /root/reference/src/sampling.jl onesample; reweightings at t > 0 are NOT applied).  1-based states."""

@@ -357,6 +357,44 @@ def beliefs(bp):
     return [T_.marginals(b) for b in bp.b]
 
 
+def beliefs_tu(bp, maxdist=None):
+    """mpbp.jl:239: two-time marginals b_i(x^t, x^u), t < u <= t + maxdist, of every node's belief; [i][t][u] is a
+    q x q array (None where not computed)."""
+    out = []
+    for b in bp.b:
+        tv = T_.twovar_marginals(b)
+        L = len(tv)
+        if maxdist is not None:
+            for t in range(L):
+                for u in range(L):
+                    if u - t > maxdist:
+                        tv[t][u] = None
+        out.append(tv)
+    return out
+
+
+def autocorrelations(bp, f=lambda x, i: x, maxdist=None):
+    """mpbp.jl:245-255: r_i[t, u] = <f(x_i^t) f(x_i^u)> for t < u (zero elsewhere), states numbered from 1."""
+    out = []
+    for i, tv in enumerate(beliefs_tu(bp, maxdist)):
+        L = len(tv)
+        q = bp.q[i]
+        fx = np.array([f(x + 1, i) for x in range(q)], dtype=float)
+        r = np.zeros((L, L))
+        for t in range(L):
+            for u in range(t + 1, L):
+                if tv[t][u] is not None:
+                    r[t, u] = fx @ np.asarray(tv[t][u]).reshape(q, q) @ fx
+        out.append(r)
+    return out
+
+
+def autocovariances(bp, f=lambda x, i: x, maxdist=None):
+    """mpbp.jl:289-296: covariance.(r, mu) = r - mu mu' (on the whole matrix, like the reference)."""
+    mu = means(bp, f)
+    return [r - np.outer(m, m) for r, m in zip(autocorrelations(bp, f, maxdist), mu)]
+
+
 def bethe_free_energy(bp):
     return float(np.sum(bp.f))
 

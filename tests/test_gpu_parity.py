@@ -518,6 +518,62 @@ def test_damped_factor_vs_oracle_and_exact():
     assert np.allclose(np.array(M.beliefs(bd)), np.array(exact.exact_marginals(bo, p)), atol=1e-8)
 
 
+@pytest.mark.parametrize("schedule", ["sequential", "parallel"])
+def test_two_time_marginals_and_autocorrelations_vs_oracle(schedule):
+    # beliefs_tu / autocorrelations / autocovariances (src/mpbp.jl:239-255,289-296) on a loopy graph with an isolated
+    # node and an active truncation: the device computes them with the beliefs (option "twovar")
+    T = 4
+    und = [(0, 1), (0, 2), (1, 2), (2, 3)]
+    N = 5
+    kinds = [("glauber", (0.4, 0.1 * (i - 2), 1.0)) for i in range(N)]
+    phi = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[1][2] = np.array([1.0, 0.2])
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=4)
+    bd.set_option("twovar", T)
+    tr = M.TruncBond(4)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0, schedule=schedule)
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule=schedule)
+    tvo, tvd = O.beliefs_tu(bo), M.beliefs_tu(bd)
+    for i in range(N):
+        for t in range(T + 1):
+            for u in range(T + 1):
+                if u <= t:
+                    assert tvd[i][t][u] is None
+                else:
+                    assert np.max(np.abs(np.asarray(tvo[i][t][u]).reshape(2, 2) - tvd[i][t][u])) < TOL, (i, t, u)
+    f = lambda x, i: 2 * x - 3
+    assert np.max(np.abs(np.array(O.autocorrelations(bo, f)) - np.array(M.autocorrelations(f, bd)))) < TOL
+    assert np.max(np.abs(np.array(O.autocovariances(bo, f)) - np.array(M.autocovariances(f, bd)))) < TOL
+    eb, ef, ep = compare(bo, bd)  # the usual read-outs are untouched by the option
+    assert eb < TOL and ef < TOL and ep < TOL, (eb, ef, ep)
+
+
+def test_two_time_marginals_sirs_tree_exact_maxdist_and_loud_when_off():
+    from oracle import exact
+    T = 2
+    und = [(0, 1), (1, 2)]
+    N = 3
+    kinds = [("sirs", (0.4, 0.15, 0.2, 0.05))] * N
+    phi = [[np.array([0.7, 0.3, 0.0]) if t == 0 else np.ones(3) for t in range(T + 1)] for _ in range(N)]
+    phi[0][2] = np.array([0.1, 1.0, 0.3])
+    bo, bd = build_pair(N, und, T, kinds, [3] * N, phi, dmax=9)
+    with pytest.raises(M.MPBPError):
+        M.beliefs_tu(bd)  # not switched on
+    bd.set_option("twovar", T)
+    tr = M.TruncBondThresh(9, 0.0)
+    O.iterate(bo, maxiter=5, trunc=OT.TruncThresh(0.0), tol=0.0)
+    M.iterate_(bd, maxiter=5, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    p, Z, _ = exact.exact_prob(bo)
+    f = lambda x, i: x - 1
+    rex = exact.exact_autocorrelations(bo, p, f)
+    assert np.max(np.abs(np.array(M.autocorrelations(f, bd)) - np.array(rex))) < TOL
+    # maxdist = 1: only adjacent times are computed
+    bd.set_option("twovar", 1)
+    M.iterate_(bd, maxiter=1, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    tv = M.beliefs_tu(bd)
+    assert tv[1][0][1] is not None and tv[1][1][2] is not None and tv[1][0][2] is None
+
+
 def test_k4_bond16_full_size_paths_vs_oracle():
     # complete graph K4, T=5, TruncBond(16): at the middle cuts D = 256 -> H=64 flat-tree QR, TSQR split (few ops per
     # launch) and the subspace-iteration SVD (d~X = 96..128 > 48) all run inside a real BP iteration

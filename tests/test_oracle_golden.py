@@ -87,6 +87,11 @@ def test_glauber_small_tree_vs_exact(generic):
     pb, _ = O.pair_beliefs(bp)
     pe = exact.exact_pair_marginals(bp, p)
     assert np.allclose(np.array(pb), np.array(pe), atol=1e-10)
+    f = lambda x, i: 2 * x - 3  # test/glauber_small_tree.jl:43-50: autocorrelations / autocovariances vs exact
+    r, rex = O.autocorrelations(bp, f), exact.exact_autocorrelations(bp, p, f)
+    assert np.allclose(np.array(r), np.array(rex), atol=1e-10)
+    mu = O.means(bp, f)
+    assert np.allclose(np.array(O.autocovariances(bp, f)), np.array([a - np.outer(m, m) for a, m in zip(rex, mu)]), atol=1e-10)
     for A in bp.mu:  # test/normalizations.jl:48-52
         assert abs(tt.lognormalization(A)) < 1e-10
 
