@@ -120,6 +120,31 @@ function beliefs(cu::CuMPBP{G,F}) where {G,F}
     end
 end
 
+# two-time marginals: switch on with enable_twovar!(cu; maxdist) BEFORE iterate! (they are computed with the beliefs)
+enable_twovar!(cu::CuMPBP; maxdist::Integer=cu.T) =
+    (check(ccall((:mpbp_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Float64), cu.h, "twovar", Float64(maxdist))); nothing)
+
+function beliefs_tu(cu::CuMPBP)
+    L = cu.T + 1; Q = maximum(Int.(cu.q))^2
+    out = zeros(Q, L, L, nv(cu.g))           # [x_t + q*x_u, u, t, i] in memory order
+    check(ccall((:mpbp_twovar_marginals, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), cu.h, out))
+    map(1:nv(cu.g)) do i
+        qi = Int(cu.q[i])
+        [t < u ? reshape(out[1:qi*qi, u, t, i], qi, qi) : zeros(qi, qi) for t in 1:L, u in 1:L]
+    end
+end
+
+function autocorrelations(f, cu::CuMPBP)
+    map(enumerate(beliefs_tu(cu))) do (i, tv)
+        expectation.(x -> f(x, i), tv)
+    end
+end
+
+function autocovariances(f, cu::CuMPBP)
+    μ = means(f, cu)
+    covariance.(autocorrelations(f, cu), μ)
+end
+
 function pair_beliefs(cu::CuMPBP)
     sizes = [Int(cu.q[i]) * Int(cu.q[j]) for (i, j) in edges(cu.g)]
     out = zeros(sum(sizes) * (cu.T + 1)); logz = zeros(nv(cu.g))
