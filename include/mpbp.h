@@ -109,6 +109,11 @@ int mpbp_free_energy(mpbp_handle h, double* f);
  * out[((i*L + t)*L + u)*Q + x_t + q_i*x_u], L = T+1, Q = qmax*qmax; entries with t >= u or u - t > maxdist are 0. */
 int mpbp_twovar_marginals(mpbp_handle h, double* out);
 
+/* alternate marginals p(x_i^t, x_j^{t+1}) of every directed edge i->j from the current messages (reference:
+ * alternate_marginals, src/mpbp.jl:270-280).  Same layout and size as the pair beliefs of mpbp_pair_beliefs:
+ * per edge e (T+1) blocks of q_src*q_dst doubles, out[...][t][x_i^t + q_src*x_j^{t+1}] for t < T; the block t = T is 0. */
+int mpbp_alternate_marginals(mpbp_handle h, double* out);
+
 /* ---- multi-GPU plumbing (no reference counterpart; see DESIGN.md "multi-GPU") ----
  * pack/unpack the fixed-capacity device slots of `n` messages into/from one contiguous DEVICE buffer so that
  * the host layer can exchange cut-edge messages with one collective.  slot size from mpbp_message_slot_bytes. */

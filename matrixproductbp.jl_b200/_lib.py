@@ -32,6 +32,7 @@ SIGNATURES = {
     "mpbp_pair_beliefs": (C.c_int, [C.c_void_p, c_dp, c_dp]),
     "mpbp_free_energy": (C.c_int, [C.c_void_p, c_dp]),
     "mpbp_twovar_marginals": (C.c_int, [C.c_void_p, c_dp]),
+    "mpbp_alternate_marginals": (C.c_int, [C.c_void_p, c_dp]),
     "mpbp_message_slot_bytes": (C.c_int64, [C.c_void_p]),
     "mpbp_pack_messages_dev": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, C.c_void_p]),
     "mpbp_unpack_messages_dev": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, C.c_void_p]),

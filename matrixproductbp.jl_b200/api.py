@@ -23,7 +23,7 @@ __all__ = [
     "BPFactor", "RecursiveBPFactor", "HomogeneousGlauberFactor", "PMJGlauberFactor", "IntegerGlauberFactor",
     "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
     "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
-    "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "pair_beliefs", "bethe_free_energy", "means",
+    "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_beliefs", "bethe_free_energy", "means",
     "reset_messages_", "glauber_factors", "MPBPError",
 ]
 
@@ -484,6 +484,32 @@ def pair_beliefs(bp: MPBP):
         res.append(np.stack([out[off + t * qs * qd: off + (t + 1) * qs * qd].reshape(qs, qd, order="F") for t in range(bp.T + 1)]))
         off += n
     return res, logz
+
+
+def alternate_marginals(bp: MPBP):
+    """alternate_marginals(bp)[e][t][x_i^t, x_j^{t+1}] for every directed edge e = i->j, t = 0..T-1 (src/mpbp.jl:270-280)"""
+    sizes = [int(bp.q[bp._src[e]]) * int(bp.q[bp._dst[e]]) for e in range(bp.E2)]
+    out = np.zeros(sum(sizes) * (bp.T + 1))
+    _lib.check(_lib.lib().mpbp_alternate_marginals(bp._h, _p(out, _lib.c_dp)))
+    res, off = [], 0
+    for e in range(bp.E2):
+        qs, qd = int(bp.q[bp._src[e]]), int(bp.q[bp._dst[e]])
+        res.append([out[off + t * qs * qd: off + (t + 1) * qs * qd].reshape(qs, qd, order="F").copy() for t in range(bp.T)])
+        off += qs * qd * (bp.T + 1)
+    return res
+
+
+def alternate_correlations(f, bp: MPBP):
+    """<f(x_i^t) f(x_j^{t+1})> per directed edge (src/mpbp.jl:282-286); states numbered from 1"""
+    res = []
+    for am in alternate_marginals(bp):
+        row = []
+        for p in am:
+            fi = np.array([f(x + 1) for x in range(p.shape[0])], dtype=float)
+            fj = np.array([f(x + 1) for x in range(p.shape[1])], dtype=float)
+            row.append(float(fi @ p @ fj))
+        res.append(row)
+    return res
 
 
 def free_energy_contributions(bp: MPBP):

@@ -181,6 +181,7 @@ int common_init(mpbp_state* h) {
     CUDA_OK(cudaFuncSetAttribute(k_damp, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_pair_belief, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_alt_marginal, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
   }
   const int L = h->L;
   h->qmax = *std::max_element(h->q.begin(), h->q.end());
@@ -1436,6 +1437,50 @@ int mpbp_pair_beliefs(mpbp_handle h, double* out, double* logz) {
       logz[j] += (1.0 / dj - 0.5) * lz[e];
     }
   }
+  return 0;
+}
+
+int mpbp_alternate_marginals(mpbp_handle h, double* out) {
+  if (!h || !out) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (ensure_arena(h)) return 1;
+  const int L = h->L, d = h->dmax;
+  const size_t smem = (4 + (size_t)h->qmax) * d * d * 8;
+  if (smem > (size_t)h->max_smem) return fail("alternate marginals: bond capacity %d exceeds the shared-memory tiling", d);
+  const MsgStore& m = h->msg[h->cur];
+  double* d_out;
+  CUDA_OK(cudaMalloc((void**)&d_out, sizeof(double) * std::max<int64_t>(h->psi_off[h->E2], 1)));
+  const size_t per = 8 * (size_t)(L + 1) * d * d + 512;
+  int64_t e0 = 0;
+  while (e0 < h->E2) {
+    h->arena.used = 0;
+    const int64_t maxn = std::max<int64_t>(1, (int64_t)((h->arena.cap / 2) / (per + sizeof(PairJob))));
+    const int64_t e1 = std::min(h->E2, e0 + maxn);
+    std::vector<PairJob> jobs;
+    for (int64_t e = e0; e < e1; ++e) {
+      PairJob jb;
+      memset(&jb, 0, sizeof jb);
+      const int qs = h->q[h->src[e]], qd = h->q[h->dst[e]];
+      jb.A = msg_ref(h, m, e, qs * qd);
+      jb.B = msg_ref(h, m, h->rev[e], qs * qd);
+      jb.psi = h->d_psi + h->psi_off[e];
+      jb.qs = qs;
+      jb.qd = qd;
+      jb.out = d_out + h->psi_off[e];
+      jb.Renv = (double*)h->arena.take(8 * (size_t)(L + 1) * d * d);
+      if (!jb.Renv) { cudaFree(d_out); return fail("arena exhausted (alternate marginals)"); }
+      jobs.push_back(jb);
+    }
+    PairJob* d_jobs;
+    if (upload_jobs(h, jobs, &d_jobs)) { cudaFree(d_out); return 1; }
+    k_alt_marginal<<<(unsigned)jobs.size(), NT, smem, h->st>>>(d_jobs, L, d);
+    h->n_launch++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->st));
+    e0 = e1;
+  }
+  CUDA_OK(cudaMemcpy(out, d_out, sizeof(double) * h->psi_off[h->E2], cudaMemcpyDeviceToHost));
+  cudaFree(d_out);
   return 0;
 }
 

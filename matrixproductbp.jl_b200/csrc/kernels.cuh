@@ -1565,6 +1565,155 @@ __global__ void __launch_bounds__(NT) k_pair_belief(const PairJob* jobs, int L, 
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
+// alternate marginals p(x_i^t, x_j^{t+1}) per directed edge i->j, t = 0..T-1 (src/mpbp.jl:270-280: the (t, t+1)
+// two-time marginal of the pair-belief MPEM summed over x_j^t and x_i^{t+1}).  One CTA per directed edge, d x d
+// environments as in k_pair_belief; with Lenv_t, Renv_{t+2} the environments around sites t, t+1:
+//   P_xs[a',b'] = sum_xd psi_t[xs,xd]      (A_t[xs,xd]^T  Lenv_t      B_t[xd,xs]   )[a',b']
+//   Q_y [a',b'] = sum_xs psi_{t+1}[xs,y]   (A_{t+1}[xs,y] Renv_{t+2}  B_{t+1}[y,xs]^T)[a',b']
+//   p[xs,y] ~ <P_xs, Q_y>.
+// dyn smem: (4 + qs) * dcap*dcap doubles.  out: [t][xs + qs*y], edge stride as for the pair beliefs (slot t = T unused).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_alt_marginal(const PairJob* jobs, int L, int dcap) {
+  extern __shared__ double smem[];
+  __shared__ double red[NW + 1];
+  __shared__ double pm[64];
+  const PairJob& jb = jobs[blockIdx.x];
+  const int qs = jb.qs, qd = jb.qd;
+  const int est = dcap * dcap;
+  double* tmp = smem;
+  double* L0 = smem + est;
+  double* L1 = smem + 2 * est;
+  double* Q = smem + 3 * est;
+  double* P = smem + 4 * est;  // [xs][a' + ar*b']
+  if (threadIdx.x == 0) jb.Renv[(size_t)L * est] = 1.0;
+  __syncthreads();
+  // backward environments, identical to k_pair_belief
+  for (int t = L - 1; t >= 0; --t) {
+    const int al = jb.A.bonds[t], ar = jb.A.bonds[t + 1], bl = jb.B.bonds[t], br = jb.B.bonds[t + 1];
+    const double* At = jb.A.data + (size_t)t * jb.A.stride;
+    const double* Bt = jb.B.data + (size_t)t * jb.B.stride;
+    const double* psi = jb.psi + (size_t)t * qs * qd;
+    const double* Rn = jb.Renv + (size_t)(t + 1) * est;
+    double* Rt = jb.Renv + (size_t)t * est;
+    for (int idx = threadIdx.x; idx < al * bl; idx += NT) Rt[idx] = 0.0;
+    __syncthreads();
+    for (int xs = 0; xs < qs; ++xs)
+      for (int xd = 0; xd < qd; ++xd) {
+        const double ps = psi[xs + qs * xd];
+        if (ps == 0.0) continue;
+        const double* Ax = At + (size_t)al * ar * (xs + qs * xd);
+        const double* Bx = Bt + (size_t)bl * br * (xd + qd * xs);
+        for (int idx = threadIdx.x; idx < al * br; idx += NT) {
+          const int a = idx % al, b2 = idx / al;
+          double acc = 0.0;
+          for (int a2 = 0; a2 < ar; ++a2) acc += Ax[a + al * a2] * Rn[a2 + ar * b2];
+          tmp[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < al * bl; idx += NT) {
+          const int a = idx % al, b = idx / al;
+          double acc = 0.0;
+          for (int b2 = 0; b2 < br; ++b2) acc += tmp[a + al * b2] * Bx[b + bl * b2];
+          Rt[idx] += ps * acc;
+        }
+        __syncthreads();
+      }
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < al * bl; idx += NT) mx = fmax(mx, fabs(Rt[idx]));
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < al * bl; idx += NT) Rt[idx] *= f;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) L0[0] = 1.0;
+  __syncthreads();
+  for (int t = 0; t < L - 1; ++t) {
+    const int al = jb.A.bonds[t], ar = jb.A.bonds[t + 1], bl = jb.B.bonds[t], br = jb.B.bonds[t + 1];
+    const int cr = jb.A.bonds[t + 2], dr = jb.B.bonds[t + 2];
+    const double* At = jb.A.data + (size_t)t * jb.A.stride;
+    const double* Bt = jb.B.data + (size_t)t * jb.B.stride;
+    const double* psi = jb.psi + (size_t)t * qs * qd;
+    const double* At1 = jb.A.data + (size_t)(t + 1) * jb.A.stride;
+    const double* Bt1 = jb.B.data + (size_t)(t + 1) * jb.B.stride;
+    const double* psi1 = jb.psi + (size_t)(t + 1) * qs * qd;
+    const double* Rn2 = jb.Renv + (size_t)(t + 2) * est;  // [a'' + cr*b'']
+    const int nab = ar * br;
+    for (int idx = threadIdx.x; idx < qs * est; idx += NT) P[idx] = 0.0;
+    __syncthreads();
+    for (int xs = 0; xs < qs; ++xs)
+      for (int xd = 0; xd < qd; ++xd) {
+        const double ps = psi[xs + qs * xd];
+        if (ps == 0.0) continue;
+        const double* Ax = At + (size_t)al * ar * (xs + qs * xd);
+        const double* Bx = Bt + (size_t)bl * br * (xd + qd * xs);
+        for (int idx = threadIdx.x; idx < ar * bl; idx += NT) {
+          const int a2 = idx % ar, b = idx / ar;
+          double acc = 0.0;
+          for (int a = 0; a < al; ++a) acc += Ax[a + al * a2] * L0[a + al * b];
+          tmp[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nab; idx += NT) {
+          const int a2 = idx % ar, b2 = idx / ar;
+          double acc = 0.0;
+          for (int b = 0; b < bl; ++b) acc += tmp[a2 + ar * b] * Bx[b + bl * b2];
+          P[(size_t)xs * est + idx] += ps * acc;
+        }
+        __syncthreads();
+      }
+    for (int y = 0; y < qd; ++y) {
+      for (int idx = threadIdx.x; idx < nab; idx += NT) Q[idx] = 0.0;
+      __syncthreads();
+      for (int xs = 0; xs < qs; ++xs) {
+        const double ps = psi1[xs + qs * y];
+        if (ps == 0.0) continue;
+        const double* Ax = At1 + (size_t)ar * cr * (xs + qs * y);
+        const double* Bx = Bt1 + (size_t)br * dr * (y + qd * xs);
+        for (int idx = threadIdx.x; idx < ar * dr; idx += NT) {
+          const int a = idx % ar, b2 = idx / ar;
+          double acc = 0.0;
+          for (int a2 = 0; a2 < cr; ++a2) acc += Ax[a + ar * a2] * Rn2[a2 + cr * b2];
+          tmp[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nab; idx += NT) {
+          const int a = idx % ar, b = idx / ar;
+          double acc = 0.0;
+          for (int b2 = 0; b2 < dr; ++b2) acc += tmp[a + ar * b2] * Bx[b + br * b2];
+          Q[idx] += ps * acc;
+        }
+        __syncthreads();
+      }
+      for (int xs = 0; xs < qs; ++xs) {
+        double part = 0.0;
+        for (int idx = threadIdx.x; idx < nab; idx += NT) part += P[(size_t)xs * est + idx] * Q[idx];
+        part = block_sum1(part, red);
+        if (threadIdx.x == 0) pm[xs + qs * y] = part;
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int i = 0; i < qs * qd; ++i) sum += pm[i];
+      for (int i = 0; i < qs * qd; ++i) jb.out[(size_t)t * qs * qd + i] = pm[i] / sum;
+    }
+    // Lenv_{t+1} = sum_xs P_xs, rescaled
+    double mx = 0.0;
+    for (int idx = threadIdx.x; idx < nab; idx += NT) {
+      double v = 0.0;
+      for (int xs = 0; xs < qs; ++xs) v += P[(size_t)xs * est + idx];
+      L1[idx] = v;
+      mx = fmax(mx, fabs(v));
+    }
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int idx = threadIdx.x; idx < nab; idx += NT) L0[idx] = L1[idx] * f;
+    __syncthreads();
+  }
+  if (threadIdx.x < qs * qd) jb.out[(size_t)(L - 1) * qs * qd + threadIdx.x] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Minit TT: [1,1,y,x] = prob_y0 per t
 struct InitJob {
   TTRef out;

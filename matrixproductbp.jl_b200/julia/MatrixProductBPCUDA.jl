@@ -157,6 +157,17 @@ function pair_beliefs(cu::CuMPBP)
     b, logz
 end
 
+function alternate_marginals(cu::CuMPBP)
+    sizes = [Int(cu.q[i]) * Int(cu.q[j]) for (i, j) in edges(cu.g)]
+    out = zeros(sum(sizes) * (cu.T + 1))
+    check(ccall((:mpbp_alternate_marginals, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), cu.h, out))
+    off = 0
+    map(edges(cu.g)) do (i, j)
+        qi, qj = Int(cu.q[i]), Int(cu.q[j])
+        am = [reshape(out[off+(t-1)*qi*qj+1:off+t*qi*qj], qi, qj) for t in 1:cu.T]; off += qi * qj * (cu.T + 1); am
+    end
+end
+
 function bethe_free_energy(cu::CuMPBP)
     f = zeros(nv(cu.g))
     check(ccall((:mpbp_free_energy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), cu.h, f))

@@ -80,6 +80,22 @@ def exact_autocorrelations(bp, p, f=lambda x, i: x):
     return out
 
 
+def exact_alternate_marginals(bp, p):
+    """p(x_i^t, x_j^{t+1}) for every directed edge i->j, t = 0..T-1 (exact_alternate_marginals of src/exact.jl)."""
+    g = bp.g
+    N, L = g.N, bp.T + 1
+    out = []
+    for e in range(g.ne):
+        i, j = g.src[e], g.dst[e]
+        row = []
+        for t in range(L - 1):
+            a, b = i * L + t, j * L + t + 1
+            m = p.sum(axis=tuple(c for c in range(N * L) if c not in (a, b)))
+            row.append(m if a < b else m.T)
+        out.append(row)
+    return out
+
+
 def onesample(bp, rng):
     """forward sample of the prior dynamics: x_i^0 ~ phi_i^0 (normalised), x_i^{t+1} ~ w_i^t(. | x_neigh^t, x_i^t)
     (the prior part of /root/reference/src/sampling.jl onesample; reweightings at t > 0 are NOT applied).  1-based states."""

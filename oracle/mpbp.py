@@ -426,3 +426,17 @@ def pair_beliefs(bp):
         b[e] = T_.marginals(P)
         logz[j] += (1 / g.degree(j) - 0.5) * T_.lognormalization(P)
     return b, logz
+
+
+def alternate_marginals(bp):
+    """mpbp.jl:270-280: p(x_i^t, x_j^{t+1}) for every directed edge i->j and t = 0..T-1, from the two-time marginals
+    of the pair-belief MPEM (twovar_marginals(pb)[t, t+1] summed over x_j^t and x_i^{t+1})."""
+    g = bp.g
+    L = bp.T + 1
+    out = []
+    for e in range(g.ne):
+        qi, qj = bp.q[g.src[e]], bp.q[g.dst[e]]
+        P = pair_belief_tt(bp.mu[e], bp.mu[g.rev[e]], bp.psi[e])
+        tv = T_.twovar_marginals(P)
+        out.append([np.asarray(tv[t][t + 1]).reshape(qi, qj, qi, qj).sum(axis=(1, 2)) for t in range(L - 1)])
+    return out

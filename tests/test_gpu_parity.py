@@ -574,6 +574,46 @@ def test_two_time_marginals_sirs_tree_exact_maxdist_and_loud_when_off():
     assert tv[1][0][1] is not None and tv[1][1][2] is not None and tv[1][0][2] is None
 
 
+def test_alternate_marginals_vs_oracle_and_exact():
+    # alternate_marginals (src/mpbp.jl:270-280): p(x_i^t, x_j^{t+1}) per directed edge; tree with psi (exact available)
+    # and a loopy truncated SIRS case (q = 3) against the oracle
+    from oracle import exact
+    T, N = 2, 5
+    rng = np.random.default_rng(2)
+    und = [(0, 1), (1, 2), (1, 3)]
+    go = O.BiDiGraph(N, und)
+    psi = [None] * go.ne
+    for e in range(go.ne):
+        if psi[e] is None:
+            ps = [0.5 + rng.random((2, 2)) for _ in range(T + 1)]
+            psi[e] = ps
+            psi[go.rev[e]] = [p.T.copy() for p in ps]
+    kinds = [("glauber", (1.0, float(rng.standard_normal()), 1.0)) for _ in range(N)]
+    phi = [[np.array([0.75, 0.25]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    phi[2][1] = np.array([1.0, 0.1])
+    bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, psi=psi, dmax=10)
+    O.iterate(bo, maxiter=5, trunc=OT.TruncBondThresh(10), tol=0.0)
+    M.iterate_(bd, maxiter=5, svd_trunc=M.TruncBondThresh(10, 0.0), tol=0.0, shuffle_nodes=False)
+    p, Z, _ = exact.exact_prob(bo)
+    amd, amo, amx = M.alternate_marginals(bd), O.alternate_marginals(bo), exact.exact_alternate_marginals(bo, p)
+    assert np.max(np.abs(np.array(amd) - np.array(amo))) < TOL and np.max(np.abs(np.array(amd) - np.array(amx))) < TOL
+    # loopy, q = 3, truncation active
+    T = 3
+    und = [(0, 1), (1, 2), (0, 2), (2, 3)]
+    N = 4
+    kinds = [("sirs", (0.3 + 0.05 * i, 0.15, 0.2, 0.02)) for i in range(N)]
+    phi = [[np.array([0.7, 0.25, 0.05]) if t == 0 else np.ones(3) for t in range(T + 1)] for _ in range(N)]
+    bo, bd = build_pair(N, und, T, kinds, [3] * N, phi, dmax=5)
+    tr = M.TruncBond(5)
+    O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0)
+    M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    amd, amo = M.alternate_marginals(bd), O.alternate_marginals(bo)
+    assert np.max(np.abs(np.array(amd) - np.array(amo))) < TOL
+    f = lambda x: x - 1
+    co = [[float(np.array([f(x + 1) for x in range(3)]) @ p @ np.array([f(x + 1) for x in range(3)])) for p in am] for am in amo]
+    assert np.max(np.abs(np.array(M.alternate_correlations(f, bd)) - np.array(co))) < TOL
+
+
 def test_k4_bond16_full_size_paths_vs_oracle():
     # complete graph K4, T=5, TruncBond(16): at the middle cuts D = 256 -> H=64 flat-tree QR, TSQR split (few ops per
     # launch) and the subspace-iteration SVD (d~X = 96..128 > 48) all run inside a real BP iteration

@@ -87,6 +87,8 @@ def test_glauber_small_tree_vs_exact(generic):
     pb, _ = O.pair_beliefs(bp)
     pe = exact.exact_pair_marginals(bp, p)
     assert np.allclose(np.array(pb), np.array(pe), atol=1e-10)
+    am, amex = O.alternate_marginals(bp), exact.exact_alternate_marginals(bp, p)  # test/glauber_small_tree.jl:58-61,66
+    assert np.allclose(np.array(am), np.array(amex), atol=1e-10)
     f = lambda x, i: 2 * x - 3  # test/glauber_small_tree.jl:43-50: autocorrelations / autocovariances vs exact
     r, rex = O.autocorrelations(bp, f), exact.exact_autocorrelations(bp, p, f)
     assert np.allclose(np.array(r), np.array(rex), atol=1e-10)
