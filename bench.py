@@ -257,11 +257,14 @@ def run_gpu(args, rank, world, local_rank):
     d2h = int(nphi * 8 + g.N * 8)
     if rank == 0:
         qr_tf = ctr["qr_flops"] / (ctr["qr_ms"] * 1e-3) / 1e12 if ctr["qr_ms"] > 0 else 0.0
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "qr_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = (f"ncu --set full capture of ONE isolated launch ({tj.get('launch')}; {tj.get('kernel')}; algorithmic bytes of that launch "
+                                f"{tj.get('algorithmic_bytes_per_launch')}); the H=64 variant used for D >= 200 halves the R re-reads; not re-captured")
             except Exception:
                 traffic = None
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -276,7 +279,7 @@ def run_gpu(args, rank, world, local_rank):
                     e2e=dict(value=edges_total / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=launches,
                     roofline=dict(kernel="k_qr_ft (flat-tree DMMA Q-less QR of the bond-D sweep, csrc/qr_ft.cuh)", bound="tensor", achieved=qr_tf, peak=float(peak[0]),
-                                  unit="TFLOP/s", frac=qr_tf / float(peak[0]) if peak[0] > 0 else None, traffic=traffic,
+                                  unit="TFLOP/s", frac=qr_tf / float(peak[0]) if peak[0] > 0 else None, traffic=traffic, traffic_note=traffic_note,
                                   peak_source="FP64 DMMA (mma.sync m8n8k4 f64) measured live by mpbp_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 entry",
                                   algorithmic_flops=ctr["qr_flops"], kernel_ms=ctr["qr_ms"], share_of_step=ctr["qr_ms"] / prof_ms if prof_ms > 0 else None,
                                   measured_on=f"one extra profiled step right after the timed region (single-stream launches, {prof_ms:.0f} ms); the timed steps use 4 concurrent streams",
