@@ -278,3 +278,33 @@ def test_schedules_share_fixed_point():
         O.iterate(bp, maxiter=200, trunc=tt.TruncBond(3), tol=1e-13, schedule=sched)
         res.append(np.array(O.beliefs(bp)))
     assert np.allclose(res[0], res[1], atol=1e-7)
+
+
+def test_mpem_evaluate_is_invariant_under_orthogonalisation_and_mpem2():
+    # /root/reference/test/mpems.jl:3-40: evaluate(A, x) unchanged by orthogonalize_left! (MPEM1, MPEM2), by compress!
+    # with a non-binding truncation, and by the MPEM3 -> MPEM2 conversion
+    rng = np.random.default_rng(4)
+    for phys, T, d in (((2,), 10, 4), ((2, 2), 5, 4), ((3, 2), 4, 3)):
+        A = tt.rand_tt([1] + [d] * T + [1], *phys, rng=rng)
+        xs = [[tuple(rng.integers(0, p) for p in phys) for _ in range(T + 1)] for _ in range(5)]
+        e1 = [A.evaluate(x) for x in xs]
+        B = A.copy()
+        tt.orthogonalize_left(B, tt.TruncThresh(0.0))
+        assert np.allclose([B.evaluate(x) for x in xs], e1, rtol=1e-10)
+        B = A.copy()
+        tt.orthogonalize_right(B, tt.TruncThresh(0.0))
+        assert np.allclose([B.evaluate(x) for x in xs], e1, rtol=1e-10)
+        B = A.copy()
+        tt.compress(B, tt.TruncBond(d * d))
+        assert np.allclose([B.evaluate(x) for x in xs], e1, rtol=1e-10)
+        assert abs(tt.lognormalization(A)) < 1e-10  # rand_tt normalises
+    Bs = [rng.random((1, 3, 2, 2, 2)), rng.random((3, 4, 2, 2, 2)), rng.random((4, 1, 2, 2, 2))]
+    Bs[-1][:, :, :, :, 1] = Bs[-1][:, :, :, :, 0]
+    C = O.mpem2(Bs, 0.0)
+    for _ in range(8):
+        x = [tuple(rng.integers(0, 2, size=2)) for _ in range(3)]
+        M = np.ones((1, 1))
+        for t in range(3):
+            xn = x[t + 1][0] if t < 2 else 0
+            M = M @ Bs[t][:, :, x[t][0], x[t][1], xn]
+        assert abs(C.evaluate(x) - M[0, 0]) < 1e-12 * max(1.0, abs(M[0, 0]))
