@@ -308,3 +308,46 @@ def test_mpem_evaluate_is_invariant_under_orthogonalisation_and_mpem2():
             xn = x[t + 1][0] if t < 2 else 0
             M = M @ Bs[t][:, :, x[t][0], x[t][1], xn]
         assert abs(C.evaluate(x) - M[0, 0]) < 1e-12 * max(1.0, abs(M[0, 0]))
+
+
+@pytest.mark.parametrize("kind", ["pmj", "integer"])
+def test_pmj_and_integer_glauber_small_tree_vs_exact(kind):
+    # /root/reference/test/glauber_pmJ_small_tree.jl:1-63 (J = +-1 on a 4-node star-like tree, beta = 2, T = 3,
+    # TruncThresh(0.0)) and the IntegerGlauber testset of test/glauber_small_tree.jl:174-230 (integer couplings)
+    rng = np.random.default_rng(111)
+    T, N = 3, 4
+    und = [(0, 1), (1, 2), (1, 3)]
+    Jm = {frozenset((0, 1)): -1, frozenset((1, 2)): 1, frozenset((1, 3)): 1} if kind == "pmj" else \
+         {frozenset((0, 1)): -2, frozenset((1, 2)): 1, frozenset((1, 3)): 3}
+    g = O.BiDiGraph(N, und)
+    h = rng.standard_normal(N)
+    beta = 2.0 if kind == "pmj" else 0.7
+    w = []
+    for i in range(N):
+        nb = [g.dst[e] for e in g.out_edges[i]]
+        Ji = [Jm[frozenset((i, j))] for j in nb]
+        if kind == "pmj":
+            w.append([F.PMJGlauberFactor(Ji, 1.0, float(h[i]), beta)] * (T + 1))
+        else:
+            w.append([F.IntegerGlauberFactor(Ji, float(h[i]), beta)] * (T + 1))
+    phi = [[np.array([0.75, 0.25]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    for _ in range(N):
+        i, t = rng.integers(N), rng.integers(1, T + 1)
+        o = np.full(2, 1e-2)
+        o[rng.integers(2)] = 1.0
+        phi[i][t] = phi[i][t] * o
+    bp = O.MPBP(g, w, [2] * N, T, phi=phi)
+    O.iterate(bp, maxiter=20, trunc=tt.TruncThresh(0.0), tol=0.0)
+    p, Z, _ = exact.exact_prob(bp)
+    assert abs(np.exp(-O.bethe_free_energy(bp)) - Z) < 1e-9 * Z
+    assert np.allclose(np.array(O.beliefs(bp)), np.array(exact.exact_marginals(bp, p)), atol=1e-10)
+    f = lambda x, i: 2 * x - 3
+    assert np.allclose(np.array(O.autocorrelations(bp, f)), np.array(exact.exact_autocorrelations(bp, p, f)), atol=1e-10)
+    # the recursive interface reproduces the factor's own definition
+    for i in range(N):
+        z = len(g.out_edges[i])
+        for xs in np.ndindex(*([2] * z)):
+            for xn in (1, 2):
+                for x in (1, 2):
+                    xs1 = [v + 1 for v in xs]
+                    assert abs(F.RecursiveBPFactor.__call__(w[i][0], xn, xs1, x) - w[i][0](xn, xs1, x)) < 1e-14
