@@ -351,3 +351,73 @@ def test_pmj_and_integer_glauber_small_tree_vs_exact(kind):
                 for x in (1, 2):
                     xs1 = [v + 1 for v in xs]
                     assert abs(F.RecursiveBPFactor.__call__(w[i][0], xn, xs1, x) - w[i][0](xn, xs1, x)) < 1e-14
+
+
+def test_periodic_glauber_tree_with_pair_observations_vs_exact():
+    # /root/reference/test/periodic.jl:1-75: periodic-in-time Glauber on a small tree with pair observations,
+    # TruncBondThresh(10) (non-binding); Z and marginals against brute force of the wrapped dynamics
+    from oracle import periodic as P
+    rng = np.random.default_rng(111)
+    T, N = 2, 5
+    und = [(0, 1), (1, 2), (1, 3)]
+    g = O.BiDiGraph(N, und)
+    h = rng.standard_normal(N)
+    w = [[F.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0)] * (T + 1) for i in range(N)]
+    obs = [(0, 1, 1, np.array([[0.1, 0.9], [0.3, 0.4]])), (1, 3, 2, np.array([[0.4, 0.6], [0.5, 0.9]])), (1, 2, T, rng.random((2, 2)))]
+    psi = [[np.ones((2, 2)) for _ in range(T + 1)] for _ in range(g.ne)]
+    for (i, j, t, m) in obs:
+        for e in range(g.ne):
+            if g.src[e] == i and g.dst[e] == j:
+                psi[e][t] = psi[e][t] * m
+            if g.src[e] == j and g.dst[e] == i:
+                psi[e][t] = psi[e][t] * m.T
+    phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(N)]
+    for i in range(N):
+        phi[i][0] = np.array([0.75, 0.25])
+    phi[2][1] = np.array([1.0, 0.1])
+    phi[0][2] = np.array([0.3, 1.0])
+    bp = P.PeriodicMPBP(g, w, [2] * N, T, phi=phi, psi=psi)
+    P.iterate(bp, maxiter=8, trunc=tt.TruncBondThresh(10))
+    p, logZ = P.exact_prob(bp)
+    assert abs(-P.bethe_free_energy(bp) - logZ) < 1e-10
+    L = T + 1
+    be = [[p.sum(axis=tuple(a for a in range(N * L) if a != i * L + t)) for t in range(L)] for i in range(N)]
+    assert np.allclose(np.array(P.beliefs(bp)), np.array(be), atol=1e-10)
+    for A in bp.mu:
+        assert abs(P.lognormalization(A)) < 1e-10
+        assert max(max(a.shape[:2]) for a in A) <= 10  # every bond, the closing one included, obeys the cap
+
+
+def test_periodic_sis_tree_vs_exact_and_ring_invariances():
+    from oracle import periodic as P
+    rng = np.random.default_rng(3)
+    T, N = 3, 3
+    g = O.BiDiGraph(N, [(0, 1), (1, 2)])
+    w = [[F.SISFactor(0.3, 0.25, 0.05)] * (T + 1) for _ in range(N)]
+    phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(N)]
+    phi[0][1] = np.array([0.2, 1.0])
+    phi[2][3] = np.array([1.0, 0.4])
+    bp = P.PeriodicMPBP(g, w, [2] * N, T, phi=phi)
+    P.iterate(bp, maxiter=6, trunc=tt.TruncThresh(0.0))
+    p, logZ = P.exact_prob(bp)
+    assert abs(-P.bethe_free_energy(bp) - logZ) < 1e-10
+    L = T + 1
+    be = [[p.sum(axis=tuple(a for a in range(N * L) if a != i * L + t)) for t in range(L)] for i in range(N)]
+    assert np.allclose(np.array(P.beliefs(bp)), np.array(be), atol=1e-10)
+    # /root/reference/test/mpems.jl:42-65: evaluate is invariant under ring orthogonalisation and periodic mpem2
+    A = tt.TT([rng.random((4, 4, 2, 2)) for _ in range(6)])
+    xs = [[tuple(rng.integers(0, 2, size=2)) for _ in range(6)] for _ in range(6)]
+    e1 = [P.evaluate(A, x) for x in xs]
+    for fn in (lambda B: P.orthogonalize_left(B, tt.TruncThresh(0.0)), lambda B: P.orthogonalize_right(B, tt.TruncThresh(0.0)),
+               lambda B: P.compress(B, tt.TruncBond(64))):
+        B = A.copy()
+        fn(B)
+        assert np.allclose([P.evaluate(B, x) for x in xs], e1, rtol=1e-9)
+    Bs = [rng.random((2, 3, 2, 2, 2)), rng.random((3, 4, 2, 2, 2)), rng.random((4, 2, 2, 2, 2))]
+    C = P.mpem2(Bs, 0.0)
+    for _ in range(8):
+        x = [tuple(rng.integers(0, 2, size=2)) for _ in range(3)]
+        M = np.eye(2)
+        for t in range(3):
+            M = M @ Bs[t][:, :, x[t][0], x[t][1], x[(t + 1) % 3][0]]
+        assert abs(P.evaluate(C, x) - np.trace(M)) < 1e-12 * max(1.0, abs(np.trace(M)))
