@@ -10,9 +10,10 @@ module MatrixProductBPCUDA
 
 using MatrixProductBP
 using MatrixProductBP: MPBP, BPFactor, RecursiveBPFactor, nstates, prob_y, prob_xy, prob_yy, prob_y0,
-    prob_y_partial, getT, CB_BP
+    prob_y_partial, getT, CB_BP, expectation, covariance
 using IndexedGraphs, TensorTrains, SparseArrays
-import MatrixProductBP: iterate!, beliefs, pair_beliefs, bethe_free_energy, reset_messages!
+import MatrixProductBP: iterate!, beliefs, pair_beliefs, bethe_free_energy, reset_messages!, means, beliefs_tu,
+    autocorrelations, autocovariances, alternate_marginals
 
 const LIB = get(ENV, "MPBP_B200_LIB", joinpath(@__DIR__, "..", "libmpbp_b200.so"))
 
@@ -119,6 +120,8 @@ function beliefs(cu::CuMPBP{G,F}) where {G,F}
         b = [out[off+(t-1)*cu.q[i]+1:off+t*cu.q[i]] for t in 1:cu.T+1]; off += cu.q[i] * (cu.T + 1); b
     end
 end
+
+means(f, cu::CuMPBP) = [[expectation(x -> f(x, i), bt) for bt in b] for (i, b) in enumerate(beliefs(cu))]
 
 # two-time marginals: switch on with enable_twovar!(cu; maxdist) BEFORE iterate! (they are computed with the beliefs)
 enable_twovar!(cu::CuMPBP; maxdist::Integer=cu.T) =
