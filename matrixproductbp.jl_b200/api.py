@@ -23,7 +23,7 @@ __all__ = [
     "BPFactor", "RecursiveBPFactor", "HomogeneousGlauberFactor", "PMJGlauberFactor", "IntegerGlauberFactor",
     "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
     "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
-    "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_beliefs", "bethe_free_energy", "means",
+    "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_correlations", "pair_beliefs", "bethe_free_energy", "means",
     "reset_messages_", "glauber_factors", "MPBPError",
 ]
 
@@ -484,6 +484,16 @@ def pair_beliefs(bp: MPBP):
         res.append(np.stack([out[off + t * qs * qd: off + (t + 1) * qs * qd].reshape(qs, qd, order="F") for t in range(bp.T + 1)]))
         off += n
     return res, logz
+
+
+def pair_correlations(f, bp: MPBP):
+    """<f(x_i^t) f(x_j^t)> per directed edge i->j (src/mpbp.jl:263-267); states numbered from 1"""
+    res = []
+    for pb in pair_beliefs(bp)[0]:
+        fi = np.array([f(x + 1) for x in range(pb.shape[1])], dtype=float)
+        fj = np.array([f(x + 1) for x in range(pb.shape[2])], dtype=float)
+        res.append([float(fi @ p @ fj) for p in pb])
+    return res
 
 
 def alternate_marginals(bp: MPBP):
