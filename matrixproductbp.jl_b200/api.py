@@ -24,7 +24,7 @@ __all__ = [
     "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
     "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
     "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_correlations", "pair_beliefs", "bethe_free_energy", "means",
-    "reset_messages_", "glauber_factors", "MPBPError",
+    "reset_messages_", "glauber_factors", "MPBPError", "onesample", "draw_node_observations_",
 ]
 
 MPBPError = _lib.MPBPError
@@ -530,6 +530,23 @@ def free_energy_contributions(bp: MPBP):
 
 def bethe_free_energy(bp: MPBP):
     return float(np.sum(free_energy_contributions(bp)))
+
+
+def onesample(bp: MPBP, rng=None):
+    """onesample(bp) -> (X, weight): forward sample of the prior dynamics of bp (host side, src/sampling.jl:30-66)"""
+    from .sampling import onesample as _one
+    return _one(bp.g, bp.w, bp.q, bp.T, bp.phi, None if bp.infinite else bp.psi, rng)
+
+
+def draw_node_observations_(bp: MPBP, nobs, rng=None, **kw):
+    """draw_node_observations!(bp, nobs): sample a trajectory from the prior, observe `nobs` of its entries (reweightings
+    bp.phi updated in place and uploaded), return (X, observed) -- src/sampling.jl:205-210"""
+    from .sampling import draw_node_observations_ as _draw
+    rng = np.random.default_rng(rng)
+    X, _ = onesample(bp, rng)
+    _, observed = _draw(bp.phi, X, nobs, rng=rng, **kw)
+    bp.sync_reweightings()
+    return X, observed
 
 
 def reset_messages_(bp: MPBP):

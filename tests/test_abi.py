@@ -92,3 +92,34 @@ def test_graph_edge_order_matches_reference_convention():
     assert list(zip(g.src, g.dst)) == [(0, 1), (0, 2), (0, 3), (1, 0), (2, 0), (3, 0)]
     assert list(g.rev) == [3, 4, 5, 0, 1, 2]
     assert list(g.colptr) == [0, 3, 4, 5, 6]
+
+
+def test_host_sampler_and_observation_drawing():
+    """src/sampling.jl:30-66,191-210 restated on the host: prior forward sampling and (soft) one-hot reweightings"""
+    import numpy as np
+    import mpbp_b200 as M
+    from mpbp_b200.sampling import draw_node_observations_, onesample
+    N, T = 12, 6
+    g = M.IndexedBiDiGraph(N, [(i, (i + 1) % N) for i in range(N)] + [(0, 6)])
+    w = [[M.SIRSFactor(0.6, 0.3, 0.2, 0.05)] * (T + 1) for _ in range(N)]
+    q = [3] * N
+    phi = [[np.array([0.5, 0.5, 0.0]) if t == 0 else np.ones(3) for t in range(T + 1)] for _ in range(N)]
+    X, wgt = onesample(g, w, q, T, phi, rng=7)
+    X2, _ = onesample(g, w, q, T, phi, rng=7)
+    assert X.shape == (N, T + 1) and np.array_equal(X, X2) and wgt == 1.0
+    assert set(np.unique(X)) <= {1, 2, 3} and not np.any(X[:, 0] == 3)
+    # SIRS: S -> R and R -> I never happen in one step
+    for t in range(T):
+        assert not np.any((X[:, t] == 1) & (X[:, t + 1] == 3)) and not np.any((X[:, t] == 3) & (X[:, t + 1] == 2))
+    _, obs = draw_node_observations_(phi, X, 10, rng=1)
+    assert len(obs) == 10 and obs == sorted(obs) and len(set(obs)) == 10
+    for (i, t) in obs:
+        assert phi[i][t][X[i, t] - 1] > 0 and np.count_nonzero(phi[i][t]) == 1
+    phi2 = [[np.ones(3) for _ in range(T + 1)] for _ in range(N)]
+    _, obs2 = draw_node_observations_(phi2, X, N, softinf=100.0, last_time=True, rng=2)
+    assert all(t == T for _, t in obs2) and len(obs2) == N
+    i, t = obs2[0]
+    assert abs(phi2[i][t][X[i, t] - 1] - 100.0 / 101.0) < 1e-12 and abs(phi2[i][t].min() - 1.0 / 101.0) < 1e-12
+    # the likelihood weight accounts for reweightings at t > 0
+    Xw, wgt2 = onesample(g, w, q, T, phi2, rng=7)
+    assert 0.0 < wgt2 < 1.0
