@@ -208,8 +208,10 @@ __device__ __forceinline__ void c2_stream(double (&a)[C2_RPL][FT_B], const int j
   c2_store_rblock(R, ldr, j0, c0, n, false, rnew);
 }
 
+// same contract as qr_ft_cta<64> (drop-in once validated): A m x n row-major read-only, R n x n fully overwritten with
+// the upper-triangular factor, optionally divided by its max-abs
 __device__ void qr_chain2_cta(const double* __restrict__ A, const int m, const int n, const int lda, double* __restrict__ R, const int ldr,
-                              double* smem) {
+                              const bool normalize, double* smem) {
   constexpr int H = C2_H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n8 = (n + 7) & ~7;
@@ -273,11 +275,28 @@ __device__ void qr_chain2_cta(const double* __restrict__ A, const int m, const i
     }
   }
   __syncthreads();
+  if (normalize) {
+    __shared__ double redn[NW + 1];
+    double mx = 0.0;
+    for (int idx = tid; idx < n * n; idx += NT) {
+      const int i = idx / n, c = idx % n;
+      if (c >= i) mx = fmax(mx, fabs(R[(size_t)i * ldr + c]));
+    }
+    mx = block_max(mx, redn);
+    if (mx > 0.0 && isfinite(mx)) {
+      const double fs = 1.0 / mx;
+      for (int idx = tid; idx < n * n; idx += NT) {
+        const int i = idx / n, c = idx % n;
+        if (c >= i) R[(size_t)i * ldr + c] *= fs;
+      }
+    }
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(NT, 1) k_chain2(const double* A, int m, int n, double* R) {
   extern __shared__ double smem[];
-  qr_chain2_cta(A + (size_t)blockIdx.x * m * n, m, n, n, R + (size_t)blockIdx.x * n * n, n, smem);
+  qr_chain2_cta(A + (size_t)blockIdx.x * m * n, m, n, n, R + (size_t)blockIdx.x * n * n, n, false, smem);
 }
 __global__ void __launch_bounds__(NT, 1) k_base(const double* A, int m, int n, double* R) {
   extern __shared__ double smem[];
