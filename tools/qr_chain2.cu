@@ -149,8 +149,8 @@ __device__ __forceinline__ void c2_factor(double (&a)[C2_RPL][FT_B], const int j
 #pragma unroll
       for (int c = k + 1; c < FT_B; ++c) rrow[c] = rk[c];
     }
-    // rows of R_jj below k are untouched by reflector k, but the rows k' > k still to be broadcast must see the
-    // updates of the earlier reflectors?  No: reflector k only changes row k of the R part (its R component is e_k).
+    // reflector k only changes row k of the R part (its R component is e_k): the rows k' > k broadcast later from
+    // rpre are still the original ones
     T[k][k] = tau;
 #pragma unroll
     for (int x = 0; x < k; ++x) {
