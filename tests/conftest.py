@@ -10,3 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+
+
+def pytest_sessionstart(session):
+    """a fresh checkout has no built library (it is git-ignored): build it once, like the driver's build() step"""
+    lib = os.path.join(ROOT, "matrixproductbp.jl_b200", "libmpbp_b200.so")
+    if not os.path.exists(lib):
+        import shutil
+        if shutil.which("nvcc"):
+            import __graft_entry__ as G
+            G.build()
