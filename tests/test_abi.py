@@ -123,3 +123,35 @@ def test_host_sampler_and_observation_drawing():
     # the likelihood weight accounts for reweightings at t > 0
     Xw, wgt2 = onesample(g, w, q, T, phi2, rng=7)
     assert 0.0 < wgt2 < 1.0
+
+
+def test_glauber_factor_selection_matches_the_transition_probability():
+    """glauber_factors (src/Models/glauber/glauber_bp.jl:121-142): homogeneous / +-J / integer / generic couplings pick
+    different factor types, all of which must equal 1 / (1 + exp(-2 beta s' (sum_j J_ij s_j + h_i)))"""
+    import itertools
+    import math
+    import numpy as np
+    import mpbp_b200 as M
+    g = M.IndexedBiDiGraph(5, [(0, 1), (1, 2), (1, 3), (3, 4), (0, 3)])
+    rng = np.random.default_rng(0)
+    nund = len(g.undirected)
+    cases = {
+        M.HomogeneousGlauberFactor: np.full(nund, 0.7),
+        M.PMJGlauberFactor: 0.7 * rng.choice([-1.0, 1.0], size=nund) * np.array([1, -1] + [1] * (nund - 2)),
+        M.IntegerGlauberFactor: np.array([1.0, -2.0, 3.0, 1.0, 2.0][:nund]),
+        M.GenericGlauberFactor: rng.standard_normal(nund),
+    }
+    h, beta, T = rng.standard_normal(5), 1.3, 2
+    spin = lambda x: 3 - 2 * x  # potts2spin: 1 -> +1, 2 -> -1
+    for cls, J in cases.items():
+        w = M.glauber_factors(M.Ising(g, J=J, h=h, beta=beta), T)
+        assert len(w) == 5 and all(len(wi) == T + 1 for wi in w)
+        assert all(type(wi[0]) is cls for wi in w), (cls, [type(wi[0]).__name__ for wi in w])
+        for i in range(5):
+            nb = g.neighbors(i)
+            Ji = [J[g.und_of[e]] for e in g.outedges(i)]
+            for xs in itertools.product((1, 2), repeat=len(nb)):
+                field = sum(j * spin(x) for j, x in zip(Ji, xs)) + h[i]
+                for xn in (1, 2):
+                    p = 1.0 / (1.0 + math.exp(-2.0 * beta * spin(xn) * field))
+                    assert abs(w[i][0](xn, list(xs), 1) - p) < 1e-12, (cls.__name__, i, xs, xn)
