@@ -155,3 +155,35 @@ def test_glauber_factor_selection_matches_the_transition_probability():
                 for xn in (1, 2):
                     p = 1.0 / (1.0 + math.exp(-2.0 * beta * spin(xn) * field))
                     assert abs(w[i][0](xn, list(xs), 1) - p) < 1e-12, (cls.__name__, i, xs, xn)
+
+
+def test_truncation_policies_and_graph_builders():
+    """(kind, d, eps) passed through the C ABI must select the same number of singular values as the oracle's
+    TensorTrains restatement; the graph builders agree on the reference's CSC edge order"""
+    import numpy as np
+    import networkx as nx
+    import mpbp_b200 as M
+    from oracle import tt as OT
+    from tests.common import otrunc
+    lam = np.array([3.0, 1.0, 0.5, 1e-3, 1e-9, 0.0])
+
+    def keep_abi(tr):  # the rule the device applies (csrc/common.cuh trunc_keep), restated
+        n = len(lam)
+        if tr.kind == 0:
+            return min(n, tr.d)
+        k = max(1, max([i + 1 for i in range(n) if lam[i] > tr.eps * np.linalg.norm(lam)], default=1))
+        return min(k, tr.d) if tr.kind == 2 else k
+
+    for tr in (M.TruncBond(2), M.TruncBond(10), M.TruncBondMax(3), M.TruncThresh(0.0), M.TruncThresh(1e-2), M.TruncThresh(1e-6),
+               M.TruncBondThresh(2, 1e-6), M.TruncBondThresh(5, 1e-2), M.TruncBondThresh(4)):
+        assert (tr.kind, tr.d >= 0, tr.eps >= 0.0) == (tr.kind, True, True)
+        assert keep_abi(tr) == otrunc(tr).keep(lam), tr
+    G = nx.petersen_graph()
+    g1 = M.IndexedBiDiGraph.from_networkx(G)
+    g2 = M.IndexedBiDiGraph.from_adjacency(nx.to_numpy_array(G))
+    g3 = M.IndexedBiDiGraph(10, list(G.edges()))
+    for g in (g2, g3):
+        assert np.array_equal(g.src, g1.src) and np.array_equal(g.dst, g1.dst) and np.array_equal(g.rev, g1.rev)
+    assert np.all(np.diff(g1.src) >= 0) and all(np.all(np.diff(g1.neighbors(i)) > 0) for i in range(10))  # sorted by (src, dst)
+    assert np.array_equal(g1.src[g1.rev], g1.dst) and np.array_equal(g1.dst[g1.rev], g1.src)
+    assert g1.ne == 30 and all(g1.degree(i) == 3 for i in range(10))
