@@ -421,3 +421,42 @@ def test_periodic_sis_tree_vs_exact_and_ring_invariances():
         for t in range(3):
             M = M @ Bs[t][:, :, x[t][0], x[t][1], x[(t + 1) % 3][0]]
         assert abs(P.evaluate(C, x) - np.trace(M)) < 1e-12 * max(1.0, abs(np.trace(M)))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small_trees_are_exact(seed):
+    """property the reference relies on throughout its test-suite: on a tree, with a non-binding truncation, MPBP is
+    exact (Z, one- and two-node marginals) for every model, any reweightings and any pair observations"""
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(3, 6))
+    T = int(rng.integers(1, 3))
+    und = [(int(rng.integers(0, k)), k) for k in range(1, N)]  # random recursive tree
+    g = O.BiDiGraph(N, und)
+    model = ["glauber", "sis", "sirs"][seed % 3]
+    q = 3 if model == "sirs" else 2
+    w = []
+    for i in range(N):
+        if model == "glauber":
+            f = F.HomogeneousGlauberFactor(float(rng.normal()), float(rng.normal()), 1.0)
+        elif model == "sis":
+            f = F.SISFactor(float(rng.random()), float(rng.random()), 0.2 * float(rng.random()))
+        else:
+            f = F.SIRSFactor(float(rng.random()), float(rng.random()), float(rng.random()), 0.2 * float(rng.random()))
+        w.append([f] * (T + 1))
+    phi = [[0.1 + rng.random(q) for _ in range(T + 1)] for _ in range(N)]
+    psi = [None] * g.ne
+    for e in range(g.ne):
+        if psi[e] is None:
+            ps = [0.2 + rng.random((q, q)) for _ in range(T + 1)]
+            psi[e] = ps
+            psi[g.rev[e]] = [p.T.copy() for p in ps]
+    bp = O.MPBP(g, w, [q] * N, T, phi=phi, psi=psi)
+    O.iterate(bp, maxiter=N + 2, trunc=tt.TruncThresh(0.0), tol=0.0)
+    p, Z, logZ = exact.exact_prob(bp)
+    assert abs(-O.bethe_free_energy(bp) - logZ) < 1e-9
+    assert np.allclose(np.array(O.beliefs(bp)), np.array(exact.exact_marginals(bp, p)), atol=1e-10)
+    pb, _ = O.pair_beliefs(bp)
+    assert np.allclose(np.array(pb), np.array(exact.exact_pair_marginals(bp, p)), atol=1e-10)
+    assert np.allclose(np.array(O.alternate_marginals(bp)), np.array(exact.exact_alternate_marginals(bp, p)), atol=1e-10)
+    fobs = lambda x, i: x * x - 1.5
+    assert np.allclose(np.array(O.autocorrelations(bp, fobs)), np.array(exact.exact_autocorrelations(bp, p, fobs)), atol=1e-10)
