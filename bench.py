@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- BP edge-updates/sec, FP64, T=50, bond dim 20 (BASELINE.json metric), Glauber on an Erdos-Renyi
-graph c=4 (configs[2] shape) with N scaled so that one step (= one Jacobi BP iteration over every node of the
-synthetic graph) fits the time budget.  Weak scaling: --nodes-per-gpu nodes per rank, edges cut by a contiguous
-node partition, one halo exchange of cut-edge messages per step.
+"""bench.py -- BP edge-updates/sec, FP64 (BASELINE.json metric) on the five BASELINE configs.
 
-  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA engine through the C-ABI)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+  python bench.py --gpus N --steps K --warmup W              # default workload: --config 3 (the metric's configuration)
+  python bench.py --config {1..5} ...                        # the other BASELINE configs (SURVEY.md 8d inputs)
+  python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host cores (oracle port)
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+--config 3 (default): Glauber on an Erdos-Renyi graph c=4, T=50, TruncBond(20); N = --nodes-per-gpu x ranks (weak
+scaling: the full N=1e5 needs 261 GB of messages and ~1e17 flop per iteration).  A step = one Jacobi BP iteration over
+every node; node partition across ranks, ONE halo exchange of cut-edge messages per step.
+
+Step budget of one run: W warm-up + K timed + 1 profiled (single stream, per-kernel-family CUDA events -> roofline)
++ 1 end-to-end (host buffers) steps.  Prints ONE JSON line (rank 0); DESIGN.md section 7 defines every field.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -22,81 +26,246 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "BP edge-updates/sec, FP64, T=50 bond dim 20"
 UNIT = "edge-updates/s"
 
 
-def make_workload(ntot, seed=1):
+# ------------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs as concrete synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def workload(args, world):
+    """returns dict(name, metric, kind, params, q, T, d, N, und, infinite_k, phi_fn, trunc, nodes_per_gpu)"""
     import networkx as nx
-    G = nx.fast_gnp_random_graph(ntot, 4.0 / ntot, seed=seed)
-    return ntot, [(int(a), int(b)) for a, b in G.edges()]
+    c = args.config
+    T = args.T
+    if c == 1:
+        # test/glauber_small_tree.jl:6-24: N=5 tree, T=2, beta=J=1, h ~ N(0,1), phi0=[.75,.25], TruncBondThresh(10)
+        T = 2 if T is None else T
+        und = [(0, 1), (1, 2), (1, 3), (3, 4)]
+        return dict(name="glauber_small_tree N=5 T=2 TruncBondThresh(10) (BASELINE configs[0], test/glauber_small_tree.jl)",
+                    kind="glauber_tree", q=2, T=T, d=args.d or 10, N=5, und=und, infinite_k=0, trunc=("bondthresh", args.d or 10, 0.0),
+                    metric=f"BP edge-updates/sec, FP64, T={T} bond dim {args.d or 10}")
+    if c == 2:
+        T = 50 if T is None else T
+        d = args.d or 10
+        n = (args.nodes_per_gpu or 10 ** 4) * (world if args.nodes_per_gpu else 1)
+        n += n % 2
+        G = nx.random_regular_graph(3, n, seed=1)
+        return dict(name=f"sis_rrg3 N={n} T={T} TruncBond({d}) (BASELINE configs[1]: nx.random_regular_graph(3, N, seed=1), SISFactor(0.1, 0.05), gamma=0.1)",
+                    kind="sis", params=(0.1, 0.05), q=2, T=T, d=d, N=n, und=[(int(a), int(b)) for a, b in G.edges()], infinite_k=0,
+                    trunc=("bond", d, 0.0), phi0=[0.9, 0.1], metric=f"BP edge-updates/sec, FP64, T={T} bond dim {d}")
+    if c == 3:
+        T = 50 if T is None else T
+        d = args.d or 20
+        npg = args.nodes_per_gpu or int(os.environ.get("MPBP_BENCH_NODES", 256))
+        n = npg * world
+        G = nx.fast_gnp_random_graph(n, 4.0 / n, seed=1)
+        return dict(name=f"glauber_er_c4 T={T} TruncBond({d}) (BASELINE configs[2] shape: nx.fast_gnp_random_graph(N, 4/N, seed=1), "
+                         f"HomogeneousGlauberFactor(J=0.5,h=0.1,beta=1), m0=-0.6), N={n} nodes; configs[2]'s N=1e5 does not fit one GPU "
+                         "(261 GB of messages) nor the time budget",
+                    kind="glauber", params=(0.5, 0.1, 1.0), q=2, T=T, d=d, N=n, und=[(int(a), int(b)) for a, b in G.edges()], infinite_k=0,
+                    trunc=("bond", d, 0.0), phi0=[0.2, 0.8], nodes_per_gpu=npg, metric=f"BP edge-updates/sec, FP64, T={T} bond dim {d}")
+    if c == 4:
+        T = 100 if T is None else T
+        d = args.d or 30
+        k = args.k or 10
+        return dict(name=f"glauber_infinite_rrg k={k} T={T} TruncBond({d}) (BASELINE configs[3]: J=0.2, beta=1, h=0, m0=0.3)",
+                    kind="glauber", params=(0.2, 0.0, 1.0), q=2, T=T, d=d, N=1, und=[], infinite_k=k, trunc=("bond", d, 0.0),
+                    phi0=[0.65, 0.35], metric=f"BP edge-updates/sec, FP64, T={T} bond dim {d}")
+    if c == 5:
+        T = 40 if T is None else T
+        d = args.d or 15
+        npg = args.nodes_per_gpu or 1024
+        n = npg * world
+        G = nx.fast_gnp_random_graph(n, 2.5 / n, seed=5)
+        return dict(name=f"sirs_inference_er_c2.5 N={n} T={T} TruncBond({d}) (BASELINE configs[4] shape: SIRSFactor(0.4,0.15,0.15), gamma=0.01, "
+                         "75% of the nodes observed at t=T/2 with hard one-hot phi drawn from one forward simulation)",
+                    kind="sirs", params=(0.4, 0.15, 0.15), q=3, T=T, d=d, N=n, und=[(int(a), int(b)) for a, b in G.edges()], infinite_k=0,
+                    trunc=("bond", d, 0.0), phi0=[0.99, 0.01, 0.0], observe=0.75, nodes_per_gpu=npg,
+                    metric=f"BP edge-updates/sec, FP64, T={T} bond dim {d}")
+    raise SystemExit(f"unknown --config {c}")
 
 
-def xweight(z):
-    """sum over the heavy ops (both operands of full bond) of X = nstates*q, Glauber: nstates(l) = l+1, q = 2."""
-    w = 0
-    for k in range(1, z):  # prefix p[k] -> nstates(k+1)
-        w += 2 * (k + 2)
-    for k in range(1, z - 1):  # suffix s[k], k <= z-2 -> nstates(z-k)
-        w += 2 * (z - k + 1)
-    for k in range(1, z - 1):  # dest[k], k <= z-2 -> nstates(z-1)
-        w += 2 * z
+def sirs_observations(wl, seed=5):
+    """hard one-hot observations of 75 % of the nodes at t = T/2 from ONE forward simulation of the prior dynamics
+    (mirrors src/sampling.jl:191-210 / notebooks/sirs_inference_single_instance.ipynb); vectorised numpy, states 0-based"""
+    rng = np.random.default_rng(seed)
+    N, T = wl["N"], wl["T"]
+    lam, rho, sig = wl["params"]
+    und = np.asarray(wl["und"], dtype=np.int64).reshape(-1, 2)
+    x = (rng.random(N) < wl["phi0"][1]).astype(np.int64)  # 0 = S, 1 = I, 2 = R
+    tobs = T // 2
+    for t in range(tobs):
+        inf = x == 1
+        ninf = np.bincount(und[:, 0], weights=inf[und[:, 1]], minlength=N) + np.bincount(und[:, 1], weights=inf[und[:, 0]], minlength=N)
+        u = rng.random(N)
+        nx_ = x.copy()
+        nx_[(x == 0) & (u < 1.0 - (1.0 - lam) ** ninf)] = 1
+        nx_[(x == 1) & (u < rho)] = 2
+        nx_[(x == 2) & (u < sig)] = 0
+        x = nx_
+    obs = rng.random(N) < wl["observe"]
+    return tobs, x, obs
+
+
+def make_phi(wl, N_local, local_to_global=None):
+    """reweightings [i][t][x] of the LOCAL nodes (all ones but the initial condition and, config 5, the observations)"""
+    T, q = wl["T"], wl["q"]
+    phi = np.ones((N_local, T + 1, q))
+    if wl["kind"] == "glauber_tree":
+        phi[:, 0, :] = [0.75, 0.25]
+        rng = np.random.default_rng(111)
+        for i in range(N_local):  # one one-hot observation per node at a random time (test/glauber_small_tree.jl:16-21)
+            t = int(rng.integers(1, T + 1))
+            o = np.zeros(q)
+            o[int(rng.integers(q))] = 1.0
+            phi[i, t, :] *= np.where(o > 0, 1.0, 0.05)
+        return phi
+    phi[:, 0, :] = wl["phi0"]
+    if wl.get("observe"):
+        tobs, x, obs = sirs_observations(wl)
+        gl = np.arange(N_local) if local_to_global is None else np.asarray(local_to_global)
+        for li, gi in enumerate(gl):
+            if obs[gi]:
+                o = np.zeros(q)
+                o[x[gi]] = 1.0
+                phi[li, tobs, :] = o
+    return phi
+
+
+def oracle_factor(wl, h=None):  # used by tools and tests that time single oracle updates
+    from oracle import factors as OF
+    if wl["kind"] == "glauber_tree":
+        return OF.HomogeneousGlauberFactor(1.0, 0.0 if h is None else h, 1.0)
+    return {"glauber": OF.HomogeneousGlauberFactor, "sis": OF.SISFactor, "sirs": OF.SIRSFactor}[wl["kind"]](*wl["params"])
+
+
+def device_factor(wl, M, h=None):
+    if wl["kind"] == "glauber_tree":
+        return M.HomogeneousGlauberFactor(1.0, 0.0 if h is None else h, 1.0)
+    return {"glauber": M.HomogeneousGlauberFactor, "sis": M.SISFactor, "sirs": M.SIRSFactor}[wl["kind"]](*wl["params"])
+
+
+def nstates(kind, l):
+    return l + 1 if kind.startswith("glauber") else (1 if l == 0 else 2)
+
+
+def node_cost(kind, q, z):
+    """sum of X = nstates*q over the heavy cavity ops of a degree-z node (+1 for the light ones): QR and SVD are linear in X"""
+    w = 1.0
+    for k in range(1, z):
+        w += q * nstates(kind, k + 1)
+    for k in range(1, z - 1):
+        w += q * nstates(kind, z - k) + q * nstates(kind, z - 1)
     return w
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on a bounded sample (one node update)
+# CPU arm (SURVEY 8d): the oracle port, ONE single-threaded worker per host core, degree-stratified bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(T, d, z, seed=0):
-    """one node update (src/recursive_bp_factor.jl:146-165) of a degree-z Glauber node whose incoming messages have
-    the steady-state bond profile min(4^t, 4^(L-t), d); returns seconds.  Uses every host core through the
-    threaded LAPACK/BLAS that numpy links (the reference threads over nodes instead; same silicon)."""
-    from oracle import factors as OF, mpbp as O, tt as OT
+def _bond_profile(T, d, q):
     L = T + 1
+    P = q * q
+    return [int(min(float(P) ** t, float(P) ** (L - t), d)) for t in range(L + 1)]
+
+
+def _site_cost(T, d, q):
+    """relative cost of the bond-D sweeps of one heavy op over the sites of a (T+1)-site train: sum_t D_l D_r^2, D = b^2"""
+    b = _bond_profile(T, d, q)
+    return float(sum((b[t] ** 2) * (b[t + 1] ** 2) ** 2 for t in range(T + 1)))
+
+
+def _cpu_worker(job):
+    """one oracle node update (src/recursive_bp_factor.jl:146-165) of the centre of a degree-z star whose incoming
+    messages have the steady-state bond profile; single BLAS thread (the reference threads over NODES, one per core)."""
+    kind, params, q, z, Ts, d, seed = job
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import factors as OF, mpbp as O, tt as OT
+    fac = {"glauber": OF.HomogeneousGlauberFactor, "glauber_tree": OF.HomogeneousGlauberFactor, "sis": OF.SISFactor, "sirs": OF.SIRSFactor}[kind](*params)
+    L = Ts + 1
     rng = np.random.default_rng(seed)
-    und = [(0, k) for k in range(1, z + 1)]
-    g = O.BiDiGraph(z + 1, und)
-    w = [[OF.HomogeneousGlauberFactor(0.5, 0.1, 1.0)] * L for _ in range(z + 1)]
-    phi = [[np.array([0.2, 0.8]) if t == 0 else np.ones(2) for t in range(L)] for _ in range(z + 1)]
-    bp = O.MPBP(g, w, [2] * (z + 1), T, phi=phi)
-    bonds = [min(4 ** t, 4 ** (L - t), d) for t in range(L + 1)]
-    for e in range(g.ne):
-        bp.mu[e] = OT.rand_tt(bonds, 2, 2, rng=rng)
+    g = O.BiDiGraph(z + 1, [(0, k) for k in range(1, z + 1)])
+    phi = [[np.ones(q) for _ in range(L)] for _ in range(z + 1)]
+    for i in range(z + 1):
+        phi[i][0] = np.array([0.2, 0.8] + [0.0] * (q - 2))[:q] if q == 2 else np.array([0.9, 0.1, 0.0])
+    bp = O.MPBP(g, [[fac] * L for _ in range(z + 1)], [q] * (z + 1), Ts, phi=phi)
+    bonds = _bond_profile(Ts, d, q)
+    for e in g.in_edges[0]:
+        bp.mu[e] = OT.rand_tt(bonds, q, q, rng=rng)
     t0 = time.perf_counter()
-    O.onebpiter_recursive(bp, 0, OT.TruncBond(d))
-    return time.perf_counter() - t0
+    O.onebpiter(bp, 0, OT.TruncBond(d))
+    return z, time.perf_counter() - t0
 
 
-def cpu_baseline(T, d, degs, z_sample=2):
-    t = cpu_sample(T, d, z_sample)
-    edges = float(np.sum(degs))
-    w_graph = float(sum(xweight(int(z)) for z in degs)) / max(edges, 1)
-    w_sample = xweight(z_sample) / z_sample
-    val = (z_sample / t) * (w_sample / w_graph)
-    return dict(value=val, unit=UNIT, cores=os.cpu_count(), kind="port",
-                sample=f"one oracle node update (degree {z_sample}, T={T}, TruncBond({d}), random full-bond incoming messages): "
-                       f"{t:.1f} s for {z_sample} edge updates, extrapolated to the graph's degree sequence by the "
-                       f"sum-of-X weight of the heavy ops ({w_sample:.2f} vs {w_graph:.2f} per edge)"), t
+def cpu_baseline(wl, degs, zmeas_max=3, cores=None):
+    """edge-updates/s of the oracle port on this box's host cores, extrapolated (SURVEY 8d recipe, bounded):
+    * one single-threaded worker PROCESS per core, all running concurrently (memory-bandwidth contention included);
+    * each worker updates the centre of a degree-z star for the degrees z <= zmeas_max present in the graph (replicated
+      to fill the cores), on a SHORT train (T_s sites reach the bond cap) -- a full d=20/T=50 update of a degree-3 node
+      alone takes minutes on one core;
+    * time per node at full T = measured x (site-cost model ratio); degrees above zmeas_max by the sum-of-X cost model;
+    * throughput = cores x (edges of the graph) / (sum over nodes of the node time)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    kind = wl["kind"]
+    params = wl.get("params", (1.0, 0.0, 1.0))
+    q, T, d = wl["q"], wl["T"], wl["d"]
+    Ts = min(T, 2 * int(math.ceil(math.log(max(d, 2)) / math.log(q * q))) + 2)
+    hist = np.bincount(np.asarray(degs, dtype=np.int64))
+    present = [z for z in range(1, len(hist)) if hist[z] > 0]
+    meas = [z for z in present if z <= zmeas_max] or [min(present)] if present else [1]
+    jobs = [(kind, params, q, meas[k % len(meas)], Ts, d, 1000 + k) for k in range(max(cores, len(meas)))]
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(processes=min(cores, len(jobs))) as pool:
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    tz = {z: float(np.mean([t for zz, t in res if zz == z])) for z in meas}
+    scale_T = _site_cost(T, d, q) / _site_cost(Ts, d, q)
+    zref = max(meas)
+
+    def node_time(z):
+        if z in tz:
+            return tz[z] * scale_T
+        if z == 0:
+            return 0.0
+        return tz[zref] * scale_T * node_cost(kind, q, z) / node_cost(kind, q, zref)
+
+    tot = float(sum(hist[z] * node_time(z) for z in range(len(hist))))
+    edges = float(sum(hist[z] * z for z in range(len(hist))))
+    val = cores * edges / tot if tot > 0 else 0.0
+    return dict(value=val, unit=UNIT, cores=cores, kind="port",
+                sample=f"oracle node updates, one single-threaded worker per core ({len(jobs)} workers, {wall:.1f} s wall): degrees {meas} measured "
+                       f"on T_s={Ts} trains at TruncBond({d}) ({', '.join(f'z={z}: {tz[z]:.2f} s' for z in meas)}), scaled to T={T} by the site-cost "
+                       f"model (x{scale_T:.1f}); degrees > {zref} extrapolated by the sum-of-X cost model; graph degree histogram "
+                       f"{ {int(z): int(hist[z]) for z in range(len(hist)) if hist[z]} }; EXTRAPOLATED"), wall
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n, und = make_workload(args.nodes_per_gpu * world)
-    degs = np.bincount(np.array(und).ravel(), minlength=n)
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(min(args.T, 4), min(args.d, 4), 2)  # warm the BLAS threads / page in numpy
-    ts, vals = [], []
-    for _ in range(args.steps):
-        cb, t = cpu_baseline(args.T, args.d, degs)
-        ts.append(t)
-        vals.append(cb["value"])
+    wl = workload(args, world)
+    degs = np.bincount(np.asarray(wl["und"], dtype=np.int64).ravel(), minlength=wl["N"]) if not wl["infinite_k"] else np.array([wl["infinite_k"]])
+    nrun = args.steps + args.warmup
+    zmax = 3 if (nrun <= 4 or wl["d"] <= 10) else 2  # bounded: the whole run stays within a few minutes (z=2 has the first heavy op)
+    vals, walls = [], []
+    cb = None
+    for k in range(nrun):
+        cb, wall = cpu_baseline(wl, degs, zmeas_max=zmax)
+        if k >= args.warmup:
+            vals.append(cb["value"])
+            walls.append(wall)
     cb["value"] = float(np.mean(vals))
-    line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * float(np.mean(ts)), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+    line = dict(metric=wl["metric"], value=cb["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * float(np.mean(walls)), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", impl="reference",
-                config=dict(workload=f"glauber_er_c4 T={args.T} TruncBond({args.d}) (BASELINE configs[2] shape), bounded sample per step",
-                            nodes_per_gpu=args.nodes_per_gpu),
+                config=dict(workload=wl["name"] + "; each step = one bounded degree-stratified sample, extrapolated",
+                            nodes_per_gpu=wl.get("nodes_per_gpu")),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
@@ -152,21 +321,47 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    T, d = args.T, args.d
-    ntot, und = make_workload(args.nodes_per_gpu * world)
-    owner = partition_balanced(ntot, und, world)
-    lp = LocalProblem(ntot, und, owner, rank)
-    g = M.IndexedBiDiGraph(len(lp.nodes), lp.local_und)
-    lp.build_exchange(g.src, g.dst, world)
-    w = [[M.HomogeneousGlauberFactor(0.5, 0.1, 1.0)] * (T + 1)] * g.N
-    # pinned host copy of the reweightings: the e2e step uploads it every step
-    nphi = g.N * (T + 1) * 2
-    phi_host = torch.empty(nphi, dtype=torch.float64).pin_memory()
-    phi_np = phi_host.numpy().reshape(g.N, T + 1, 2)
-    phi_np[:] = 1.0
-    phi_np[:, 0, :] = [0.2, 0.8]
-    phi = [[phi_np[i, t] for t in range(T + 1)] for i in range(g.N)]
-    bp = M.mpbp(g, w, [2] * g.N, T, phi=phi, dmax=d, device=local_rank)
+    wl = workload(args, world)
+    T, d, q = wl["T"], wl["d"], wl["q"]
+    tr = {"bond": lambda: M.TruncBond(d), "bondthresh": lambda: M.TruncBondThresh(d, 0.0)}[wl["trunc"][0]]()
+    if wl["infinite_k"]:
+        if world > 1 and rank > 0:
+            # the infinite-graph (iid) path is single-GPU ("replicas only"): rank 0 reports, the others idle
+            dist.barrier()
+            dist.destroy_process_group()
+            return
+        fac = device_factor(wl, M)
+        nphi = (T + 1) * q
+        phi_host = torch.empty(nphi, dtype=torch.float64).pin_memory()
+        phi_np = phi_host.numpy().reshape(1, T + 1, q)
+        phi_np[:] = make_phi(wl, 1)
+        bp = M.mpbp_infinite_graph(wl["infinite_k"], [fac] * (T + 1), q, phi=[phi_np[0, t] for t in range(T + 1)], dmax=d, device=local_rank)
+        g_N, edges_local, degs_all = 1, wl["infinite_k"], np.array([wl["infinite_k"]])
+        drv = None
+        world_eff = 1
+    else:
+        owner = partition_balanced(wl["N"], wl["und"], world, cost=lambda z: node_cost(wl["kind"], q, int(z)))
+        lp = LocalProblem(wl["N"], wl["und"], owner, rank)
+        g = M.IndexedBiDiGraph(len(lp.nodes), lp.local_und)
+        lp.build_exchange(g.src, g.dst, world)
+        g_N = g.N
+        if wl["kind"] == "glauber_tree":
+            hs = np.random.default_rng(111).standard_normal(wl["N"])
+            w = [[device_factor(wl, M, float(hs[int(lp.nodes[i])]))] * (T + 1) for i in range(g.N)]
+        else:
+            fac = device_factor(wl, M)
+            w = [[fac] * (T + 1)] * g.N
+        # pinned host copy of the reweightings: the e2e step uploads it every step
+        nphi = g.N * (T + 1) * q
+        phi_host = torch.empty(nphi, dtype=torch.float64).pin_memory()
+        phi_np = phi_host.numpy().reshape(g.N, T + 1, q)
+        phi_np[:] = make_phi(wl, g.N, lp.nodes)
+        phi = [[phi_np[i, t] for t in range(T + 1)] for i in range(g.N)]
+        bp = M.mpbp(g, w, [q] * g.N, T, phi=phi, dmax=d, device=local_rank)
+        degs_owned = np.array([g.degree(int(i)) for i in lp.owned_local])
+        edges_local = int(degs_owned.sum())
+        degs_all = np.bincount(np.asarray(wl["und"], dtype=np.int64).ravel(), minlength=wl["N"])
+        world_eff = world
     stream = torch.cuda.Stream()
     bp.set_stream(stream.cuda_stream)
     if args.arena_gb > 0:
@@ -174,18 +369,21 @@ def run_gpu(args, rank, world, local_rank):
     for kv in args.set:  # engine tuning knobs (mpbp_set_option), e.g. --set level_balance=0
         k, v = kv.split("=")
         bp.set_option(k, float(v))
-    backend = CudaBackend(bp, lp.owned_local, M.TruncBond(d))
-    drv = DistMPBP(lp, backend, dist if world > 1 else None, device=f"cuda:{local_rank}")
-    degs_owned = np.array([g.degree(int(i)) for i in lp.owned_local])
-    edges_local = int(degs_owned.sum())
+    if wl["infinite_k"]:
+        def step():
+            with torch.cuda.stream(stream):
+                M.iterate_(bp, maxiter=1, svd_trunc=tr, tol=0.0, shuffle_nodes=False)
+    else:
+        backend = CudaBackend(bp, lp.owned_local, tr)
+        drv = DistMPBP(lp, backend, dist if world > 1 else None, device=f"cuda:{local_rank}")
 
-    def step():
-        with torch.cuda.stream(stream):
-            drv.iterate(1)
+        def step():
+            with torch.cuda.stream(stream):
+                drv.iterate(1)
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
+        if world_eff > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -209,52 +407,60 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = int(bp.counters(reset=True)["launches"])
-    # ---- one extra PROFILED step for the roofline: single-stream launches so that the CUDA-event duration of every
-    # kernel family is its own (the timed steps above run op groups on 4 concurrent streams, where durations overlap)
-    bp.set_option("nstreams", 1)
-    bp.set_option("profile", 1)
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        pe0.record()
-    step()
-    with torch.cuda.stream(stream):
-        pe1.record()
-    barrier()
-    prof_ms = pe0.elapsed_time(pe1)
-    ctr = bp.counters(reset=True)
-    fam = bp.kernel_times(reset=True)
-    bp.set_option("profile", 0)
-    bp.set_option("nstreams", 4)
-    # max over ranks of the device time, sum over ranks of the units
-    tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    ee = torch.tensor([float(edges_local)], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
+    ctr_timed = bp.counters(reset=True)
+    launches = int(ctr_timed["launches"])
+    # ---- ONE extra PROFILED step for the roofline: single-stream launches so that the CUDA-event duration of every
+    # kernel family is its own (the timed steps above run op groups on concurrent streams, where durations overlap)
+    prof_ms, ctr, fam = None, ctr_timed, {}
+    if not args.no_profile:
+        bp.set_option("nstreams", 1)
+        bp.set_option("profile", 1)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            pe0.record()
+        step()
+        with torch.cuda.stream(stream):
+            pe1.record()
+        barrier()
+        prof_ms = pe0.elapsed_time(pe1)
+        ctr = bp.counters(reset=True)
+        fam = bp.kernel_times(reset=True)
+        bp.set_option("profile", 0)
+        bp.set_option("nstreams", 4)
+    # max over ranks of the device time, sum over ranks of the units; per-rank times show the imbalance
+    dev = f"cuda:{local_rank}"
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ee = torch.tensor([float(edges_local)], dtype=torch.float64, device=dev)
+    per_rank = [ms / args.steps]
+    if world_eff > 1:
+        gath = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gath, tt)
+        per_rank = [float(x.item()) / args.steps for x in gath]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ee, op=dist.ReduceOp.SUM)
     ms = float(tt.item())
     edges_total = float(ee.item())
     ms_per_step = ms / args.steps
     value = edges_total / (ms_per_step / 1e3)
-    # ---- e2e: same step through the public API with host buffers (H2D of phi, D2H of beliefs + f) ----
-    e2e_steps = max(1, min(args.steps, 2))
+    # ---- e2e: the same step through the public API with HOST buffers (H2D of phi from pinned memory, D2H of beliefs + f)
+    e2e_steps = 1 if ms_per_step > 3000 else max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         with torch.cuda.stream(stream):
             bp.upload_phi(phi_host.numpy())  # host -> device from the pinned buffer
-            drv.iterate(1)
+            step()
             b = M.beliefs(bp)
             f = M.bethe_free_energy(bp)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t2 = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
+    t2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world_eff > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_s = float(t2.item())
     h2d = int(nphi * 8)
-    d2h = int(nphi * 8 + g.N * 8)
+    d2h = int(nphi * 8 + g_N * 8)
     if rank == 0:
         qr_tf = ctr["qr_flops"] / (ctr["qr_ms"] * 1e-3) / 1e12 if ctr["qr_ms"] > 0 else 0.0
         traffic, traffic_note = None, None
@@ -263,32 +469,38 @@ def run_gpu(args, rank, world, local_rank):
             try:
                 tj = json.load(open(tpath))
                 traffic = tj.get("dram_bytes_per_launch")
-                traffic_note = (f"ncu --set full capture of ONE isolated launch ({tj.get('launch')}; {tj.get('kernel')}; algorithmic bytes of that launch "
-                                f"{tj.get('algorithmic_bytes_per_launch')}); the H=64 variant used for D >= 200 halves the R re-reads; not re-captured")
+                traffic_note = (f"ncu --set full capture of one launch ({tj.get('launch')}; {tj.get('kernel')}); algorithmic bytes of that launch "
+                                f"{tj.get('algorithmic_bytes_per_launch')}")
             except Exception:
                 traffic = None
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        roof = dict(kernel="k_qr_ft (flat-tree DMMA Q-less QR of the bond-D sweep, csrc/qr_ft.cuh)", bound="tensor", achieved=qr_tf, peak=float(peak[0]),
+                    unit="TFLOP/s", frac=qr_tf / float(peak[0]) if peak[0] > 0 else None, traffic=traffic, traffic_note=traffic_note,
+                    peak_source="FP64 DMMA (mma.sync m8n8k4 f64) measured live by mpbp_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 entry",
+                    algorithmic_flops=ctr["qr_flops"], kernel_ms=ctr["qr_ms"],
+                    share_of_step=(ctr["qr_ms"] / prof_ms) if prof_ms else None,
+                    measured_on=(f"one extra profiled step right after the timed region (single-stream launches, {prof_ms:.0f} ms); the timed steps use "
+                                 "concurrent streams") if prof_ms else "profiling skipped (--no-profile)",
+                    heavy_ops=int(ctr["ops"]),
+                    subspace_svd=dict(calls=int(ctr["svd_calls"]), iters=int(ctr["svd_iters"]), exact_fallbacks=int(ctr["svd_unconverged"])),
+                    kernel_family_ms={k: round(v, 1) for k, v in fam.items()})
+        line = dict(metric=wl["metric"], value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                    config=dict(workload=f"glauber_er_c4 T={T} TruncBond({d}) (BASELINE configs[2] shape: nx.fast_gnp_random_graph(N, 4/N, seed=1), "
-                                         f"HomogeneousGlauberFactor(J=0.5,h=0.1,beta=1), m0=-0.6), N={ntot} nodes, {int(edges_total)} directed edges; "
-                                         "configs[2]'s N=1e5 does not fit one GPU (261 GB of messages) nor the time budget",
-                                nodes_per_gpu=args.nodes_per_gpu, schedule="parallel (Jacobi), one halo exchange per step",
-                                l2="working set per step >> L2 (126 MB): every heavy op streams ~70 MB of scratch",
-                                parallelism=f"node partition x{world} (cost-balanced by degree)"),
+                    config=dict(workload=wl["name"] + f", {int(edges_total)} directed edges", config_id=args.config,
+                                nodes_per_gpu=wl.get("nodes_per_gpu"), schedule="parallel (Jacobi), one halo exchange per step",
+                                l2="working set per step >> L2 (126 MB): every heavy op streams tens of MB of scratch",
+                                parallelism=(f"node partition x{world} (cost-balanced by degree)" if not wl["infinite_k"] else "single GPU (iid infinite graph: replicas only)"),
+                                step_budget=f"{args.warmup} warm-up + {args.steps} timed + {0 if args.no_profile else 1} profiled + {e2e_steps} e2e"),
                     clocks=clocks,
                     e2e=dict(value=edges_total / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=launches,
-                    roofline=dict(kernel="k_qr_ft (flat-tree DMMA Q-less QR of the bond-D sweep, csrc/qr_ft.cuh)", bound="tensor", achieved=qr_tf, peak=float(peak[0]),
-                                  unit="TFLOP/s", frac=qr_tf / float(peak[0]) if peak[0] > 0 else None, traffic=traffic, traffic_note=traffic_note,
-                                  peak_source="FP64 DMMA (mma.sync m8n8k4 f64) measured live by mpbp_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 entry",
-                                  algorithmic_flops=ctr["qr_flops"], kernel_ms=ctr["qr_ms"], share_of_step=ctr["qr_ms"] / prof_ms if prof_ms > 0 else None,
-                                  measured_on=f"one extra profiled step right after the timed region (single-stream launches, {prof_ms:.0f} ms); the timed steps use 4 concurrent streams",
-                                  heavy_ops=int(ctr["ops"]), subspace_svd=dict(calls=int(ctr["svd_calls"]), iters=int(ctr["svd_iters"]), unconverged=int(ctr["svd_unconverged"])), kernel_family_ms={k: round(v, 1) for k, v in fam.items()}))
+                    per_rank_ms_per_step=dict(max=max(per_rank), mean=float(np.mean(per_rank)), all=[round(x, 1) for x in per_rank]),
+                    roofline=roof)
         if world == 1 and not args.no_cpu:
-            degs = np.array([g.degree(i) for i in range(g.N)])
-            line["cpu_baseline"], _ = cpu_baseline(T, d, degs)
+            line["cpu_baseline"], _ = cpu_baseline(wl, degs_all, zmeas_max=3 if d >= 20 else 4)
         print(json.dumps(line))
     if world > 1:
+        if wl["infinite_k"]:
+            dist.barrier()
         dist.destroy_process_group()
 
 
@@ -298,11 +510,14 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nodes-per-gpu", type=int, default=int(os.environ.get("MPBP_BENCH_NODES", 384)))
-    ap.add_argument("--T", type=int, default=50)
-    ap.add_argument("--d", type=int, default=20)
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--nodes-per-gpu", type=int, default=None)
+    ap.add_argument("--T", type=int, default=None)
+    ap.add_argument("--d", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--arena-gb", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--set", action="append", default=[], metavar="OPTION=VALUE")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -312,7 +527,7 @@ def main():
         run_reference(args, rank, world)
     else:
         import __graft_entry__ as G
-        G.build()
+        G.build()  # serialised across the ranks of a node by a file lock; a no-op when the in-tree .so is current
         run_gpu(args, rank, world, local_rank)
 
 

@@ -65,6 +65,9 @@ int mpbp_add_node_class(mpbp_handle h, int z, int q, const int32_t* qn, int nt, 
                         const double* pxy, int npairs, const int32_t* pair_d1, const int32_t* pair_d2,
                         const double* pyy, const double* w, const double* wd, const double* minit,
                         int32_t* class_id);
+/* drop every node class uploaded so far (device tables freed, all nodes unassigned): called by the host layer before it
+ * re-tabulates the factors (bp.w edited in place), so that repeated syncs do not accumulate tables */
+int mpbp_clear_node_classes(mpbp_handle h);
 int mpbp_set_node_classes(mpbp_handle h, const int32_t* class_of_node /* N */);
 
 /* Generic BPFactor (src/bp_core.jl:1-57): dense table per node, for t<T+1 (nt = 1 or T+1):
@@ -116,15 +119,18 @@ int mpbp_alternate_marginals(mpbp_handle h, double* out);
 
 /* ---- multi-GPU plumbing (no reference counterpart; see DESIGN.md "multi-GPU") ----
  * pack/unpack the fixed-capacity device slots of `n` messages into/from one contiguous DEVICE buffer so that
- * the host layer can exchange cut-edge messages with one collective.  slot size from mpbp_message_slot_bytes. */
+ * the host layer can exchange cut-edge messages with one collective.  Record size from mpbp_message_slot_bytes
+ * (a multiple of 16).  Each call is ONE gather/scatter kernel on the engine's stream, synchronised before it returns.
+ * unpack: the caller must have ordered the producer of dev_buf (e.g. the collective's stream) before the call. */
 int64_t mpbp_message_slot_bytes(mpbp_handle h);
 int mpbp_pack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, void* dev_buf);
 int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, const void* dev_buf);
 
 /* ---- introspection for bench / roofline accounting ----
- * counters accumulated since the last reset: [0] kernel launches, [1] algorithmic FLOPs of the Q-less QR
- * sweeps, [2] executed FLOPs of all kernels (model), [3] device ms in QR kernels (CUDA events, only when
- * profiling is on), [4] heavy ops run, [5] edge updates. */
+ * counters accumulated since the last reset: [0] kernel launches, [1] ALGORITHMIC FLOPs of the sweep-1 Q-less QRs
+ * (2mn^2 - 2/3 n^3 of the unsplit matrices; TSQR chunk/merge overhead is not counted), [2] subspace-SVD calls,
+ * [3] device ms in the sweep-1 QR kernels (CUDA events, only when profiling is on), [4] heavy ops run,
+ * [5] edge updates, [6] subspace-SVD iterations, [7] subspace-SVD calls resolved by the exact Jacobi fallback. */
 int mpbp_counters(mpbp_handle h, double* out8, int reset);
 /* engine tuning knobs (none changes a result bit): "arena_gb" scratch arena size, "max_group_ops" ops per launch group,
  * "nstreams" (1..4) concurrent streams per cavity round, "qr_fill" CTAs below which tall QRs are TSQR-split,

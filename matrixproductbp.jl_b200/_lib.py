@@ -21,6 +21,7 @@ SIGNATURES = {
     "mpbp_destroy": (C.c_int, [C.c_void_p]),
     "mpbp_add_node_class": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p, c_dp, C.c_int, c_i32p, c_i32p, c_dp, c_dp, c_dp, c_dp, c_i32p]),
     "mpbp_set_node_classes": (C.c_int, [C.c_void_p, c_i32p]),
+    "mpbp_clear_node_classes": (C.c_int, [C.c_void_p]),
     "mpbp_add_generic_class": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i32p, C.c_int, c_dp, c_i32p]),
     "mpbp_set_phi": (C.c_int, [C.c_void_p, c_dp]),
     "mpbp_set_psi": (C.c_int, [C.c_void_p, c_dp]),

@@ -240,6 +240,7 @@ class MPBP:
         L = _lib.lib()
         cache = {}
         cls = np.zeros(self.N, dtype=np.int32)
+        _lib.check(L.mpbp_clear_node_classes(self._h))  # every table is re-uploaded below
         for i in range(self.N):
             z = self.g.degree(i)
             if active is not None and not active[i]:
@@ -390,10 +391,7 @@ def iterate_(bp: MPBP, maxiter=5, svd_trunc: SVDTrunc = None, showprogress=False
         bp.sync_factors()
     cb = CB_BP(bp) if cb is None else cb
     nodes_arr = np.arange(bp.N, dtype=np.int64) if nodes is None else np.ascontiguousarray(np.asarray(nodes, dtype=np.int64))
-    order = None
-    if shuffle_nodes and schedule == "sequential" and len(nodes_arr) > 1:
-        rng = np.random.default_rng(rng)
-        order = np.ascontiguousarray(np.stack([nodes_arr] + [rng.permutation(nodes_arr) for _ in range(maxiter - 1)]))
+    shuffle = shuffle_nodes and schedule == "sequential" and len(nodes_arr) > 1
     obs = None
     if cb.f is not None:
         qmax = int(bp.q.max())
@@ -403,11 +401,29 @@ def iterate_(bp: MPBP, maxiter=5, svd_trunc: SVDTrunc = None, showprogress=False
                 obs[i, x] = cb.f(x + 1, i)
         obs = np.ascontiguousarray(obs)
     iters = C.c_int()
-    deltas = np.zeros(max(maxiter, 1))
     sched = {"sequential": 0, "parallel": 1}[schedule]
-    _lib.check(L.mpbp_iterate(bp._h, int(maxiter), svd_trunc.kind, svd_trunc.d, svd_trunc.eps, float(tol), float(damp), sched,
-                              _p(nodes_arr, _lib.c_i64p), len(nodes_arr), None if order is None else _p(order, _lib.c_i64p),
-                              None if obs is None else _p(obs, _lib.c_dp), C.byref(iters), _p(deltas, _lib.c_dp)))
+
+    def call(n_it, nodes_now, deltas):
+        _lib.check(L.mpbp_iterate(bp._h, int(n_it), svd_trunc.kind, svd_trunc.d, svd_trunc.eps, float(tol), float(damp), sched,
+                                  _p(nodes_now, _lib.c_i64p), len(nodes_now), None,
+                                  None if obs is None else _p(obs, _lib.c_dp), C.byref(iters), _p(deltas, _lib.c_dp)))
+
+    if shuffle:
+        # src/mpbp.jl:188-196: the first sweep visits `nodes` in the given order; after every sweep
+        # `sample!(nodes, vertices(bp.g), replace=false)` redraws the list from ALL vertices (a permutation when `nodes`
+        # covers the graph).  One C call per iteration with that iteration's list: nothing of size maxiter x N is
+        # materialised.  Delta is taken over the nodes just updated (the others did not move).
+        rng = np.random.default_rng(rng)
+        d1 = np.zeros(1)
+        for it in range(int(maxiter)):
+            order = nodes_arr if it == 0 else np.ascontiguousarray(rng.choice(bp.N, size=len(nodes_arr), replace=False).astype(np.int64))
+            call(1, order, d1)
+            cb.deltas.append(float(d1[0]))
+            if d1[0] < tol:
+                return it + 1, cb
+        return int(maxiter), cb
+    deltas = np.zeros(max(maxiter, 1))
+    call(maxiter, nodes_arr, deltas)
     cb.deltas.extend(deltas[:iters.value].tolist())
     return iters.value, cb
 

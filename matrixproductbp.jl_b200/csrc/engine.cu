@@ -92,6 +92,8 @@ struct mpbp_state {
   double* d_delta = nullptr;
   int* d_err = nullptr;
   double* d_flops = nullptr;
+  int64_t* d_edge_idx = nullptr;  // device copy of the edge list of the last pack/unpack call
+  size_t edge_idx_cap = 0;
   std::vector<NodeClass> classes;
   std::vector<int> class_of_node;
   Arena arena;
@@ -102,6 +104,8 @@ struct mpbp_state {
   double nstreams = 4;
   int twovar = 0;            // > 0: maxdist of the two-time marginals computed with every belief (option "twovar")
   double* d_tv = nullptr;    // [N][L][L][qmax*qmax]
+  double outlier_split = 0;  // > 0: ops costing more than this multiple of the mean of their launch group run in a
+                             // group of their own, TSQR-split, next to the other groups (0 = off; experimental)
   double level_balance = 1;  // stagger the cavity levels of the nodes of a chunk so that every round carries similar work
   double damp = 0.0;  // set by mpbp_iterate for the duration of the call
   // options
@@ -129,9 +133,10 @@ int upload(T** dptr, const T* host, size_t n) {
 }
 
 int alloc_msg_store(mpbp_state* h, MsgStore& m) {
-  CUDA_OK(cudaMalloc((void**)&m.data, sizeof(double) * h->slot * h->E2));
-  CUDA_OK(cudaMalloc((void**)&m.bonds, sizeof(int) * (h->L + 1) * h->E2));
-  CUDA_OK(cudaMalloc((void**)&m.ls, sizeof(double) * h->E2));
+  const int64_t ne = std::max<int64_t>(h->E2, 1);
+  CUDA_OK(cudaMalloc((void**)&m.data, sizeof(double) * h->slot * ne));
+  CUDA_OK(cudaMalloc((void**)&m.bonds, sizeof(int) * (h->L + 1) * ne));
+  CUDA_OK(cudaMalloc((void**)&m.ls, sizeof(double) * ne));
   return 0;
 }
 
@@ -146,6 +151,7 @@ TTRef msg_ref(const mpbp_state* h, const MsgStore& m, int64_t e, int P) {
 }
 
 int flat_messages(mpbp_state* h, MsgStore& m) {
+  if (h->E2 == 0) return 0;  // a graph without edges is legal (the reference accepts it): nothing to initialise
   k_flat_messages<<<(unsigned)h->E2, 128, 0, h->st>>>(m.data, m.bonds, m.ls, h->d_qprod, h->slot, h->L, h->E2, h->sstride);
   h->n_launch++;
   CUDA_OK(cudaGetLastError());
@@ -708,11 +714,12 @@ struct GroupRun {
   int kc_rb;
   int bigH, smallH;  // row-block height of the flat-tree QR: 64 (one CTA/SM, D >= 200), 32 (two CTAs/SM) or 16
   int dXcap;
+  int nsplit;  // TSQR chunks allowed per matrix in this group's QR launches
 };
 
 // run the groups of one level concurrently: the per-site launch sequences of the groups are issued interleaved on
 // their own streams, so the tail of one group's launch is filled by the other groups' kernels
-int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr, int nsplit) {
+int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr) {
   const int L = h->L, d = h->dmax;
   const size_t kp_smem = (size_t)d * d * d * 8;
   const size_t jac_fixed = 3 * SUB_BMAX;
@@ -750,6 +757,7 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr,
       ev_end(h, g.st);
       h->n_launch++;
       ev_begin(h, F_QR, g.st);
+      const int nsplit = g.nsplit;
       dim3 gq(g.nops, nsplit);
       if (g.bigH == 64) k_qr_ft<64><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
       else if (g.bigH == 32) k_qr_ft<32><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
@@ -883,10 +891,22 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         gr.nops = 0; gr.maxD = 1; gr.maxX = 1; gr.maxNy = 1; gr.maxq = 1;
         gr.st = gi == 0 ? st : h->aux[gi - 1];
       }
+      // optional: the few ops far above the mean cost of this launch (they come first after the LPT sort) bound the
+      // launch by themselves; give them group 0 alone, where the small op count makes the TSQR split kick in
+      int nhead = 0;
+      if (h->outlier_split > 0 && G >= 2) {
+        auto cst = [&](size_t k) { return (double)P.capA[lev][k] * P.capB[lev][k] * ops[k].nyo * ops[k].q; };
+        double mean = 0.0;
+        for (int k = 0; k < nops; ++k) mean += cst(i0 + k);
+        mean /= nops;
+        while (nhead < nops && cst(i0 + nhead) >= h->outlier_split * mean) ++nhead;
+        if (nhead * 4 > (int)h->qr_fill || nops - nhead < G - 1) nhead = 0;  // too many to be outliers / nothing left for the other groups
+      }
       for (int k = 0; k < nops; ++k) {
         const OpDesc& op = ops[i0 + k];
-        GroupRun& gr = groups[k % G];
-        gops[k % G].push_back(op);
+        const int gsel = nhead > 0 ? (k < nhead ? 0 : 1 + (k - nhead) % (G - 1)) : k % G;
+        GroupRun& gr = groups[gsel];
+        gops[gsel].push_back(op);
         gr.nops++;
         gr.maxD = std::max(gr.maxD, P.capA[lev][i0 + k] * P.capB[lev][i0 + k]);
         gr.maxX = std::max(gr.maxX, op.nyo * op.q);
@@ -906,7 +926,13 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         for (int gi = 1; gi < G; ++gi) CUDA_OK(cudaStreamWaitEvent(h->aux[gi - 1], h->ev_fork, 0));
       }
       const int nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(nops, 1))));
-      if (run_op_groups(h, groups, tr, nsplit)) return 1;
+      for (int gi = 0; gi < G; ++gi) groups[gi].nsplit = nsplit;
+      if (nhead > 0) groups[0].nsplit = std::max(nsplit, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / nhead)));
+      if (run_op_groups(h, groups, tr)) {
+        for (int k = 0; k < 3; ++k) cudaStreamSynchronize(h->aux[k]);  // do not leave forked streams running
+        cudaStreamSynchronize(st);
+        return 1;
+      }
       for (int gi = 1; gi < G; ++gi) {
         CUDA_OK(cudaEventRecord(h->ev_join[gi - 1], h->aux[gi - 1]));
         CUDA_OK(cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
@@ -960,15 +986,17 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
       }
     }
     const size_t bsm = 2 * (size_t)d * qm * 8;
-    ev_begin(h, F_BEL, st);
-    k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
-    ev_end(h, st);
-    if (h->twovar > 0) {
+    if (!P.bel.empty()) {
+      ev_begin(h, F_BEL, st);
+      k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
+      ev_end(h, st);
+    }
+    if (h->twovar > 0 && !P.bel.empty()) {
       const size_t tsm = 2 * (size_t)qm * d * qm * 8;
       k_twovar<<<(unsigned)P.bel.size(), NT, tsm, st>>>(d_bel, L, d, h->twovar, qm * qm);
       h->n_launch++;
     }
-    k_free_energy<<<(unsigned)(P.fj.size() + 127) / 128, 128, 0, st>>>(d_fj, (int)P.fj.size());
+    if (!P.fj.empty()) k_free_energy<<<(unsigned)(P.fj.size() + 127) / 128, 128, 0, st>>>(d_fj, (int)P.fj.size());
     h->n_launch += 2;
   }
   CUDA_OK(cudaGetLastError());
@@ -1090,7 +1118,7 @@ int mpbp_destroy(mpbp_handle h) {
   for (int b = 0; b < 2; ++b) { cudaFree(h->msg[b].data); cudaFree(h->msg[b].bonds); cudaFree(h->msg[b].ls); }
   cudaFree(h->d_phi); cudaFree(h->d_psi); cudaFree(h->d_qprod); cudaFree(h->d_marg); cudaFree(h->d_logzi);
   cudaFree(h->d_logzij); cudaFree(h->d_f); cudaFree(h->d_means); cudaFree(h->d_marg_off); cudaFree(h->d_q);
-  cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->arena.base); cudaFree(h->d_tv);
+  cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->d_edge_idx); cudaFree(h->arena.base); cudaFree(h->d_tv);
   for (auto& e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (h->own_stream) cudaStreamDestroy(h->st);
   for (int k = 0; k < 3; ++k) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
@@ -1203,6 +1231,18 @@ int mpbp_add_generic_class(mpbp_handle h, int z, int q, const int32_t* qn, int n
   return 0;
 }
 
+int mpbp_clear_node_classes(mpbp_handle h) {
+  if (!h) return fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  for (auto& c : h->classes) {
+    cudaFree(c.d_pxy); cudaFree(c.d_pyy); cudaFree(c.d_w); cudaFree(c.d_wd); cudaFree(c.d_minit);
+  }
+  h->classes.clear();
+  std::fill(h->class_of_node.begin(), h->class_of_node.end(), -1);
+  return 0;
+}
+
 int mpbp_set_node_classes(mpbp_handle h, const int32_t* cls) {
   if (!h) return fail("null handle");
   for (int64_t i = 0; i < h->N; ++i) {
@@ -1301,12 +1341,25 @@ int mpbp_iterate(mpbp_handle h, int maxiter, int trunc_kind, int trunc_d, double
   if (nodes_in) base.assign(nodes_in, nodes_in + n_nodes);
   else { base.resize(h->N); for (int64_t i = 0; i < h->N; ++i) base[i] = i; n_nodes = h->N; }
   for (int64_t i : base) if (i < 0 || i >= h->N) return fail("node index %lld out of range", (long long)i);
+  struct DevBuf {  // freed on every exit path (the loud device errors below are expected in normal use)
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+  } obs_buf, nodes_buf;
   double* d_obs = nullptr;
   if (obs) { if (upload(&d_obs, obs, (size_t)h->N * h->qmax)) return 1; }
+  obs_buf.p = d_obs;
   int64_t* d_nodes = nullptr;
   if (upload(&d_nodes, base.data(), base.size())) return 1;
+  nodes_buf.p = d_nodes;
   if (schedule == MPBP_SCHEDULE_PARALLEL && !h->msg[1].data) {
     if (alloc_msg_store(h, h->msg[1])) return 1;
+  }
+  // CB_BP builds its baseline m = means(f, bp) from the beliefs as they are NOW and with the caller's f
+  // (src/mpbp.jl:165-171): recompute it here, the delta of this pass is discarded
+  if (!base.empty()) {
+    k_means_delta<<<(unsigned)base.size(), 64, 0, h->st>>>(h->d_marg, h->d_marg_off, h->d_q, d_obs, h->qmax, d_nodes,
+                                                           (long long)base.size(), h->L, h->d_means, h->d_delta);
+    h->n_launch++;
   }
   int done = 0;
   for (int it = 0; it < maxiter; ++it) {
@@ -1343,9 +1396,11 @@ int mpbp_iterate(mpbp_handle h, int maxiter, int trunc_kind, int trunc_d, double
     if (check_err(h)) return 1;
     // CB_BP: Delta = max |means_new - means_old| (src/mpbp.jl:174-183)
     CUDA_OK(cudaMemsetAsync(h->d_delta, 0, sizeof(double), h->st));
-    k_means_delta<<<(unsigned)base.size(), 64, 0, h->st>>>(h->d_marg, h->d_marg_off, h->d_q, d_obs, h->qmax, d_nodes,
-                                                           (long long)base.size(), h->L, h->d_means, h->d_delta);
-    h->n_launch++;
+    if (!base.empty()) {
+      k_means_delta<<<(unsigned)base.size(), 64, 0, h->st>>>(h->d_marg, h->d_marg_off, h->d_q, d_obs, h->qmax, d_nodes,
+                                                             (long long)base.size(), h->L, h->d_means, h->d_delta);
+      h->n_launch++;
+    }
     double delta = 0;
     CUDA_OK(cudaMemcpyAsync(&delta, h->d_delta, sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CUDA_OK(cudaStreamSynchronize(h->st));
@@ -1354,8 +1409,6 @@ int mpbp_iterate(mpbp_handle h, int maxiter, int trunc_kind, int trunc_d, double
     if (delta < tol) break;
   }
   ev_flush(h);
-  cudaFree(d_obs);
-  cudaFree(d_nodes);
   if (iters) *iters = done;
   return 0;
 }
@@ -1487,43 +1540,79 @@ int mpbp_alternate_marginals(mpbp_handle h, double* out) {
 int64_t mpbp_message_slot_bytes(mpbp_handle h) {
   if (!h) return 0;
   // data + bonds + ls, padded to 8 bytes
-  return (int64_t)(sizeof(double) * h->slot + sizeof(double) * ((h->L + 1 + 1) / 2) + sizeof(double));
+  const int64_t b = (int64_t)(sizeof(double) * h->slot + sizeof(double) * ((h->L + 1 + 1) / 2) + sizeof(double));
+  return (b + 15) & ~int64_t(15);  // records stay 16-byte aligned in a packed buffer (128-bit copies)
 }
 
-int mpbp_pack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, void* dev_buf) {
-  if (!h || (!edges && n) || (!dev_buf && n)) return fail("null argument");
-  CUDA_OK(cudaSetDevice(h->device));
-  const int64_t sb = mpbp_message_slot_bytes(h);
-  const MsgStore& m = h->msg[h->cur];
-  const int L = h->L;
-  for (int64_t k = 0; k < n; ++k) {
-    const int64_t e = edges[k];
-    if (e < 0 || e >= h->E2) return fail("bad edge index");
-    char* p = (char*)dev_buf + k * sb;
-    CUDA_OK(cudaMemcpyAsync(p, m.data + e * h->slot, sizeof(double) * h->slot, cudaMemcpyDeviceToDevice, h->st));
-    CUDA_OK(cudaMemcpyAsync(p + sizeof(double) * h->slot, m.bonds + e * (L + 1), sizeof(int) * (L + 1), cudaMemcpyDeviceToDevice, h->st));
-    CUDA_OK(cudaMemcpyAsync(p + sb - sizeof(double), m.ls + e, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+}  // extern "C"
+// halo payload: one fixed-size record per message = [slot doubles][L+1 bond ints, padded to 8 bytes][log-scale]
+// PACK: message store -> records ; !PACK: records -> message store.  grid (n, segments), 128-bit copies.
+template <bool PACK>
+__global__ void __launch_bounds__(NT) k_pack_messages(double* mdata, int* mbonds, double* mls, const int64_t* edges, char* buf,
+                                                      long long slot, int L, long long sb) {
+  const long long e = edges[blockIdx.x];
+  double2* m2 = reinterpret_cast<double2*>(mdata + e * slot);  // slot is a multiple of 2 doubles whenever dmax*q is even;
+  double2* b2 = reinterpret_cast<double2*>(buf + (long long)blockIdx.x * sb);
+  const long long n2 = slot / 2;
+  if ((slot & 1) == 0 && ((reinterpret_cast<uintptr_t>(m2) | reinterpret_cast<uintptr_t>(b2)) & 15) == 0) {
+    for (long long i = (long long)blockIdx.y * NT + threadIdx.x; i < n2; i += (long long)gridDim.y * NT) {
+      if (PACK) b2[i] = m2[i]; else m2[i] = b2[i];
+    }
+  } else {
+    double* m1 = mdata + e * slot;
+    double* b1 = reinterpret_cast<double*>(buf + (long long)blockIdx.x * sb);
+    for (long long i = (long long)blockIdx.y * NT + threadIdx.x; i < slot; i += (long long)gridDim.y * NT) {
+      if (PACK) b1[i] = m1[i]; else m1[i] = b1[i];
+    }
   }
-  CUDA_OK(cudaStreamSynchronize(h->st));
-  return 0;
+  if (blockIdx.y == 0) {
+    int* bb = reinterpret_cast<int*>(buf + (long long)blockIdx.x * sb + sizeof(double) * slot);
+    double* bl = reinterpret_cast<double*>(buf + (long long)blockIdx.x * sb + sb - sizeof(double));
+    for (int i = threadIdx.x; i <= L; i += NT) {
+      if (PACK) bb[i] = mbonds[e * (L + 1) + i]; else mbonds[e * (L + 1) + i] = bb[i];
+    }
+    if (threadIdx.x == 0) {
+      if (PACK) *bl = mls[e]; else mls[e] = *bl;
+    }
+  }
 }
-
-int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, const void* dev_buf) {
+namespace {
+int pack_unpack(mpbp_state* h, int64_t n, const int64_t* edges, void* dev_buf, bool pack) {
   if (!h || (!edges && n) || (!dev_buf && n)) return fail("null argument");
+  if (n == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
+  for (int64_t k = 0; k < n; ++k)
+    if (edges[k] < 0 || edges[k] >= h->E2) return fail("bad edge index");
+  if ((int64_t)h->edge_idx_cap < n) {
+    cudaFree(h->d_edge_idx);
+    h->d_edge_idx = nullptr;
+    CUDA_OK(cudaMalloc((void**)&h->d_edge_idx, sizeof(int64_t) * n));
+    h->edge_idx_cap = (size_t)n;
+  }
+  CUDA_OK(cudaMemcpyAsync(h->d_edge_idx, edges, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->st));
   const int64_t sb = mpbp_message_slot_bytes(h);
   MsgStore& m = h->msg[h->cur];
-  const int L = h->L;
-  for (int64_t k = 0; k < n; ++k) {
-    const int64_t e = edges[k];
-    if (e < 0 || e >= h->E2) return fail("bad edge index");
-    const char* p = (const char*)dev_buf + k * sb;
-    CUDA_OK(cudaMemcpyAsync(m.data + e * h->slot, p, sizeof(double) * h->slot, cudaMemcpyDeviceToDevice, h->st));
-    CUDA_OK(cudaMemcpyAsync(m.bonds + e * (L + 1), p + sizeof(double) * h->slot, sizeof(int) * (L + 1), cudaMemcpyDeviceToDevice, h->st));
-    CUDA_OK(cudaMemcpyAsync(m.ls + e, p + sb - sizeof(double), sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-  }
+  const int segs = (int)std::max<int64_t>(1, std::min<int64_t>(64, h->slot / (8 * NT)));
+  dim3 grid((unsigned)n, segs);
+  if (pack) k_pack_messages<true><<<grid, NT, 0, h->st>>>(m.data, m.bonds, m.ls, h->d_edge_idx, (char*)dev_buf, h->slot, h->L, sb);
+  else k_pack_messages<false><<<grid, NT, 0, h->st>>>(m.data, m.bonds, m.ls, h->d_edge_idx, (char*)dev_buf, h->slot, h->L, sb);
+  h->n_launch++;
+  CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->st));
   return 0;
+}
+}  // namespace
+extern "C" {
+
+// One gather kernel on the engine's stream, synchronised before returning: the buffer is complete when the call returns.
+int mpbp_pack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, void* dev_buf) {
+  return pack_unpack(h, n, edges, dev_buf, true);
+}
+
+// One scatter kernel on the engine's stream.  The CALLER orders the producer of dev_buf (e.g. the NCCL stream of an
+// all_to_all) before this call: the engine's stream does not know about it.
+int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, const void* dev_buf) {
+  return pack_unpack(h, n, edges, const_cast<void*>(dev_buf), false);
 }
 
 int mpbp_counters(mpbp_handle h, double* out8, int reset) {
@@ -1539,7 +1628,7 @@ int mpbp_counters(mpbp_handle h, double* out8, int reset) {
   out8[4] = h->n_ops;
   out8[5] = h->n_edge_updates;
   out8[6] = fl5[2];  // subspace-SVD iterations (sum)
-  out8[7] = fl5[5];  // subspace-SVD calls that hit the iteration cap
+  out8[7] = fl5[5];  // subspace-SVD calls that hit the iteration cap (resolved by the exact Jacobi fallback)
   if (reset) {
     h->n_launch = h->qr_ms = h->n_ops = h->n_edge_updates = 0;
     CUDA_OK(cudaMemset(h->d_flops, 0, 24 * sizeof(double)));
@@ -1622,6 +1711,7 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "qr_fill") h->qr_fill = value;
   else if (n == "nstreams") h->nstreams = std::max(1.0, std::min(4.0, value));
   else if (n == "level_balance") h->level_balance = value;
+  else if (n == "outlier_split") h->outlier_split = value;
   else if (n == "twovar") {
     // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
     h->twovar = value > 0 ? (int)std::min<double>(value, h->L) : 0;

@@ -161,5 +161,8 @@ class CudaBackend:
 
     def unpack(self, edges, buf):
         edges = np.ascontiguousarray(edges, dtype=np.int64)
+        # The collective that filled `buf` is ordered on torch's CURRENT stream (all_to_all_single makes it wait for
+        # NCCL); the engine scatters on its OWN stream, which knows nothing about either: drain the current stream first.
+        self.torch.cuda.current_stream().synchronize()
         if len(edges):
             self._lib.check(self._lib.lib().mpbp_unpack_messages_dev(self.bp._h, len(edges), edges.ctypes.data_as(self._lib.c_i64p), buf.data_ptr()))

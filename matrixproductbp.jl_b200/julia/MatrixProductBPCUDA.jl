@@ -63,6 +63,7 @@ end
 function sync_factors!(cu::CuMPBP)
     N = nv(cu.g); T = cu.T
     cache = Dict{Any,Int32}(); cls = zeros(Int32, N)
+    check(ccall((:mpbp_clear_node_classes, LIB), Cint, (Ptr{Cvoid},), cu.h))   # re-sync replaces every table
     for i in 1:N
         wᵢ = cu.w[i]; z = length(outedges(cu.g, i)); qi = Int(cu.q[i])
         qn = Int32[cu.q[dst(e)] for e in outedges(cu.g, i)]
@@ -96,20 +97,46 @@ trunc_args(t::TruncBondMax) = (Cint(0), Cint(t.mprime), 0.0)
 trunc_args(t::TruncThresh) = (Cint(1), Cint(0), Float64(t.ε))
 trunc_args(t::TruncBondThresh) = (Cint(2), Cint(t.mprime), Float64(t.ε))
 
-"`iterate!(bp; maxiter, svd_trunc, tol, damp, nodes, shuffle_nodes)` -- same keywords and return value as src/mpbp.jl:185-198"
+"""
+Convergence record, the device-side twin of `CB_BP` (src/mpbp.jl:157-183): `Δs` per iteration, `f` the observable
+`f(x, i)` whose means define Δ (default: the state index, as `CB_BP`'s default).  `iterate!` returns `(iters, cb)`.
+"""
+mutable struct CB_CuBP{TF}
+    f::TF
+    Δs::Vector{Float64}
+end
+CB_CuBP(cu::CuMPBP; f=(x, i) -> x) = CB_CuBP(f, Float64[])
+
+"`iterate!(bp; maxiter, svd_trunc, tol, damp, nodes, shuffle_nodes, cb)` -- same keywords and return value `(iters, cb)` as src/mpbp.jl:185-198"
 function iterate!(cu::CuMPBP; maxiter::Integer=5, svd_trunc=TruncThresh(1e-6), tol=1e-10, damp=0.0,
-        nodes=collect(vertices(cu.g)), shuffle_nodes::Bool=true, schedule::Symbol=:sequential, showprogress=false, cb=nothing)
+        nodes=collect(vertices(cu.g)), shuffle_nodes::Bool=true, schedule::Symbol=:sequential, showprogress=false,
+        cb=CB_CuBP(cu))
     cu.classes_dirty && sync_factors!(cu)
     kind, d, ε = trunc_args(svd_trunc)
     nd = Int64.(nodes .- 1)
-    order = shuffle_nodes && schedule == :sequential ?
-        reduce(vcat, [it == 1 ? nd : nd[randperm(length(nd))] for it in 1:maxiter]) : Int64[]
-    iters = Ref{Cint}(0); Δs = zeros(maxiter)
-    check(ccall((:mpbp_iterate, LIB), Cint,
+    qmax = maximum(Int.(cu.q))
+    obs = zeros(qmax, nv(cu.g))                       # obs[x, i] = f(x, i): row-major [i][x] on the C side
+    for i in 1:nv(cu.g), x in 1:Int(cu.q[i]); obs[x, i] = cb.f(x, i); end
+    iters = Ref{Cint}(0); Δ = zeros(1)
+    call(nodes_now, n_it, Δs) = check(ccall((:mpbp_iterate, LIB), Cint,
         (Ptr{Cvoid}, Cint, Cint, Cint, Float64, Float64, Float64, Cint, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Float64}, Ref{Cint}, Ptr{Float64}),
-        cu.h, maxiter, kind, d, ε, tol, damp, schedule == :parallel ? 1 : 0, nd, length(nd),
-        isempty(order) ? C_NULL : pointer(order), C_NULL, iters, Δs))
-    return Int(iters[]), Δs[1:iters[]]
+        cu.h, n_it, kind, d, ε, tol, damp, schedule == :parallel ? 1 : 0, nodes_now, length(nodes_now), C_NULL, obs, iters, Δs))
+    if shuffle_nodes && schedule == :sequential
+        # src/mpbp.jl:188-196: first sweep in the given order, then `sample!(nodes, vertices(bp.g), replace=false)` after
+        # every sweep.  One C call per iteration with that iteration's list (nothing of size maxiter x N is
+        # materialised); Δ and the tol test are the library's.
+        for it in 1:maxiter
+            call(nd, 1, Δ)
+            push!(cb.Δs, Δ[1])
+            Δ[1] < tol && return it, cb
+            nd = Int64.(randperm(nv(cu.g))[1:length(nd)] .- 1)
+        end
+        return maxiter, cb
+    end
+    Δs = zeros(maxiter)
+    call(nd, maxiter, Δs)
+    append!(cb.Δs, Δs[1:iters[]])
+    return Int(iters[]), cb
 end
 
 function beliefs(cu::CuMPBP{G,F}) where {G,F}
@@ -193,5 +220,5 @@ function get_message(cu::CuMPBP, e::Integer)
     TensorTrain(tensors)
 end
 
-export CuMPBP, sync_factors!, sync_reweightings!, get_message
+export CuMPBP, CB_CuBP, sync_factors!, sync_reweightings!, get_message
 end # module

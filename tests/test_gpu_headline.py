@@ -1,0 +1,175 @@
+"""Parity at the shapes the bench numbers are quoted on, Delta / means on the device, and the
+CUDA multi-rank path on one GPU.
+
+* headline node updates: ONE node update with random full-bond incoming messages at d=20/T=50 (D=400: H=64 QR,
+  subspace SVD, TSQR), SIS d=10/T=50, SIRS d=15/T=40 with hard one-hot observations (rank drops), infinite graph
+  k=4, d=30 (D=900: H=16 QR).  Expected values = the oracle's, committed under tests/golden/ (the oracle needs up to
+  13 minutes per case; tests/golden/make_headline_golden.py regenerates them).  Tolerance 1e-8 (north_star).
+* the subspace-SVD non-convergence counter must stay an exact-fallback count, never a silent approximation.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import mpbp_b200 as M
+from mpbp_b200.dist import CudaBackend, DistMPBP, LocalProblem, partition_balanced
+from oracle import mpbp as O, tt as OT
+from tests.common import build_pair, compare, otrunc
+from tests.headline_cases import CASES, case_inputs
+
+TOL = 1e-8
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FACTORS = {"glauber": M.HomogeneousGlauberFactor, "sis": M.SISFactor, "sirs": M.SIRSFactor}
+
+
+def _device_case(name):
+    c = CASES[name]
+    inp = case_inputs(name)
+    T, d = c["T"], c["d"]
+    L = T + 1
+    fac = FACTORS[c["kind"]](*c["params"])
+    msgs = []
+    for k in range(len(inp["msgs"])):
+        A = OT.TT([a.copy() for a in inp["msgs"][k]])
+        OT.normalize(A)  # same normalisation as the golden generator: the tensors carry everything, ls = 0
+        msgs.append([np.array(a) for a in A])
+    if c["infinite"]:
+        bp = M.mpbp_infinite_graph(c["z"], [fac] * L, c["q"], phi=[p.copy() for p in inp["phi"][0]], dmax=d)
+        bp.set_message(0, msgs[0])
+    else:
+        g = M.IndexedBiDiGraph(inp["N"], inp["und"])
+        bp = M.mpbp(g, [[fac] * L for _ in range(inp["N"])], inp["q"], T, phi=[[p.copy() for p in ph] for ph in inp["phi"]], dmax=d)
+        og = O.BiDiGraph(inp["N"], inp["und"])
+        assert list(g.src) == og.src and list(g.dst) == og.dst
+        for k, e in enumerate(og.in_edges[0]):
+            bp.set_message(e, msgs[k])
+    checksum = float(sum(np.sum(t) for m in msgs for t in m))
+    return bp, c, checksum
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_headline_node_update_vs_oracle_golden(name):
+    gold = np.load(os.path.join(GOLD, f"headline_{name}.npz"), allow_pickle=True)
+    bp, c, checksum = _device_case(name)
+    # the golden file's inputs are these inputs (flat d=1 messages on the other edges add their own constant)
+    nflat = int(gold["nedges"]) - (1 if c["infinite"] else c["z"])
+    flat_sum = nflat * (c["T"] + 1) * c["q"] * c["q"] * (1.0 / (c["q"] * c["q"]))
+    assert abs(float(gold["input_checksum"]) - checksum - flat_sum) < 1e-9 * max(1.0, abs(checksum))
+    bp.counters(reset=True)
+    iters, cb = M.iterate_(bp, maxiter=1, svd_trunc=M.TruncBond(c["d"]), tol=0.0, nodes=[0], shuffle_nodes=False)
+    ctr = bp.counters()
+    b0 = M.beliefs(bp)[0]
+    f0 = M.api.free_energy_contributions(bp)[0]
+    pb, lz = M.pair_beliefs(bp)
+    eb = float(np.max(np.abs(b0 - gold["belief0"])))
+    ef = abs(f0 - float(gold["f0"]))
+    ep = max(float(np.max(np.abs(np.array(a) - np.array(b)))) for a, b in zip(pb, gold["pair"]))
+    el = float(np.max(np.abs(np.asarray(lz) - gold["pair_logz"])))
+    print(f"{name}: |db|={eb:.2e} |df|={ef:.2e} |dpair|={ep:.2e} |dlogz|={el:.2e} heavy ops={ctr['ops']:.0f} "
+          f"subspace svd calls={ctr['svd_calls']:.0f} iters={ctr['svd_iters']:.0f} exact fallbacks={ctr['svd_unconverged']:.0f}")
+    assert eb < TOL and ef < TOL and ep < TOL and el < TOL, (eb, ef, ep, el)
+    # outgoing bonds are at the cap in the bulk, exactly like the oracle's
+    out_e = 0 if c["infinite"] else int(M.IndexedBiDiGraph(c["z"] + 1, [(0, k) for k in range(1, c["z"] + 1)]).outedges(0)[0])
+    assert max(t.shape[1] for t in bp.get_message(out_e)) == c["d"]
+
+
+def test_deltas_and_custom_observable_vs_oracle():
+    """CB_BP (src/mpbp.jl:157-183): Delta_it = max |means_f(new) - means_f(old)| with the caller's f, baseline = the
+    means of the beliefs at the start of the call.  Device deltas == oracle deltas, over several calls, for the default
+    observable and for potts2spin, both schedules; the tol stop fires at the same iteration."""
+    T = 4
+    und = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2), (3, 4)]
+    N = 5
+    kinds = [("glauber", (0.6, 0.1 * (i - 2), 1.0)) for i in range(N)]
+    phi = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    f_spin = lambda x, i: 3 - 2 * x  # potts2spin
+    for schedule in ("sequential", "parallel"):
+        bo, bd = build_pair(N, und, T, kinds, [2] * N, phi, dmax=6)
+        tr = M.TruncBond(6)
+        # call 1: default observable
+        it_o, d_o = O.iterate(bo, maxiter=2, trunc=otrunc(tr), tol=0.0, schedule=schedule)
+        it_d, cb = M.iterate_(bd, maxiter=2, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule=schedule)
+        assert it_o == it_d and np.allclose(cb.deltas, d_o, rtol=0, atol=1e-9), (cb.deltas, d_o)
+        # call 2: a DIFFERENT observable; the baseline must be recomputed from the current beliefs with f_spin
+        it_o, d_o = O.iterate(bo, maxiter=3, trunc=otrunc(tr), tol=0.0, schedule=schedule, f=f_spin)
+        cb2 = M.CB_BP(bd, f=f_spin)
+        it_d, cb2 = M.iterate_(bd, maxiter=3, svd_trunc=tr, tol=0.0, shuffle_nodes=False, schedule=schedule, cb=cb2)
+        assert it_o == it_d and np.allclose(cb2.deltas, d_o, rtol=0, atol=1e-9), (cb2.deltas, d_o)
+        assert d_o[0] > 1e-6  # a non-trivial first delta (against the wrong baseline it would be O(1) off)
+        # call 3: convergence stop at the same iteration
+        it_o, d_o = O.iterate(bo, maxiter=30, trunc=otrunc(tr), tol=1e-5, schedule=schedule, f=f_spin)
+        it_d, cb3 = M.iterate_(bd, maxiter=30, svd_trunc=tr, tol=1e-5, shuffle_nodes=False, schedule=schedule, cb=M.CB_BP(bd, f=f_spin))
+        assert it_o == it_d < 30, (it_o, it_d)
+        assert np.allclose(cb3.deltas, d_o, rtol=0, atol=1e-9)
+        # means(f, bp) read-out
+        mo = O.means(bo, f_spin)
+        md = M.means(f_spin, bd)
+        assert max(abs(a - b) for x, y in zip(mo, md) for a, b in zip(x, y)) < TOL
+
+
+def test_cuda_multirank_equals_single_rank_bitwise():
+    """two LocalProblem partitions = two engine handles on cuda:0, the halo exchange done by splitting / concatenating the
+    packed device buffers exactly as all_to_all_single would: beliefs, free energies and Delta after 3 Jacobi iterations
+    must equal the single-handle run BIT FOR BIT (order-preserving local ids keep the cavity order, hence every
+    truncation, independent of the partition)."""
+    import torch
+    T, d = 5, 6
+    import networkx as nx
+    G = nx.random_regular_graph(3, 12, seed=3)
+    und = [(int(a), int(b)) for a, b in G.edges()]
+    N = 12
+    fac = M.HomogeneousGlauberFactor(0.5, 0.1, 1.0)
+    tr = M.TruncBond(d)
+
+    # single rank
+    lp1 = LocalProblem(N, und, np.zeros(N, dtype=np.int64), 0)
+    g1 = M.IndexedBiDiGraph(N, lp1.local_und)
+    lp1.build_exchange(g1.src, g1.dst, 1)
+    phi1 = [[np.array([0.2, 0.8]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+    bp1 = M.mpbp(g1, [[fac] * (T + 1)] * N, [2] * N, T, phi=phi1, dmax=d)
+    bp1.set_option("qr_fill", 1)  # no TSQR split: its chunking depends on how many ops share a launch, i.e. on the partition
+    be1 = CudaBackend(bp1, lp1.owned_local, tr)
+    d1 = []
+    for it in range(3):
+        d1.append(be1.iterate_owned())
+    b1 = M.beliefs(bp1)
+    f1 = M.api.free_energy_contributions(bp1)
+    # two ranks on one GPU
+    owner = partition_balanced(N, und, 2)
+    assert 0 < owner.sum() < N
+    lps, bps, bes = [], [], []
+    for r in range(2):
+        lp = LocalProblem(N, und, owner, r)
+        g = M.IndexedBiDiGraph(len(lp.nodes), lp.local_und)
+        lp.build_exchange(g.src, g.dst, 2)
+        phi = [[np.array([0.2, 0.8]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(g.N)]
+        bp = M.mpbp(g, [[fac] * (T + 1)] * g.N, [2] * g.N, T, phi=phi, dmax=d)
+        bp.set_option("qr_fill", 1)
+        lps.append(lp); bps.append(bp); bes.append(CudaBackend(bp, lp.owned_local, tr))
+    sb = bes[0].slot_bytes
+    d2 = []
+    for it in range(3):
+        dd = [bes[r].iterate_owned() for r in range(2)]
+        # all_to_all_single: rank r's send buffer is the concatenation over destination peers; peer p receives from r the
+        # slice addressed to it, in rank order
+        sbuf = [bes[r].pack(np.concatenate(lps[r].send)) for r in range(2)]
+        for p in range(2):
+            parts = []
+            for r in range(2):
+                off = sum(len(lps[r].send[k]) for k in range(p)) * sb
+                parts.append(sbuf[r][off:off + len(lps[r].send[p]) * sb])
+                assert len(lps[r].send[p]) == len(lps[p].recv[r])
+            rbuf = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device="cuda")
+            bes[p].unpack(np.concatenate(lps[p].recv), rbuf.contiguous())
+        d2.append(max(dd))
+    assert d2 == d1, (d1, d2)  # bitwise: the same floating-point operations in the same order
+    for r in range(2):
+        b = M.beliefs(bps[r])
+        f = M.api.free_energy_contributions(bps[r])
+        for li in lps[r].owned_local:
+            gi = int(lps[r].nodes[int(li)])
+            assert np.array_equal(b[int(li)], b1[gi]), (r, gi)
+            assert f[int(li)] == f1[gi]
