@@ -104,6 +104,7 @@ struct mpbp_state {
   double nstreams = 4;
   int twovar = 0;            // > 0: maxdist of the two-time marginals computed with every belief (option "twovar")
   double* d_tv = nullptr;    // [N][L][L][qmax*qmax]
+  double kron_mma = 1;       // 1: DMMA Kronecker-carry kernel (k_kron_carry_mma), 0: scalar FP64 kernel (k_kron_carry)
   double outlier_split = 0;  // > 0: ops costing more than this multiple of the mean of their launch group run in a
                              // group of their own, TSQR-split, next to the other groups (0 = off; experimental)
   double level_balance = 1;  // stagger the cavity levels of the nodes of a chunk so that every round carries similar work
@@ -172,6 +173,9 @@ int common_init(mpbp_state* h) {
     const int ms = h->max_smem;
     CUDA_OK(cudaFuncSetAttribute(k_kron_carry<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_kron_carry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_kron_carry_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_kron_carry_mma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
+    CUDA_OK(cudaFuncSetAttribute(k_kron_carry_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_ft_merge<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
     CUDA_OK(cudaFuncSetAttribute(k_qr_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms));
@@ -708,7 +712,8 @@ void ev_end(mpbp_state* h, cudaStream_t st) {
 // one group of ops of one level (scratch already assigned) and the stream it runs on
 struct GroupRun {
   const OpDesc* d_ops;
-  int nops, maxD, maxX, maxNy, maxq;
+  int nops, maxD, maxX, maxNy, maxq, maxNyS;
+  int kc_mma_rb;  // 16 / 8 / 4: right-bond columns per CTA of the DMMA Kronecker-carry kernel; 0 = scalar kernel
   cudaStream_t st;
   size_t kc_smem, ft_big, ft_small;
   int kc_rb;
@@ -732,6 +737,14 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
     g.kc_smem *= g.kc_rb;
     if (g.kc_smem > (size_t)h->max_smem)
       return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, g.maxNy);
+    g.kc_mma_rb = 0;
+    if (h->kron_mma > 0) {
+      // prefer two CTAs per SM (the A fragments come from L1/L2: latency hiding), else the widest tile that fits
+      for (int rb : {16, 8, 4})
+        if (!g.kc_mma_rb && kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS) * 8 <= (size_t)h->max_smem / 2) g.kc_mma_rb = rb;
+      for (int rb : {16, 8, 4})
+        if (!g.kc_mma_rb && kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS) * 8 <= (size_t)h->max_smem) g.kc_mma_rb = rb;
+    }
     g.dXcap = d * g.maxX;
     auto pickH = [&](int n, size_t& bytes) -> int {
       const size_t s64 = ft_smem_doubles<64>(n) * 8, s32 = ft_smem_doubles<32>(n) * 8, s16 = ft_smem_doubles<16>(n) * 8;
@@ -752,7 +765,14 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
     for (auto& g : groups) {
       dim3 g1(g.nops, g.maxq, (g.maxD + KC_RC - 1) / KC_RC);
       ev_begin(h, F_KC, g.st);
-      if (g.kc_rb == 4) k_kron_carry<4><<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
+      if (g.kc_mma_rb) {
+        const int rb = g.kc_mma_rb;
+        dim3 gm(g.nops, g.maxq, (g.maxD + rb - 1) / rb);
+        const size_t sm = kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS) * 8;
+        if (rb == 16) k_kron_carry_mma<16><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, h->d_flops + 17);
+        else if (rb == 8) k_kron_carry_mma<8><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, h->d_flops + 17);
+        else k_kron_carry_mma<4><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, h->d_flops + 17);
+      } else if (g.kc_rb == 4) k_kron_carry<4><<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
       else k_kron_carry<1><<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
       ev_end(h, g.st);
       h->n_launch++;
@@ -888,7 +908,7 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
       std::vector<GroupRun> groups(G);
       for (int gi = 0; gi < G; ++gi) {
         GroupRun& gr = groups[gi];
-        gr.nops = 0; gr.maxD = 1; gr.maxX = 1; gr.maxNy = 1; gr.maxq = 1;
+        gr.nops = 0; gr.maxD = 1; gr.maxX = 1; gr.maxNy = 1; gr.maxq = 1; gr.maxNyS = 1;
         gr.st = gi == 0 ? st : h->aux[gi - 1];
       }
       // optional: the few ops far above the mean cost of this launch (they come first after the LPT sort) bound the
@@ -912,6 +932,7 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         gr.maxX = std::max(gr.maxX, op.nyo * op.q);
         gr.maxNy = std::max(gr.maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
         gr.maxq = std::max(gr.maxq, op.q);
+        gr.maxNyS = std::max(gr.maxNyS, std::min(op.ny1, op.ny2));
       }
       {
         size_t off = 0;
@@ -1712,6 +1733,7 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "nstreams") h->nstreams = std::max(1.0, std::min(4.0, value));
   else if (n == "level_balance") h->level_balance = value;
   else if (n == "outlier_split") h->outlier_split = value;
+  else if (n == "kron_mma") h->kron_mma = value;
   else if (n == "twovar") {
     // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
     h->twovar = value > 0 ? (int)std::min<double>(value, h->L) : 0;
@@ -1807,16 +1829,15 @@ __global__ void __launch_bounds__(NT) k_test_svd(const double* M, int p, int n, 
   __shared__ double red[NW + 1];
   const double* Mb = M + (size_t)blockIdx.x * p * n;
   double* sc = scratch + (size_t)blockIdx.x * scratch_per;
-  double* R2 = sc;                       // p*p (direct, n > p) or p*64
-  double* Zg = R2 + (size_t)p * max(p, 64);
-  double* Mt = Zg + (size_t)n * 64;
-  double* Mcopy = Mt + (size_t)p * n;    // n*p row-major copy for the QR pre-reduction (destroyed)
+  double* R2 = sc;                                  // p*p (direct path, n > p)
+  double* Mcopy = R2 + (size_t)p * p;               // n*p row-major copy for the QR pre-reduction (destroyed)
+  double* svdscr = Mcopy + (size_t)p * n;            // svd_scratch_doubles(p, n)
   if (n > p && svd_direct(p, n, jac_doubles)) {
     for (int i = threadIdx.x; i < p * n; i += NT) Mcopy[i] = Mb[i];
     __syncthreads();
     qr_ft_cta<16>(Mcopy, n, p, p, R2, p, false, smem);  // M^T (n x p row-major == M col-major) -> R (p x p)
   }
-  const SvdLeft sv = svd_left_cta(Mb, R2, R2, Zg, Mt, p, n, tr, tr.d, jac_doubles, smem, &flag, &s_done, red, err, stats);
+  const SvdLeft sv = svd_left_cta(Mb, R2, svdscr, p, n, tr, tr.d, jac_doubles, smem, &flag, &s_done, red, err, stats);
   const double* sig = smem;
   const int* order = reinterpret_cast<const int*>(smem + SUB_BMAX);
   const int keep = min(tr.d, sv.ceff);
@@ -1828,14 +1849,14 @@ __global__ void __launch_bounds__(NT) k_test_svd(const double* M, int p, int n, 
 }
 // leading-d left singular vectors of `batch` column-major p x n matrices through the op-truncation SVD core
 // (direct Jacobi or blocked subspace iteration, chosen as in the engine).  U: [batch][p x d], S: [batch][d].
-// stats[0..4] = subspace calls, iterations, block sizes (sum), max sweeps (sum), unconverged.  *ms = best of 3.
+// stats[0..4] = subspace calls, iterations, block sizes (sum), max sweeps (sum), exact fallbacks.  *ms = best of 3.
 int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, double* S, double* stats5, double* ms) {
   int maxs = 0;
   CUDA_OK(cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0));
   maxs -= 2048;
   const size_t jac_fixed = 3 * SUB_BMAX, jac_doubles = (size_t)maxs / 8 - jac_fixed;
   CUDA_OK(cudaFuncSetAttribute(k_test_svd, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-  const size_t per = (size_t)p * std::max(p, 64) + (size_t)n * 64 + 2 * (size_t)p * n + 64;
+  const size_t per = (size_t)p * p + (size_t)p * n + svd_scratch_doubles(p, n) + 64;
   double *dM, *dU, *dS, *dscr, *dst;
   int* derr;
   CUDA_OK(cudaMalloc((void**)&dM, sizeof(double) * (size_t)batch * p * n));
@@ -1871,7 +1892,7 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
   {
     double ph[6];
     CUDA_OK(cudaMemcpy(ph, dst + 8, sizeof(double) * 6, cudaMemcpyDeviceToHost));
-    if (getenv("MPBP_SVD_PHASES")) printf("svd phases (Mcycles/call): transpose %.2f  select %.2f  start-jacobi %.2f  iter-gemms %.2f  iter-jacobi %.2f  final %.2f\n", ph[0] / batch / 1e6, ph[1] / batch / 1e6, ph[2] / batch / 1e6, ph[3] / batch / 1e6, ph[4] / batch / 1e6, ph[5] / batch / 1e6);
+    if (getenv("MPBP_SVD_PHASES")) printf("svd phases (Mcycles/call): final %.2f  select %.2f  start-orth %.2f  iter-gemms %.2f  iter-orth %.2f  iter-ritz %.2f\n", ph[0] / batch / 1e6, ph[1] / batch / 1e6, ph[2] / batch / 1e6, ph[3] / batch / 1e6, ph[4] / batch / 1e6, ph[5] / batch / 1e6);
   }
   cudaFree(dM); cudaFree(dU); cudaFree(dS); cudaFree(dscr); cudaFree(dst); cudaFree(derr);
   cudaEventDestroy(e0); cudaEventDestroy(e1);

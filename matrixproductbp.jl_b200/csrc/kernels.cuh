@@ -14,6 +14,7 @@
 #include "jacobi.cuh"
 #include "qr.cuh"
 #include "qr_ft.cuh"
+#include "svd_block.cuh"
 
 namespace mpbp {
 
@@ -224,6 +225,163 @@ __global__ void __launch_bounds__(NT) k_kron_carry(const OpDesc* ops, int t, int
   }
 }
 
+// DMMA version of k_kron_carry (same contract, same output).  The two contractions are GEMMs:
+//   stage 1 (per y_S)        Z_yS[m_S, (n_F,u)] = sum_{n_S} S[m_S,n_S,y_S,x] * Lc[(n_F,n_S), u]          M = bl_S, K = br_S, N = br_F*RB
+//   stage 2 (per output y)   out_y[m_F, (m_S,u)] = sum_{(y_F,y_S)} Pyy * sum_{n_F} F[m_F,n_F,y_F,x] * Z_yS[m_S,n_F,u]   M = bl_F, K = br_F, N = bl_S*RB
+// where u indexes the RB right-bond columns of L_{t+1} handled by the CTA and (F, S) = (B1, B2) or (B2, B1): the operand
+// with FEWER auxiliary states is contracted first (Z holds ny_S copies in shared memory).  M is padded to a multiple of 8
+// and K to a multiple of 4 with zeros (bonds are 1..30); one B fragment feeds every m-tile.  A fragments come straight
+// from L1/L2 (a site of an operand train is a few KB).  grid (nops, q, ceil(rcap/RB)).
+// dyn smem: RB*DrP + nySmax*RB*brFmax*ZP doubles (see kc_mma_smem_doubles).
+__host__ __device__ inline int kc_pad4(int n) { return n + ((12 - (n & 7)) & 7); }  // == 4 (mod 8): conflict-free B fragments
+__host__ __device__ inline size_t kc_mma_smem_doubles(int RB, int Dcap, int dcap, int nyS) {
+  return (size_t)RB * (Dcap + 8) + (size_t)nyS * RB * dcap * kc_pad4(dcap);
+}
+template <int RB>
+__global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t, int L, int nyS_cap, double* flops) {
+  extern __shared__ double smem[];
+  const OpDesc& op = ops[blockIdx.x];
+  const int x = blockIdx.y;
+  if (x >= op.q) return;
+  const int bl1 = op.a.bonds[t], br1 = op.a.bonds[t + 1], bl2 = op.b.bonds[t], br2 = op.b.bonds[t + 1];
+  const int Dl = bl1 * bl2, Dr = br1 * br2;
+  const int rn = op.r[t + 1];
+  const int rr0 = blockIdx.z * RB;
+  if (rr0 >= rn) return;
+  const int nb = min(RB, rn - rr0);
+  const double* A1 = op.a.data + (size_t)t * op.a.stride;
+  const double* A2 = op.b.data + (size_t)t * op.b.stride;
+  const double* Lm = (t + 1 < L) ? op.Lbuf + (size_t)(t + 1) * op.Lstride : nullptr;
+  const double* pyy = op.pyy + (size_t)t * op.pyy_tstride;
+  const int ny1 = op.ny1, ny2 = op.ny2, nyo = op.nyo;
+  // roles: S is contracted first
+  const bool swap = ny1 < ny2;  // true: S = B1, F = B2
+  const double* Sd = swap ? A1 : A2;
+  const double* Fd = swap ? A2 : A1;
+  const int blS = swap ? bl1 : bl2, brS = swap ? br1 : br2, nyS = swap ? ny1 : ny2;
+  const int blF = swap ? bl2 : bl1, brF = swap ? br2 : br1, nyF = swap ? ny2 : ny1;
+  const int sLF = swap ? br1 : 1, sLS = swap ? 1 : br1;        // L row index = nF*sLF + nS*sLS
+  const int sOF = swap ? bl1 : 1, sOS = swap ? 1 : bl1;        // out row index = mF*sOF + mS*sOS
+  const int pF = swap ? nyo * ny1 : nyo, pS = swap ? nyo : nyo * ny1;  // pyy index = y + yF*pF + yS*pS + nyo*ny1*ny2*x
+  if (nyS > nyS_cap) return;  // host guarantees this does not happen (falls back to the scalar kernel otherwise)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q4 = lane & 3;
+  const int DrP = Dr + 8;
+  const int ZP = kc_pad4(blS);
+  double* Lc = smem;                       // [u][DrP]
+  double* Z = smem + (size_t)RB * DrP;     // [(yS*RB + u)*brF + nF][ZP]  (mS fastest)
+  if (flops && blockIdx.z == 0 && threadIdx.x == 0) {
+    int npairs = 0;
+    for (int yS = 0; yS < nyS; ++yS)
+      for (int yF = 0; yF < nyF; ++yF) {
+        bool any = false;
+        for (int y = 0; y < nyo; ++y) any |= pyy[y + yF * pF + yS * pS + (size_t)nyo * ny1 * ny2 * x] != 0.0;
+        npairs += any;
+      }
+    atomicAdd(flops, 2.0 * rn * ((double)blS * brS * brF * nyS + (double)blF * brF * blS * npairs));
+  }
+  for (int i = threadIdx.x; i < RB * DrP; i += NT) {
+    const int u = i / DrP, e = i % DrP;
+    Lc[i] = (u < nb && e < Dr) ? (Lm ? Lm[e + (size_t)Dr * (rr0 + u)] : 1.0) : 0.0;
+  }
+  __syncthreads();
+  // ---------------- stage 1 ----------------
+  const int mtS = (blS + 7) >> 3, ksS = (brS + 3) >> 2;
+  const int ncol1 = brF * RB, nt1 = (ncol1 + 7) >> 3;
+  for (int yS = 0; yS < nyS; ++yS) {
+    const double* Sy = Sd + (size_t)blS * brS * (yS + nyS * x);
+    for (int nt = warp; nt < nt1; nt += NW) {
+      const int cB = 8 * nt + g;                       // B-fragment column of this lane
+      const bool cBok = cB < ncol1;
+      const int boff = cBok ? (cB / brF) * DrP + (cB % brF) * sLF : 0;  // column (nF, u), nF fastest
+      double acc[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+      for (int ks = 0; ks < ksS; ++ks) {
+        const int kB = 4 * ks + q4;
+        const double bf = (cBok && kB < brS) ? Lc[boff + kB * sLS] : 0.0;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          if (mt < mtS) {
+            const int mr = 8 * mt + g;
+            const double af = (mr < blS && kB < brS) ? Sy[mr + blS * kB] : 0.0;
+            dmma884(acc[mt][0], acc[mt][1], af, bf);
+          }
+        }
+      }
+      // C tile: rows mS = 8mt+g, columns c0, c0+1
+      const int c0 = 8 * nt + 2 * q4;
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        if (mt < mtS) {
+          const int mr = 8 * mt + g;
+          if (mr < ZP) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = c0 + e;
+              if (c < ncol1) {
+                const int u = c / brF, nF = c % brF;
+                Z[((size_t)(yS * RB + u) * brF + nF) * ZP + mr] = mr < blS ? acc[mt][e] : 0.0;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- stage 2 ----------------
+  const int mtF = (blF + 7) >> 3, ksF = (brF + 3) >> 2;
+  const int ncol2 = blS * RB, nt2 = (ncol2 + 7) >> 3;
+  const size_t pyx = (size_t)nyo * ny1 * ny2 * x;
+  for (int y = 0; y < nyo; ++y) {
+    for (int nt = warp; nt < nt2; nt += NW) {
+      const int cB = 8 * nt + g;
+      const bool cBok = cB < ncol2;
+      const int uB = cBok ? cB / blS : 0, mSB = cBok ? cB % blS : 0;  // column (mS, u), mS fastest
+      double acc[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+      for (int yS = 0; yS < nyS; ++yS) {
+        const double* zb = Z + ((size_t)(yS * RB + uB) * brF) * ZP + mSB;
+        for (int yF = 0; yF < nyF; ++yF) {
+          const double pv = pyy[y + yF * pF + yS * pS + pyx];
+          if (pv == 0.0) continue;
+          const double* Fy = Fd + (size_t)blF * brF * (yF + nyF * x);
+          for (int ks = 0; ks < ksF; ++ks) {
+            const int kB = 4 * ks + q4;
+            const double bf = (cBok && kB < brF) ? zb[(size_t)kB * ZP] : 0.0;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+              if (mt < mtF) {
+                const int mr = 8 * mt + g;
+                const double af = (mr < blF && kB < brF) ? pv * Fy[mr + blF * kB] : 0.0;
+                dmma884(acc[mt][0], acc[mt][1], af, bf);
+              }
+            }
+          }
+        }
+      }
+      const int c0 = 8 * nt + 2 * q4;
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        if (mt < mtF) {
+          const int mF = 8 * mt + g;
+          if (mF < blF) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = c0 + e;
+              if (c < ncol2) {
+                const int u = c / blS, mS = c % blS;
+                if (u < nb) op.M[(size_t)(mF * sOF + mS * sOS) + (size_t)Dl * (rr0 + u + (size_t)rn * (y + nyo * x))] = acc[mt][e];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Sweep-1 factor of site t with the flat-tree DMMA QR: L_t = R^T of M_t ((rn*X) x Dl), r[t] = min(rows, Dl).
 // When a launch holds few matrices (nsplit > 1) tall matrices are split TSQR-style over several CTAs: row chunks
 // are factored independently into op.Ms (n x n each) and k_qr_ft_merge factors the stack.
@@ -404,91 +562,45 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_small(const OpDesc
 
 // ---- truncated SVD of M2 (p x n, p = d~X, n = r_{t+1}) : only the leading left singular vectors are needed ----
 // small matrices : one-sided Jacobi on the (QR-reduced) matrix in shared memory ("direct");
-// large matrices : blocked subspace iteration  Z <- orth(M^T Q), Q <- orth(M Z)  with b <= 64 columns, the
-//                  tall-skinny blocks orthonormalised by one-sided Jacobi in shared memory.  Converges like
-//                  (sigma_{b+1}/sigma_k)^2 per iteration; validated against exact SVDs in DESIGN.md / tests.
+// large matrices : un-squared block subspace iteration (svd_block.cuh)
+//                    Z = orth(M^T Q),  Y = M Z = Q R,  Ritz values = singular values of the b x b factor R
+//                  with b <= 64 columns: DMMA GEMMs, Householder orthonormalisation of the blocks, Jacobi only on R.
+//                  Converges like (sigma_{b+1}/sigma_k)^2 per iteration; validated against exact SVDs in the tests.
 constexpr int SUB_BMAX = 64;   // storage bound of the block
-constexpr int SUB_BLOCK = 48;  // block width used (>= 2d+8 at d = 20): Jacobi cost ~ b^2, convergence ~ (sigma_{b+1}/sigma_k)^2
+constexpr int SUB_BLOCK = 48;  // block width used (>= 2d+8 at d = 20): convergence ~ (sigma_{b+1}/sigma_k)^2
 constexpr int SUB_MAXIT = 60;
 __host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles) {
   const int c = p < n ? p : n;
   return c <= SUB_BMAX && (long long)p * c <= jac_doubles;
 }
-__device__ inline void normalize_cols(double* W, int rows, int b, const double* sig, const bool squared = false) {
+// doubles of global scratch svd_left_cta needs for a p x n matrix (subspace path + exact fallback)
+__host__ __device__ inline size_t svd_scratch_doubles(int p, int n) {
+  const size_t mx = (size_t)(p > n ? p : n) + 8;
+  return 3 * SUB_BMAX * mx + (size_t)p * n;
+}
+__device__ inline void normalize_cols(double* W, int rows, int b, int ld, const double* sig) {
   double smax = 0.0;
   for (int j = 0; j < b; ++j) smax = fmax(smax, sig[j]);
-  if (squared) smax *= smax;
   for (int j = threadIdx.x >> 5; j < b; j += NW) {
-    const double f = jacobi_inv_sigma(squared ? sig[j] * sig[j] : sig[j], smax);
-    for (int k = threadIdx.x & 31; k < rows; k += 32) W[k + (size_t)j * rows] *= f;
+    const double f = jacobi_inv_sigma(sig[j], smax);
+    for (int k = threadIdx.x & 31; k < rows; k += 32) W[k + (size_t)j * ld] *= f;
   }
   __syncthreads();
-}
-// OUT[r + rows_out*j] = sum_k MT(k, r) * W[k + kdim*j]   with M addressed as M[a + p*rr]
-// OUT (rows_out x b) = Mx W  where Mx (rows_out x kdim) is column-major with leading dimension rows_out
-// (thread per output row: consecutive lanes read consecutive addresses of Mx), W (kdim x b) in shared memory.
-__device__ inline void sub_gemm(const double* __restrict__ Mx, int rows_out, int kdim, const double* W, int b, double* OUT) {
-  for (int r = threadIdx.x; r < rows_out; r += NT) {
-    for (int j0 = 0; j0 < b; j0 += 16) {
-      double acc[16];
-#pragma unroll
-      for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
-      const double* w = W + (size_t)j0 * kdim;
-      const int nj = min(16, b - j0);
-      // the Mx loads come from L2: keep 8 of them in flight per thread
-      int k = 0;
-      for (; k + 8 <= kdim; k += 8) {
-        double m8[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) m8[u] = Mx[r + (size_t)rows_out * (k + u)];
-        if (nj == 16 && (kdim & 1) == 0) {
-          // 128-bit shared-memory loads: two consecutive k per load (kdim even -> 16-byte aligned)
-#pragma unroll
-          for (int u = 0; u < 8; u += 2)
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const double2 ww = *reinterpret_cast<const double2*>(w + k + u + (size_t)jj * kdim);
-              acc[jj] += m8[u] * ww.x;
-              acc[jj] += m8[u + 1] * ww.y;
-            }
-        } else if (nj == 16) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) acc[jj] += m8[u] * w[k + u + (size_t)jj * kdim];
-        } else {
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) acc[jj] += m8[u] * w[k + u + (size_t)jj * kdim];
-        }
-      }
-      for (; k < kdim; ++k) {
-        const double m = Mx[r + (size_t)rows_out * k];
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
-          if (jj < nj) acc[jj] += m * w[k + (size_t)jj * kdim];
-      }
-#pragma unroll
-      for (int jj = 0; jj < 16; ++jj)
-        if (jj < nj) OUT[r + (size_t)rows_out * (j0 + jj)] = acc[jj];
-    }
-  }
 }
 
 // Leading left singular vectors of M (p x n column-major at Mcm; when n > p and the direct path applies, R2 must
 // hold the Q-less QR factor of M^T as produced by k_qr_small).  On return (all threads): columns of A (p x ceff,
 // lda = p, in shared memory) are orthonormal left singular vectors, sig[col] their singular values, order[] sorts
 // them descending; nrm2_all = ||M||_F^2 when known (subspace path) else -1.
-// smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles].  Scratch (global): Qg >= p*64, Zg >= n*64, Mt >= p*n.
+// smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles].  scratch (global): svd_scratch_doubles(p, n) doubles.
 struct SvdLeft {
   double* A;
   int ceff;
   double nrm2_all;
 };
-__device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, double* Qg, double* Zg, double* Mt, const int p,
-                                       const int rn, const Trunc tr, const int dcap, const int jac_doubles, double* smem,
-                                       int* flagp, int* s_donep, double* red, int* err, double* stats) {
+__device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, double* scratch, const int p, const int rn, const Trunc tr,
+                                       const int dcap, const int jac_doubles, double* smem, int* flagp, int* s_donep, double* red,
+                                       int* err, double* stats) {
   int& flag = *flagp;
   int& s_done = *s_donep;
   const int c = min(p, rn);
@@ -508,7 +620,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
     const int sweeps = jacobi_cols(A, p, ceff, p, &flag);
     if (sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
     jacobi_sort(A, p, ceff, p, sig, order);
-    normalize_cols(A, p, ceff, sig);
+    normalize_cols(A, p, ceff, p, sig);
   } else {
     const int n = rn;
     const double* M = Mcm;  // column-major p x n
@@ -519,17 +631,27 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       if (stats && threadIdx.x == 0) atomicAdd(stats + 8 + which, (double)(now - tph));
       tph = now;
     };
-    for (int idx = threadIdx.x; idx < p * n; idx += NT) Mt[(idx / p) + (size_t)n * (idx % p)] = M[idx];
-    phase(0);
-    int b = min(min(max(SUB_BLOCK, min(SUB_BMAX, 2 * (tr.kind == 1 ? dcap : tr.d) + 8)), c), jac_doubles / max(p, n));
-    b &= ~7;
-    if (b < 8 || b < min(c, (tr.kind == 1 ? dcap : tr.d))) {
-      if (threadIdx.x == 0) atomicOr(err, ERR_BOND_OVERFLOW);  // shared memory cannot hold a block wide enough
+    const int kwant = tr.kind == 1 ? dcap : tr.d;
+    int b = min(min(max(SUB_BLOCK, min(SUB_BMAX, 2 * kwant + 8)), c), SUB_BMAX) & ~7;
+    if (b < 8 || b < min(c, kwant)) {
+      if (threadIdx.x == 0) atomicOr(err, ERR_BOND_OVERFLOW);  // the block cannot hold the kept bond
       b = max(b, 8);
     }
+    const int ldq = blk_ld(p), ldz = blk_ld(n);
+    const size_t mx8 = (size_t)max(p, n) + 8;
+    double* Zg = scratch;                         // GEMM output n x b (ld = ldz)
+    double* Qg = scratch + SUB_BMAX * mx8;        // GEMM output p x b (ld = ldq)
+    double* Gblk = scratch + 2 * SUB_BMAX * mx8;  // the block itself when shared memory cannot hold it
+    double* Mwork = scratch + 3 * SUB_BMAX * mx8;  // p x n work copy of the exact fallback
+    // shared-memory carve-up of W: [block : cap][S : b*b][scal : 3*b]
+    const int fixed = SUB_BMAX * SUB_BMAX + 3 * SUB_BMAX;
+    const int cap = jac_doubles - fixed;
+    double* S = W + cap;
+    double* scal = S + SUB_BMAX * SUB_BMAX;
+    double* blk = ((long long)max(ldq, ldz) * b <= cap) ? W : Gblk;
     // ---- start block: the b largest-norm columns of M ----
-    double* nrm = W;
-    int* sel = reinterpret_cast<int*>(W + n);
+    double* nrm = (n + n / 2 + 2 <= SUB_BMAX * SUB_BMAX) ? S : Zg;  // n column norms + n ints
+    int* sel = reinterpret_cast<int*>(nrm + n);
     for (int rr = threadIdx.x >> 5; rr < n; rr += NW) {
       double s = 0.0;
       for (int a = threadIdx.x & 31; a < p; a += 32) { const double x = M[a + (size_t)p * rr]; s += x * x; }
@@ -549,108 +671,112 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
     __syncthreads();
     for (int j = threadIdx.x; j < b; j += NT) order[j] = sel[j];
     __syncthreads();
-    for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = M[(idx % p) + (size_t)p * order[idx / p]];
+    for (int idx = threadIdx.x; idx < p * b; idx += NT) blk[(idx % p) + (size_t)ldq * (idx / p)] = M[(idx % p) + (size_t)p * order[idx / p]];
     for (int j = threadIdx.x; j < SUB_BMAX; j += NT) sprev[j] = 0.0;
     __syncthreads();
     phase(1);
-    // start block: two sweeps are enough (only a well-conditioned basis is needed here)
-    int sw = 0;
-    jacobi_cols(W, p, b, p, &flag, 2);
-    jacobi_sort(W, p, b, p, sig, order);
-    normalize_cols(W, p, b, sig);
+    hh_orth(blk, p, b, ldq, nullptr, scal);
     phase(2);
+    int sw = 0;
     int extra = -1;
-    const int kchk = min(b, tr.kind == 1 ? dcap : tr.d);
+    double dprev = 0.0;
+    const int kchk = min(b, kwant);
     int nit = 0;
     for (int it = 0; it < SUB_MAXIT; ++it) {
-      // one application of M M^T per iteration, ONE orthonormalisation: the kept singular values span only a few
-      // orders of magnitude, so the squared spectrum of the block stays far inside FP64 range
-      sub_gemm(Mt, n, p, W, b, Zg);  // Z = M^T Q   (n x b, not orthonormalised)
+      blk_gemm_dmma(M, (long long)p, 1LL, n, p, blk, ldq, b, Zg, ldz);  // Z = M^T Q   (n x b)
       __syncthreads();
-      for (int idx = threadIdx.x; idx < n * b; idx += NT) W[idx] = Zg[idx];
-      __syncthreads();
-      sub_gemm(M, p, n, W, b, Qg);  // Y = M Z
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
+      for (int idx = threadIdx.x; idx < n * b; idx += NT) { const size_t o = (idx % n) + (size_t)ldz * (idx / n); blk[o] = Zg[o]; }
       phase(3);
-      jacobi_cols(W, p, b, p, &flag);
-      jacobi_sort(W, p, b, p, sig, order);
-      for (int j = threadIdx.x; j < b; j += NT) sig[j] = sqrt(sig[j]);  // singular values of M (Y ~ U Sigma^2)
+      hh_orth(blk, n, b, ldz, nullptr, scal);
+      phase(4);
+      blk_gemm_dmma(M, 1LL, (long long)p, p, n, blk, ldz, b, Qg, ldq);  // Y = M Z   (p x b)
       __syncthreads();
+      for (int idx = threadIdx.x; idx < p * b; idx += NT) { const size_t o = (idx % p) + (size_t)ldq * (idx / p); blk[o] = Qg[o]; }
+      phase(3);
+      hh_orth(blk, p, b, ldq, S, scal);  // Y = Q R, R -> S (b x b)
+      phase(4);
+      sw = max(sw, jacobi_cols(S, b, b, b, &flag));  // R V = U_r Sigma: the columns of S become U_r Sigma
+      jacobi_sort(S, b, b, b, sig, order);
       ++nit;
       if (threadIdx.x == 0) {
-        // Ritz values of the squared iteration carry a noise floor eps*sigma_1^2/sigma_i: tolerate it here, the
-        // final un-squared refinement below restores the small directions
+        // Ritz VALUES converge like angle^2: once they are stationary to 1e-13 sigma_1 the subspace angle is still up to
+        // ~sqrt(1e-13).  The contraction of the last step (value error ratio r = rho_angle^2) says how many more
+        // iterations bring the angle to 1e-13 (1-2 for decaying spectra, many for flat ones, where it matters).
         const double s1 = sig[order[0]];
-        bool conv = true;
+        double dm = 0.0;
         for (int i = 0; i < kchk; ++i) {
           const double s = sig[order[i]];
-          const double tol_i = 1e-13 * s1 + 8e-16 * s1 * s1 / fmax(s, 1e-300);
-          conv = conv && (fabs(s - sprev[i]) <= tol_i);
+          dm = fmax(dm, fabs(s - sprev[i]));
           sprev[i] = s;
         }
-        if (extra < 0 && conv) extra = 1;
-        else if (extra > 0) extra--;
+        dm = s1 > 0.0 ? dm / s1 : 0.0;
+        if (extra < 0 && dm <= 1e-13) {
+          const double r = fmin(0.9, fmax(1e-8, dprev > 0.0 ? dm / dprev : 1e-8));
+          const double ang = sqrt(fmax(dm, 1e-18));
+          extra = (int)fmin(30.0, fmax(1.0, ceil(log(1e-13 / ang) / (0.5 * log(r)))));
+        } else if (extra > 0) extra--;
+        dprev = dm;
         s_done = (extra == 0);
       }
       __syncthreads();
-      normalize_cols(W, p, b, sig, true);
-      phase(4);
+      phase(5);
       if (s_done) break;
     }
     const bool converged = s_done;
-    if (!converged) {
+    if (converged) {
+      // Ritz vectors: U = Q U_r  (p x b), sorted by decreasing singular value
+      for (int idx = threadIdx.x; idx < b * b; idx += NT) {
+        const int l = idx % b, j = idx / b;
+        const int cj = order[j];
+        Zg[idx] = S[l + (size_t)b * cj] * jacobi_inv_sigma(sig[cj], sig[order[0]]);
+      }
+      for (int j = threadIdx.x; j < b; j += NT) sprev[j] = sig[order[j]];
+      __syncthreads();
+      blk_gemm_dmma(blk, 1LL, (long long)ldq, p, b, Zg, b, b, Qg, p);  // U = Q U_r  (p x b, compact ld = p)
+      __syncthreads();
+    } else {
       // The block iteration hit its cap (clustered singular values across the block edge).  Exact fallback, rare
-      // and slow on purpose: one-sided Jacobi on ALL n columns of M in global memory (work copy in Mt, whose
-      // transposed copy is no longer needed), then the b leading columns become the block.  Counted in stats[4].
+      // and slow on purpose: one-sided Jacobi on ALL n columns of a work copy of M in global memory, then the b leading
+      // columns become the block.  Counted in stats[4].
       if (threadIdx.x == 0)
         printf("[mpbp] subspace SVD not converged after %d iterations (p=%d n=%d b=%d, s1=%.3e s_k=%.3e): exact Jacobi fallback\n",
                nit, p, n, b, sig[order[0]], sig[order[kchk - 1]]);
       __syncthreads();
-      for (int idx = threadIdx.x; idx < p * n; idx += NT) Mt[idx] = M[idx];
+      for (int idx = threadIdx.x; idx < p * n; idx += NT) Mwork[idx] = M[idx];
       __syncthreads();
-      sw = max(sw, jacobi_cols(Mt, p, n, p, &flag));
-      double* sall = W;                                  // n doubles
-      int* oall = reinterpret_cast<int*>(W + n);          // n ints
-      jacobi_sort(Mt, p, n, p, sall, oall);
-      for (int idx = threadIdx.x; idx < p * b; idx += NT) Qg[idx] = Mt[(idx % p) + (size_t)p * oall[idx / p]];
+      sw = max(sw, jacobi_cols(Mwork, p, n, p, &flag));
+      double* sall = Zg;                              // n doubles
+      int* oall = reinterpret_cast<int*>(Zg + n);      // n ints
+      jacobi_sort(Mwork, p, n, p, sall, oall);
       for (int j = threadIdx.x; j < b; j += NT) sprev[j] = sall[oall[j]];
       __syncthreads();
-      for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
-      for (int j = threadIdx.x; j < b; j += NT) {
-        sig[j] = sprev[j];
-        order[j] = j;
-      }
+      const double smax = sprev[0];
+      for (int idx = threadIdx.x; idx < p * b; idx += NT)
+        Qg[idx] = Mwork[(idx % p) + (size_t)p * oall[idx / p]] * jacobi_inv_sigma(sprev[idx / p], smax);
       __syncthreads();
-      normalize_cols(W, p, b, sig);
-      phase(5);
-    } else {
-      // final un-squared Rayleigh-Ritz refinement: Z = orth(M^T Q), Y = M Z, SVD(Y) -> U, sigma
-      sub_gemm(Mt, n, p, W, b, Zg);
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < n * b; idx += NT) W[idx] = Zg[idx];
-      __syncthreads();
-      sw = max(sw, jacobi_cols(W, n, b, n, &flag));
-      jacobi_sort(W, n, b, n, sig, order);
-      normalize_cols(W, n, b, sig);
-      sub_gemm(M, p, n, W, b, Qg);
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
-      __syncthreads();
-      sw = max(sw, jacobi_cols(W, p, b, p, &flag));
-      jacobi_sort(W, p, b, p, sig, order);
-      normalize_cols(W, p, b, sig);
-      phase(5);
     }
+    // compact copy into shared memory when it fits (lda = p), singular values sorted: order = identity
+    A = Qg;
+    if ((long long)p * b <= jac_doubles) {
+      for (int idx = threadIdx.x; idx < p * b; idx += NT) W[idx] = Qg[idx];
+      A = W;
+    }
+    for (int j = threadIdx.x; j < b; j += NT) {
+      sig[j] = sprev[j];
+      order[j] = j;
+    }
+    __syncthreads();
+    phase(0);
     if (stats && threadIdx.x == 0) {
       atomicAdd(stats + 0, 1.0);
       atomicAdd(stats + 1, (double)nit);
       atomicAdd(stats + 2, (double)b);
       atomicAdd(stats + 3, (double)sw);
       if (!converged) atomicAdd(stats + 4, 1.0);  // hit SUB_MAXIT: the exact Jacobi fallback above produced the result
+      // executed flops of the iteration: two p x n x b GEMMs and two Householder orthonormalisations (4 rows b^2 each)
+      atomicAdd(stats + 6, (double)nit * (4.0 * p * n * b + 4.0 * (p + n) * b * b) + 2.0 * p * b * b);
     }
     if (sw >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
-    A = W;
     ceff = b;
   }
   SvdLeft out;
@@ -679,8 +805,9 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
   const int c = min(p, rn);
   double* sig = smem;
   int* order = reinterpret_cast<int*>(smem + SUB_BMAX);
-  const SvdLeft sv = svd_left_cta(op.M2T, op.R2, op.R2, op.M, op.M + 32768, p, rn, tr, dcap, jac_doubles, smem, &flag, &s_done, red,
-                                  err, stats);
+  // global scratch of the subspace path: the tall sweep-1 matrix op.M is dead during sweep 2 (D^2 X doubles >= what is needed
+  // whenever the subspace path can occur, i.e. min(p, n) > 64)
+  const SvdLeft sv = svd_left_cta(op.M2T, op.R2, op.M, p, rn, tr, dcap, jac_doubles, smem, &flag, &s_done, red, err, stats);
   double* A = sv.A;
   const int ceff = sv.ceff;
   const double nrm2_all = sv.nrm2_all;
@@ -1178,7 +1305,7 @@ __global__ void __launch_bounds__(NT) k_damp(const DampJob* jobs, int L, Trunc t
     }
     __syncthreads();
     const int keep = s_keep;
-    normalize_cols(A, p_rows, c, sig);
+    normalize_cols(A, p_rows, c, p_rows, sig);
     for (int idx = threadIdx.x; idx < dt * keep * P; idx += NT) {
       const int mt = idx % dt, kk = (idx / dt) % keep, p = idx / (dt * keep);
       O[idx] = A[(mt + dt * p) + (size_t)order[kk] * p_rows];

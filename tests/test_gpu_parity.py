@@ -61,7 +61,8 @@ def test_qr_flat_tree_dmma(m, n, H):
 
 
 @pytest.mark.parametrize("p,n,d,decay", [(200, 400, 20, 0.85), (440, 400, 20, 0.9), (80, 400, 20, 0.7), (100, 100, 10, 0.8),
-                                          (60, 30, 10, 0.5), (640, 400, 20, 0.93)])
+                                          (60, 30, 10, 0.5), (640, 400, 20, 0.93), (200, 400, 20, 0.97), (660, 900, 30, 0.9),
+                                          (72, 100, 10, 0.6)])
 def test_truncation_svd_core_vs_numpy(p, n, d, decay):
     """the op-truncation SVD (direct Jacobi / blocked subspace iteration) against LAPACK: what matters is the
     rank-d projection P M, weighted by the singular values"""
