@@ -104,6 +104,11 @@ struct mpbp_state {
   double nstreams = 4;
   int twovar = 0;            // > 0: maxdist of the two-time marginals computed with every belief (option "twovar")
   double* d_tv = nullptr;    // [N][L][L][qmax*qmax]
+  double hub_lane = 1;       // 1: high-degree nodes of a chunk run on their own stream (2: also for tiny chunks, tests)
+  double hub_frac = 0.3;     // share of the chunk's cost the hub lane may take
+  cudaStream_t hub_st = nullptr;
+  cudaEvent_t ev_hub_fork = nullptr, ev_hub_join = nullptr;
+  double tri_merge = 1;      // 1: the TSQR merge skips the zero panels of the stacked triangular chunk factors
   double kron_mma = 1;       // 1: DMMA Kronecker-carry kernel (k_kron_carry_mma), 0: scalar FP64 kernel (k_kron_carry)
   double outlier_split = 0;  // > 0: ops costing more than this multiple of the mean of their launch group run in a
                              // group of their own, TSQR-split, next to the other groups (0 = off; experimental)
@@ -167,6 +172,9 @@ int common_init(mpbp_state* h) {
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
   }
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->hub_st, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_hub_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_hub_join, cudaEventDisableTiming));
   CUDA_OK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   h->max_smem -= 2048;  // head-room for the kernels' static shared memory
   {
@@ -260,6 +268,10 @@ struct Plan {
   std::vector<InitJob> init;
   std::vector<std::vector<OpDesc>> levels;  // ops by level (scratch pointers filled per group)
   std::vector<std::vector<int>> capA, capB;  // bond capacities of the operands per op (1 or dmax)
+  // hub lane: the ops of the few high-degree nodes of the chunk, whose level chains are the critical path; they run on
+  // their own stream, concurrently with the rounds of the bulk
+  std::vector<std::vector<OpDesc>> hlevels;
+  std::vector<std::vector<int>> hcapA, hcapB;
   std::vector<FinJob> fin;
   std::vector<DampJob> damp;  // one per FinJob when damp > 0 (same order)
   std::vector<BelJob> bel;
@@ -413,13 +425,26 @@ std::vector<int> plan_level_offsets(const mpbp_state* h, const std::vector<int64
   return off;
 }
 
-int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, Plan& P) {
+int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vector<char>& hub, int rb, int wb, Plan& P) {
   const int L = h->L, d = h->dmax;
   bool ok = true;
-  const std::vector<int> lev_off = plan_level_offsets(h, nodes);
+  // level offsets are planned per lane (each lane balances its own rounds)
+  std::vector<int> lev_off(nodes.size(), 0);
+  {
+    std::vector<int64_t> nb, nh;
+    std::vector<size_t> ib, ih;
+    for (size_t k = 0; k < nodes.size(); ++k) {
+      if (hub[k]) { nh.push_back(nodes[k]); ih.push_back(k); }
+      else { nb.push_back(nodes[k]); ib.push_back(k); }
+    }
+    const std::vector<int> ob = plan_level_offsets(h, nb), oh = plan_level_offsets(h, nh);
+    for (size_t k = 0; k < ib.size(); ++k) lev_off[ib[k]] = ob[k];
+    for (size_t k = 0; k < ih.size(); ++k) lev_off[ih[k]] = oh[k];
+  }
   for (size_t inode = 0; inode < nodes.size(); ++inode) {
     const int64_t i = nodes[inode];
     const int loff = lev_off[inode];
+    const bool in_hub = hub[inode] != 0;
     const int ci = h->class_of_node[i];
     if (ci < 0 || ci >= (int)h->classes.size()) return fail("node %lld has no factor class", (long long)i);
     const NodeClass& c = h->classes[ci];
@@ -564,14 +589,17 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb,
       op.o = out;
       op.pyy = c.d_pyy + it->second.first;
       op.pyy_tstride = (int)it->second.second;
-      if ((int)P.levels.size() <= level) {
-        P.levels.resize(level + 1);
-        P.capA.resize(level + 1);
-        P.capB.resize(level + 1);
+      auto& LV = in_hub ? P.hlevels : P.levels;
+      auto& CA = in_hub ? P.hcapA : P.capA;
+      auto& CB = in_hub ? P.hcapB : P.capB;
+      if ((int)LV.size() <= level) {
+        LV.resize(level + 1);
+        CA.resize(level + 1);
+        CB.resize(level + 1);
       }
-      P.levels[level].push_back(op);
-      P.capA[level].push_back(ca);
-      P.capB[level].push_back(cb);
+      LV[level].push_back(op);
+      CA[level].push_back(ca);
+      CB[level].push_back(cb);
       return 0;
     };
     std::vector<TTRef> dest(z);
@@ -695,6 +723,7 @@ void ev_flush(mpbp_state* h) {
   if (!h->profile || h->ev_used == 0) return;
   cudaStreamSynchronize(h->st);
   for (int k = 0; k < 3; ++k) cudaStreamSynchronize(h->aux[k]);
+  cudaStreamSynchronize(h->hub_st);
   for (size_t k = 0; k < h->ev_used; ++k) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_pool[k].first, h->ev_pool[k].second);
@@ -784,9 +813,9 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
       else k_qr_ft<16><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
       h->n_launch++;
       if (nsplit > 1) {
-        if (g.bigH == 64) k_qr_ft_merge<64><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
-        else if (g.bigH == 32) k_qr_ft_merge<32><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
-        else k_qr_ft_merge<16><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+        if (g.bigH == 64) k_qr_ft_merge<64><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge);
+        else if (g.bigH == 32) k_qr_ft_merge<32><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge);
+        else k_qr_ft_merge<16><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge);
         h->n_launch++;
       }
       ev_end(h, g.st);
@@ -824,11 +853,65 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
   return 0;
 }
 
+// scratch of one heavy op from the arena (false: does not fit)
+bool alloc_op_scratch(mpbp_state* h, OpDesc& op, int ca, int cb) {
+  const int L = h->L, d = h->dmax;
+  const int X = op.nyo * op.q;
+  if (h->arena.used + op_scratch_bytes(h, ca, cb, X) > h->arena.cap) return false;
+  const size_t D = (size_t)ca * cb;
+  const size_t mrows = D * X;
+  op.r = (int*)h->arena.take(4 * (L + 1));
+  op.Lstride = (long long)(D * D);
+  op.Lbuf = (double*)h->arena.take(8 * (size_t)L * D * D);
+  op.M = (double*)h->arena.take(8 * mrows * D);
+  op.Ms = (double*)h->arena.take(8 * (size_t)QR_NSPLIT_MAX * D * D);
+  op.G = (double*)h->arena.take(8 * (size_t)d * D * X);
+  op.M2T = (double*)h->arena.take(8 * D * (size_t)d * X);
+  op.R2 = (double*)h->arena.take(8 * (size_t)(d * X) * (d * X));
+  op.Pc[0] = (double*)h->arena.take(8 * (size_t)d * D);
+  op.Pc[1] = (double*)h->arena.take(8 * (size_t)d * D);
+  return op.r && op.Lbuf && op.M && op.Ms && op.G && op.M2T && op.R2 && op.Pc[0] && op.Pc[1];
+}
+
+// Which nodes of a chunk go to the hub lane: the highest degrees, as long as they hold at most hub_frac of the chunk's
+// cost.  Their cavity chains (z sequential levels, each 2L sites deep, the heaviest ops of the graph) are the critical
+// path of a step; run next to the bulk instead of inside its rounds they no longer stretch every round.
+std::vector<char> pick_hub_nodes(const mpbp_state* h, const std::vector<int64_t>& nodes) {
+  std::vector<char> hub(nodes.size(), 0);
+  if (h->hub_lane <= 0 || (nodes.size() < 64 && h->hub_lane < 2) || h->inf_k > 0) return hub;
+  std::map<int, double> cost_by_z;
+  std::vector<int> zs(nodes.size(), -1);
+  double total = 0.0;
+  for (size_t k = 0; k < nodes.size(); ++k) {
+    const int ci = h->class_of_node[nodes[k]];
+    if (ci < 0 || ci >= (int)h->classes.size() || h->classes[ci].generic) continue;
+    const NodeClass& c = h->classes[ci];
+    double w = 0.0;
+    for (double v : node_level_cost(c, h->dmax)) w += v;
+    zs[k] = c.z;
+    cost_by_z[c.z] += w;
+    total += w;
+  }
+  int zhub = 1 << 30;
+  double acc = 0.0;
+  for (auto it = cost_by_z.rbegin(); it != cost_by_z.rend(); ++it) {
+    if (it->first < 4 || acc + it->second > h->hub_frac * total) break;
+    acc += it->second;
+    zhub = it->first;
+  }
+  size_t nh = 0;
+  for (size_t k = 0; k < nodes.size(); ++k)
+    if (zs[k] >= zhub) { hub[k] = 1; ++nh; }
+  if (nh == nodes.size()) std::fill(hub.begin(), hub.end(), 0);
+  return hub;
+}
+
 int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, const Trunc& tr) {
   const int L = h->L, d = h->dmax;
   h->arena.used = 0;
   Plan P;
-  if (build_plan(h, nodes, rb, wb, P)) return 1;
+  const std::vector<char> hub = pick_hub_nodes(h, nodes);
+  if (build_plan(h, nodes, hub, rb, wb, P)) return 1;
   cudaStream_t st = h->st;
   BtJob* d_bt;
   InitJob* d_init;
@@ -854,8 +937,88 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     k_init_tt<<<(unsigned)P.init.size(), 64, 0, st>>>(d_init, (int)P.init.size(), L);
     h->n_launch++;
   }
-  // ---- cavity levels ----
-  const size_t persistent = h->arena.used;
+  // ---- hub lane: every level of the high-degree nodes, enqueued back to back on its own stream (no host sync: the
+  // scratch region below is reused level after level in stream order) ----
+  size_t persistent = h->arena.used;
+  bool hub_running = false;
+  if (!P.hlevels.empty()) {
+    // scratch region = the largest level; if it would take more than 40 % of what is left, run the hubs with the bulk
+    size_t need = 0;
+    for (size_t lev = 1; lev < P.hlevels.size(); ++lev) {
+      size_t nl = sizeof(OpDesc) * P.hlevels[lev].size() + 4096;
+      for (size_t k = 0; k < P.hlevels[lev].size(); ++k)
+        nl += op_scratch_bytes(h, P.hcapA[lev][k], P.hcapB[lev][k], P.hlevels[lev][k].nyo * P.hlevels[lev][k].q) + 4096;
+      need = std::max(need, nl);
+    }
+    if (need > (size_t)(0.4 * (double)(h->arena.cap - persistent))) {
+      // merge the lanes again (level by level; the result does not depend on the lane)
+      for (size_t lev = 1; lev < P.hlevels.size(); ++lev) {
+        if (P.levels.size() <= lev) { P.levels.resize(lev + 1); P.capA.resize(lev + 1); P.capB.resize(lev + 1); }
+        for (size_t k = 0; k < P.hlevels[lev].size(); ++k) {
+          P.levels[lev].push_back(P.hlevels[lev][k]);
+          P.capA[lev].push_back(P.hcapA[lev][k]);
+          P.capB[lev].push_back(P.hcapB[lev][k]);
+        }
+      }
+      P.hlevels.clear();
+    } else {
+      // in profile mode the lane runs inline on the main stream so that per-family event times stay exclusive
+      cudaStream_t hs = h->profile ? st : h->hub_st;
+      if (hs != st) {
+        CUDA_OK(cudaEventRecord(h->ev_hub_fork, st));
+        CUDA_OK(cudaStreamWaitEvent(hs, h->ev_hub_fork, 0));
+      }
+      const size_t hub_lo = persistent;
+      for (size_t lev = 1; lev < P.hlevels.size(); ++lev) {
+        auto& ops = P.hlevels[lev];
+        if (ops.empty()) continue;
+        h->arena.used = hub_lo;
+        OpDesc* d_ops = (OpDesc*)h->arena.take(sizeof(OpDesc) * ops.size());
+        bool fit = d_ops != nullptr;
+        GroupRun gr;
+        memset(&gr, 0, sizeof gr);
+        gr.nops = (int)ops.size(); gr.maxD = 1; gr.maxX = 1; gr.maxNy = 1; gr.maxq = 1; gr.maxNyS = 1;
+        gr.st = hs;
+        // heaviest first (LPT), as in the bulk launches
+        std::vector<size_t> idx(ops.size());
+        for (size_t k = 0; k < idx.size(); ++k) idx[k] = k;
+        auto cost = [&](size_t k) { return (double)P.hcapA[lev][k] * P.hcapB[lev][k] * ops[k].nyo * ops[k].q; };
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+        std::vector<OpDesc> sorted(ops.size());
+        for (size_t k = 0; k < idx.size() && fit; ++k) {
+          OpDesc op = ops[idx[k]];
+          const int ca = P.hcapA[lev][idx[k]], cb = P.hcapB[lev][idx[k]];
+          fit = alloc_op_scratch(h, op, ca, cb);
+          sorted[k] = op;
+          gr.maxD = std::max(gr.maxD, ca * cb);
+          gr.maxX = std::max(gr.maxX, op.nyo * op.q);
+          gr.maxNy = std::max(gr.maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
+          gr.maxq = std::max(gr.maxq, op.q);
+          gr.maxNyS = std::max(gr.maxNyS, std::min(op.ny1, op.ny2));
+        }
+        if (!fit) return fail("arena exhausted in the hub lane (internal sizing error)");
+        CUDA_OK(cudaMemcpyAsync(d_ops, sorted.data(), sizeof(OpDesc) * sorted.size(), cudaMemcpyHostToDevice, hs));
+        gr.d_ops = d_ops;
+        gr.nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(gr.nops, 1))));
+        std::vector<GroupRun> one(1, gr);
+        if (run_op_groups(h, one, tr)) {
+          cudaStreamSynchronize(hs);
+          return 1;
+        }
+        h->n_ops += gr.nops;
+      }
+      persistent = hub_lo + need;
+      h->arena.used = persistent;
+      if (hs != st) {
+        CUDA_OK(cudaEventRecord(h->ev_hub_join, hs));
+        hub_running = true;
+      } else {
+        CUDA_OK(cudaStreamSynchronize(st));
+        ev_flush(h);
+      }
+    }
+  }
+  // ---- cavity levels of the bulk ----
   for (size_t lev = 1; lev < P.levels.size(); ++lev) {
     auto& ops = P.levels[lev];
     {
@@ -881,23 +1044,7 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
       if (!d_ops) return fail("arena exhausted (op descriptors)");
       while (i1 < ops.size() && (double)(i1 - i0) < h->max_group_ops) {
         OpDesc& op = ops[i1];
-        const int ca = P.capA[lev][i1], cb = P.capB[lev][i1];
-        const int X = op.nyo * op.q;
-        const size_t need = op_scratch_bytes(h, ca, cb, X);
-        if (h->arena.used + need > h->arena.cap) break;
-        const size_t D = (size_t)ca * cb;
-        const size_t mrows = D * X;
-        op.r = (int*)h->arena.take(4 * (L + 1));
-        op.Lstride = (long long)(D * D);
-        op.Lbuf = (double*)h->arena.take(8 * (size_t)L * D * D);
-        op.M = (double*)h->arena.take(8 * mrows * D);
-        op.Ms = (double*)h->arena.take(8 * (size_t)QR_NSPLIT_MAX * D * D);
-        op.G = (double*)h->arena.take(8 * (size_t)d * D * X);
-        op.M2T = (double*)h->arena.take(8 * D * (size_t)d * X);
-        op.R2 = (double*)h->arena.take(8 * (size_t)(d * X) * (d * X));
-        op.Pc[0] = (double*)h->arena.take(8 * (size_t)d * D);
-        op.Pc[1] = (double*)h->arena.take(8 * (size_t)d * D);
-        if (!op.r || !op.Lbuf || !op.M || !op.Ms || !op.G || !op.M2T || !op.R2 || !op.Pc[0] || !op.Pc[1]) break;
+        if (!alloc_op_scratch(h, op, P.capA[lev][i1], P.capB[lev][i1])) break;
         ++i1;
       }
       if (i1 == i0) return fail("arena too small for a single op (need %.1f MB)", op_scratch_bytes(h, d, d, ops[i0].nyo * ops[i0].q) / 1e6);
@@ -966,6 +1113,7 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     }
   }
   h->arena.used = persistent;
+  if (hub_running) CUDA_OK(cudaStreamWaitEvent(st, h->ev_hub_join, 0));
   // ---- outgoing messages, beliefs, free energy ----
   {
     int qm = h->qmax;
@@ -1144,6 +1292,9 @@ int mpbp_destroy(mpbp_handle h) {
   if (h->own_stream) cudaStreamDestroy(h->st);
   for (int k = 0; k < 3; ++k) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->hub_st) cudaStreamDestroy(h->hub_st);
+  if (h->ev_hub_fork) cudaEventDestroy(h->ev_hub_fork);
+  if (h->ev_hub_join) cudaEventDestroy(h->ev_hub_join);
   delete h;
   return 0;
 }
@@ -1734,6 +1885,9 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "level_balance") h->level_balance = value;
   else if (n == "outlier_split") h->outlier_split = value;
   else if (n == "kron_mma") h->kron_mma = value;
+  else if (n == "hub_lane") h->hub_lane = value;
+  else if (n == "tri_merge") h->tri_merge = value;
+  else if (n == "hub_frac") h->hub_frac = value;
   else if (n == "twovar") {
     // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
     h->twovar = value > 0 ? (int)std::min<double>(value, h->L) : 0;

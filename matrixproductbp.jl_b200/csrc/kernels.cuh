@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* o
   }
 }
 template <int H>
-__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft_merge(const OpDesc* ops, int t, int nsplit, double* flops) {
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft_merge(const OpDesc* ops, int t, int nsplit, double* flops, int tri) {
   extern __shared__ double smem[];
   const OpDesc& op = ops[blockIdx.x];
   const int Dl = op.a.bonds[t] * op.b.bonds[t];
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft_merge(const OpD
   ft_split(m, Dl, nsplit, nch, ch_rows);
   if (nch == 1) return;
   if (flops && threadIdx.x == 0) atomicAdd(flops + 16, qr_flops((double)nch * Dl, Dl));
-  qr_ft_cta<H>(op.Ms, nch * Dl, Dl, Dl, op.Lbuf + (size_t)t * op.Lstride, Dl, true, smem);
+  qr_ft_cta<H>(op.Ms, nch * Dl, Dl, Dl, op.Lbuf + (size_t)t * op.Lstride, Dl, true, smem, /*tri_n=*/tri ? Dl : 0);
   if (threadIdx.x == 0) op.r[t] = Dl;
 }
 

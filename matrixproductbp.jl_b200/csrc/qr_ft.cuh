@@ -238,9 +238,12 @@ __device__ __forceinline__ void ft_update_slab(double* Ablk, const int ld, const
 // A: m x n row-major (lda), read-only.  R: n x n row-major (ldr) in global memory, fully overwritten with the
 // upper-triangular factor (R^T R = A^T A).  For m < n use the matrix itself as the factor instead (callers do).
 // If normalize: R is divided by its max-abs.
+// tri_n > 0: A is a stack of m / tri_n upper-triangular tri_n x n blocks (the chunk factors of a TSQR split): the first
+// triangle is copied into R instead of being factored, and a row block that starts at local row r of its triangle skips
+// the panels left of column r (they hold only zeros there) -- the merge then costs ~0.45 of a dense stack.
 template <int H>
 __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n, const int lda, double* __restrict__ R,
-                          const int ldr, const bool normalize, double* smem) {
+                          const int ldr, const bool normalize, double* smem, const int tri_n = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n8 = (n + 7) & ~7;
   const int ld = ft_ld(n);
@@ -249,20 +252,35 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
   double* Ablk = smem;                       // H x ld
   double* VT0 = Ablk + (size_t)H * ld;       // 2 x (V^T 8 x LDV, T 8x8)
   double* Ws = VT0 + 2 * VT_SZ + warp * 72;  // per-warp 8x8 scratch (ld 9)
-  for (int idx = tid; idx < n * n; idx += NT) R[(size_t)(idx / n) * ldr + (idx % n)] = 0.0;
+  if (tri_n > 0) {
+    for (int idx = tid; idx < n * n; idx += NT) {
+      const int i = idx / n, c = idx % n;
+      R[(size_t)i * ldr + c] = (c >= i && i < tri_n) ? A[(size_t)i * lda + c] : 0.0;
+    }
+  } else {
+    for (int idx = tid; idx < n * n; idx += NT) R[(size_t)(idx / n) * ldr + (idx % n)] = 0.0;
+  }
   const int g = lane >> 2, q4 = lane & 3;  // DMMA fragment coordinates
   const int npanel = n8 / FT_B;
-  for (int row0 = 0; row0 < m; row0 += H) {
+  // row blocks: dense -> [row0, row0+H) ; triangle stack -> blocks never straddle two triangles
+  const int seg_rows = tri_n > 0 ? tri_n : m;
+  const int nseg = tri_n > 0 ? m / tri_n : 1;
+  const int blocks_per_seg = (seg_rows + H - 1) / H;
+  for (int blk = (tri_n > 0 ? blocks_per_seg : 0); blk < nseg * blocks_per_seg; ++blk) {
+    const int seg = blk / blocks_per_seg, lrow0 = (blk % blocks_per_seg) * H;
+    const int row0 = seg * seg_rows + lrow0;
+    const int row_end = seg * seg_rows + seg_rows;      // rows of this block stay below row_end
+    const int jp0 = tri_n > 0 ? min(lrow0 / FT_B, npanel - 1) : 0;  // first panel with a non-zero column in this block
     __syncthreads();
     // ---- stage the row block (zero padded) ----
     for (int idx = tid; idx < H * n8; idx += NT) {
       const int i = idx / n8, c = idx % n8;
       const int gi = row0 + i;
-      Ablk[(size_t)i * ld + (c ^ ft_sw(i))] = (gi < m && c < n) ? A[(size_t)gi * lda + c] : 0.0;
+      Ablk[(size_t)i * ld + (c ^ ft_sw(i))] = (gi < row_end && gi < m && c < n) ? A[(size_t)gi * lda + c] : 0.0;
     }
     __syncthreads();
-    if (warp == 0) ft_panel<H>(Ablk, ld, 0, n, R, ldr, VT0, VT0 + FT_B * LDV);
-    for (int jp = 0; jp < npanel; ++jp) {
+    if (warp == 0) ft_panel<H>(Ablk, ld, jp0 * FT_B, n, R, ldr, VT0 + (jp0 & 1) * VT_SZ, VT0 + (jp0 & 1) * VT_SZ + FT_B * LDV);
+    for (int jp = jp0; jp < npanel; ++jp) {
       const int j0 = jp * FT_B;
       double* Vt = VT0 + (jp & 1) * VT_SZ;
       double* Tm = Vt + FT_B * LDV;
