@@ -279,9 +279,25 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
       }
     atomicAdd(flops, 2.0 * rn * ((double)blS * brS * brF * nyS + (double)blF * brF * blS * npairs));
   }
-  for (int i = threadIdx.x; i < RB * DrP; i += NT) {
-    const int u = i / DrP, e = i % DrP;
-    Lc[i] = (u < nb && e < Dr) ? (Lm ? Lm[e + (size_t)Dr * (rr0 + u)] : 1.0) : 0.0;
+  // stage the RB columns of L_{t+1}: one TMA bulk copy per column (Dr contiguous doubles) when 16-byte aligned
+  __shared__ uint64_t kc_mbar;
+  const bool bulk = Lm != nullptr && (Dr & 1) == 0 && aligned16(Lm) && aligned16(Lc);
+  if (bulk) {
+    if (threadIdx.x == 0) mbar_init(&kc_mbar, 1);
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(&kc_mbar, (uint32_t)(nb * Dr * 8));
+      __syncwarp();
+      for (int u = lane; u < nb; u += 32) bulk_g2s(Lc + (size_t)u * DrP, Lm + (size_t)Dr * (rr0 + u), (uint32_t)(Dr * 8), &kc_mbar);
+    }
+    for (int i = threadIdx.x; i < nb * (DrP - Dr); i += NT) Lc[(size_t)(i / (DrP - Dr)) * DrP + Dr + i % (DrP - Dr)] = 0.0;
+    for (int i = threadIdx.x; i < (RB - nb) * DrP; i += NT) Lc[(size_t)nb * DrP + i] = 0.0;
+    mbar_wait(&kc_mbar, 0);
+  } else {
+    for (int i = threadIdx.x; i < RB * DrP; i += NT) {
+      const int u = i / DrP, e = i % DrP;
+      Lc[i] = (u < nb && e < Dr) ? (Lm ? Lm[e + (size_t)Dr * (rr0 + u)] : 1.0) : 0.0;
+    }
   }
   __syncthreads();
   // ---------------- stage 1 ----------------
@@ -679,6 +695,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
     phase(2);
     int sw = 0;
     int extra = -1;
+    __shared__ int s_extra;
     double dprev = 0.0;
     const int kchk = min(b, kwant);
     int nit = 0;
@@ -695,9 +712,16 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       phase(3);
       hh_orth(blk, p, b, ldq, S, scal);  // Y = Q R, R -> S (b x b)
       phase(4);
+      ++nit;
+      if (extra > 1) {
+        // blind iterations after convergence was detected (their count came from the contraction rate): no Ritz step
+        if (threadIdx.x == 0) s_done = 0;
+        --extra;
+        __syncthreads();
+        continue;
+      }
       sw = max(sw, jacobi_cols(S, b, b, b, &flag));  // R V = U_r Sigma: the columns of S become U_r Sigma
       jacobi_sort(S, b, b, b, sig, order);
-      ++nit;
       if (threadIdx.x == 0) {
         // Ritz VALUES converge like angle^2: once they are stationary to 1e-13 sigma_1 the subspace angle is still up to
         // ~sqrt(1e-13).  The contraction of the last step (value error ratio r = rho_angle^2) says how many more
@@ -710,15 +734,18 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
           sprev[i] = s;
         }
         dm = s1 > 0.0 ? dm / s1 : 0.0;
-        if (extra < 0 && dm <= 1e-13) {
+        int ex = extra;
+        if (ex < 0 && dm <= 1e-13) {
           const double r = fmin(0.9, fmax(1e-8, dprev > 0.0 ? dm / dprev : 1e-8));
           const double ang = sqrt(fmax(dm, 1e-18));
-          extra = (int)fmin(30.0, fmax(1.0, ceil(log(1e-13 / ang) / (0.5 * log(r)))));
-        } else if (extra > 0) extra--;
+          ex = (int)fmin(30.0, fmax(1.0, ceil(log(1e-13 / ang) / (0.5 * log(r)))));
+        } else if (ex > 0) ex--;
         dprev = dm;
-        s_done = (extra == 0);
+        s_extra = ex;
+        s_done = (ex == 0);
       }
       __syncthreads();
+      extra = s_extra;  // every thread follows the same schedule
       phase(5);
       if (s_done) break;
     }

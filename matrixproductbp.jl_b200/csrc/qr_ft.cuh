@@ -20,6 +20,7 @@
 // compact-WY factor T follows the LAPACK dlarft recurrence.
 #pragma once
 #include "common.cuh"
+#include "bulk_copy.cuh"
 
 namespace mpbp {
 
@@ -262,6 +263,11 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
   }
   const int g = lane >> 2, q4 = lane & 3;  // DMMA fragment coordinates
   const int npanel = n8 / FT_B;
+  // TMA bulk staging needs 16-byte aligned, 16-byte-multiple rows (even n and lda); odd bonds use the plain loop
+  __shared__ uint64_t ft_mbar;
+  const bool bulk = ((n & 1) == 0) && ((lda & 1) == 0) && aligned16(A) && aligned16(smem);
+  uint32_t phase = 0;
+  if (bulk && tid == 0) mbar_init(&ft_mbar, 1);
   // row blocks: dense -> [row0, row0+H) ; triangle stack -> blocks never straddle two triangles
   const int seg_rows = tri_n > 0 ? tri_n : m;
   const int nseg = tri_n > 0 ? m / tri_n : 1;
@@ -273,10 +279,39 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
     const int jp0 = tri_n > 0 ? min(lrow0 / FT_B, npanel - 1) : 0;  // first panel with a non-zero column in this block
     __syncthreads();
     // ---- stage the row block (zero padded) ----
-    for (int idx = tid; idx < H * n8; idx += NT) {
-      const int i = idx / n8, c = idx % n8;
-      const int gi = row0 + i;
-      Ablk[(size_t)i * ld + (c ^ ft_sw(i))] = (gi < row_end && gi < m && c < n) ? A[(size_t)gi * lda + c] : 0.0;
+    if (bulk) {
+      // one TMA bulk copy per row (n contiguous doubles), completion on the mbarrier; the other threads zero the padding
+      const int vrows = min(H, min(row_end, m) - row0);
+      if (warp == 0) {
+        if (lane == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&ft_mbar, (uint32_t)(vrows * n * 8));
+        }
+        __syncwarp();
+        for (int i = lane; i < vrows; i += 32) bulk_g2s(Ablk + (size_t)i * ld, A + (size_t)(row0 + i) * lda, (uint32_t)(n * 8), &ft_mbar);
+      }
+      const int npad = n8 - n;
+      for (int idx = tid; idx < vrows * npad; idx += NT) Ablk[(size_t)(idx / npad) * ld + n + idx % npad] = 0.0;
+      for (int idx = tid; idx < (H - vrows) * n8; idx += NT) Ablk[(size_t)(vrows + idx / n8) * ld + idx % n8] = 0.0;
+      mbar_wait(&ft_mbar, phase);
+      phase ^= 1;
+      __syncthreads();
+      // swizzle in place: rows with bit 1 set swap the two halves of every 8-column group (c -> c ^ 4)
+      const int ng = n8 >> 3;
+      for (int idx = tid; idx < (H / 2) * ng * 4; idx += NT) {
+        const int e = idx & 3, gq = (idx >> 2) % ng, ih = (idx >> 2) / ng;
+        const int i = ((ih >> 1) << 2) + 2 + (ih & 1);
+        double* p = Ablk + (size_t)i * ld + 8 * gq + e;
+        const double t0 = p[0];
+        p[0] = p[4];
+        p[4] = t0;
+      }
+    } else {
+      for (int idx = tid; idx < H * n8; idx += NT) {
+        const int i = idx / n8, c = idx % n8;
+        const int gi = row0 + i;
+        Ablk[(size_t)i * ld + (c ^ ft_sw(i))] = (gi < row_end && gi < m && c < n) ? A[(size_t)gi * lda + c] : 0.0;
+      }
     }
     __syncthreads();
     if (warp == 0) ft_panel<H>(Ablk, ld, jp0 * FT_B, n, R, ldr, VT0 + (jp0 & 1) * VT_SZ, VT0 + (jp0 & 1) * VT_SZ + FT_B * LDV);
@@ -331,6 +366,7 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
     }
   }
   __syncthreads();
+  if (bulk && tid == 0) mbar_inval(&ft_mbar);
   if (normalize) {
     __shared__ double redn[NW + 1];
     double mx = 0.0;

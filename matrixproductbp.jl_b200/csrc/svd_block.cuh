@@ -89,6 +89,77 @@ __device__ inline void blk_gemm_dmma(const double* __restrict__ A, const long lo
   }
 }
 
+// 8 simultaneous warp-wide sums: v[j] per lane -> every lane holds all 8 totals (transpose-reduce: 9 + 8 shuffles
+// instead of 40)
+__device__ __forceinline__ void warp_reduce8(double (&v)[8]) {
+  const int lane = threadIdx.x & 31;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  double w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = b3 ? w4[i] : w4[i + 2], keep = b3 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  double t;
+  {
+    const double send = b2 ? w2[0] : w2[1], keep = b2 ? w2[1] : w2[0];
+    t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = __shfl_sync(0xffffffffu, t, (((c >> 2) & 1) << 4) | (((c >> 1) & 1) << 3) | ((c & 1) << 2));
+}
+
+// one Householder step on the warp's own trailing columns c = c0, c0+NW, ... (< b), all at once: the 8 dot products
+// share every load of the reflector column and their reductions overlap (the step is latency-bound otherwise).
+// mode 0 (forward): w = tau (cc[k] + sc x.cc),  cc[k] -= w ;   mode 1 (backward): w = tau sc x.cc,  cc[k] = -w.
+__device__ __forceinline__ void hh_apply_cols(double* W, const int rows, const int b, const int ld, const int k, const double tau,
+                                              const double sc, const int mode) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* col = W + (size_t)k * ld;
+  const int c0 = k + 1 + warp;
+  if (c0 >= b) return;
+  const int nc = min(8, (b - c0 + NW - 1) / NW);
+  double* cp[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cp[j] = W + (size_t)(c0 + NW * min(j, nc - 1)) * ld;
+  double acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+  for (int i = k + 1 + lane; i < rows; i += 32) {
+    const double x = col[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nc) acc[j] += x * cp[j][i];
+  }
+  warp_reduce8(acc);
+  double ws[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double w = mode == 0 ? tau * (cp[j][k] + sc * acc[j]) : tau * sc * acc[j];
+    ws[j] = w * sc;
+    acc[j] = w;
+  }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nc) cp[j][k] = mode == 0 ? cp[j][k] - acc[j] : -acc[j];
+  }
+  for (int i = k + 1 + lane; i < rows; i += 32) {
+    const double x = col[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nc) cp[j][i] -= ws[j] * x;
+  }
+}
+
 // In-place Householder QR with explicit thin Q of the rows x b block W (column-major, ld), rows >= b, b <= 64:
 // on return the columns of W are orthonormal (to machine precision, whatever the conditioning of the input) and, if
 // Rout != nullptr, Rout (b x b column-major, ld = b) holds the triangular factor (zeros below the diagonal).
@@ -103,12 +174,15 @@ __device__ inline void hh_orth(double* W, const int rows, const int b, const int
   __syncthreads();
   for (int k = 0; k < b; ++k) {
     const double* col = W + (size_t)k * ld;
-    double s = 0.0;
-    for (int i = k + 1 + lane; i < rows; i += 32) {
-      const double x = col[i];
-      s += x * x;
+    double s0 = 0.0, s1 = 0.0;
+    int i = k + 1 + lane;
+    for (; i + 32 < rows; i += 64) {
+      const double x = col[i], y = col[i + 32];
+      s0 += x * x;
+      s1 += y * y;
     }
-    const double sig2 = warp_sum(s);
+    if (i < rows) s0 += col[i] * col[i];
+    const double sig2 = warp_sum(s0 + s1);
     const double alpha = col[k];
     double tau = 0.0, sc = 0.0, beta = alpha;
     if (sig2 > 0.0) {
@@ -120,22 +194,7 @@ __device__ inline void hh_orth(double* W, const int rows, const int b, const int
       tau = alpha >= 0.0 ? u * rs : -u * rs;
       sc = 1.0 / u;
     }
-    for (int c = k + 1 + warp; c < b; c += NW) {
-      double* cc = W + (size_t)c * ld;
-      double d0 = 0.0, d1 = 0.0;
-      int i = k + 1 + lane;
-      for (; i + 32 < rows; i += 64) {
-        d0 += col[i] * cc[i];
-        d1 += col[i + 32] * cc[i + 32];
-      }
-      if (i < rows) d0 += col[i] * cc[i];
-      const double dot = warp_sum(d0 + d1);
-      const double w = tau * (cc[k] + sc * dot);
-      const double ws = w * sc;
-      __syncwarp();
-      if (lane == 0) cc[k] -= w;
-      for (int i2 = k + 1 + lane; i2 < rows; i2 += 32) cc[i2] -= ws * col[i2];
-    }
+    hh_apply_cols(W, rows, b, ld, k, tau, sc, 0);
     if (warp == (k & (NW - 1)) && lane == 0) {
       s_tau[k] = tau;
       s_sc[k] = sc;
@@ -150,25 +209,11 @@ __device__ inline void hh_orth(double* W, const int rows, const int b, const int
     }
     __syncthreads();
   }
-  // Q = H_0 ... H_{b-1} [I; 0], accumulated backwards in place (column k holds x with v = [1; sc*x] until its turn)
+  // Q = H_0 ... H_{b-1} [I; 0], accumulated backwards in place (column k holds x with v = [1; sc*x] until its turn;
+  // rows <= k of the columns c > k are zero at that point: their stale R entries are never read)
   for (int k = b - 1; k >= 0; --k) {
-    const double* col = W + (size_t)k * ld;
     const double tau = s_tau[k], sc = s_sc[k];
-    for (int c = k + 1 + warp; c < b; c += NW) {
-      double* cc = W + (size_t)c * ld;  // rows <= k of this column are zero at this point (its stale R entries are not read)
-      double d0 = 0.0, d1 = 0.0;
-      int i = k + 1 + lane;
-      for (; i + 32 < rows; i += 64) {
-        d0 += col[i] * cc[i];
-        d1 += col[i + 32] * cc[i + 32];
-      }
-      if (i < rows) d0 += col[i] * cc[i];
-      const double w = tau * sc * warp_sum(d0 + d1);
-      const double ws = w * sc;
-      __syncwarp();
-      if (lane == 0) cc[k] = -w;
-      for (int i2 = k + 1 + lane; i2 < rows; i2 += 32) cc[i2] -= ws * col[i2];
-    }
+    hh_apply_cols(W, rows, b, ld, k, tau, sc, 1);
     __syncthreads();
     double* ck = W + (size_t)k * ld;
     const double ts = tau * sc;
