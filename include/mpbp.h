@@ -46,6 +46,11 @@ int mpbp_create(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* c
 /* InfiniteRegularGraph(k) / mpbp_infinite_graph, src/infinite_graph.jl:8-35: one node, one stored message
  * that plays the role of all k incoming ones. */
 int mpbp_create_infinite(int k, int T, int q, int dmax, int device, mpbp_handle* out);
+/* InfiniteBipartiteRegularGraph((kA, kB)) (src/infinite_graph.jl:62-122): node 0 = class A (degree kA, qA states), node 1 =
+ * class B (degree kB, qB states); edge 0 = message A -> B, edge 1 = message B -> A (reverse of each other).  Everything
+ * else (factor classes, phi, psi per edge, iterate, read-outs) works as on a 2-node graph; the Bethe free energy of the
+ * infinite graph is (f[0]*kB + f[1]*kA)/(kA+kB) (src/infinite_graph.jl:120-122, host side). */
+int mpbp_create_infinite_bipartite(int kA, int kB, int T, int qA, int qB, int dmax, int device, mpbp_handle* out);
 
 int mpbp_destroy(mpbp_handle h);
 

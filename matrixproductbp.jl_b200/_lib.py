@@ -18,6 +18,7 @@ SIGNATURES = {
     "mpbp_version": (C.c_int, []),
     "mpbp_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mpbp_create_infinite": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mpbp_create_infinite_bipartite": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mpbp_destroy": (C.c_int, [C.c_void_p]),
     "mpbp_add_node_class": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p, c_dp, C.c_int, c_i32p, c_i32p, c_dp, c_dp, c_dp, c_dp, c_i32p]),
     "mpbp_set_node_classes": (C.c_int, [C.c_void_p, c_i32p]),

@@ -22,7 +22,7 @@ from .truncations import SVDTrunc, TruncBond, TruncBondMax, TruncBondThresh, Tru
 __all__ = [
     "BPFactor", "RecursiveBPFactor", "HomogeneousGlauberFactor", "PMJGlauberFactor", "IntegerGlauberFactor",
     "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
-    "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
+    "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "InfiniteBipartiteRegularGraph", "mpbp_infinite_bipartite_graph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
     "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_correlations", "pair_beliefs", "bethe_free_energy", "means",
     "reset_messages_", "glauber_factors", "MPBPError", "onesample", "draw_node_observations_",
 ]
@@ -98,6 +98,25 @@ class InfiniteRegularGraph:
 
     def degree(self, i):
         return self.k
+
+
+class InfiniteBipartiteRegularGraph:
+    """src/infinite_graph.jl:62-85: two node classes of degrees k = (kA, kB); message slot e (0-based) holds the message INTO
+    node e (from the other class), exactly like the reference's edge indices."""
+
+    def __init__(self, k):
+        self.k = (int(k[0]), int(k[1]))
+        self.N = 2
+
+    @property
+    def ne(self):
+        return 2
+
+    def degree(self, i):
+        return self.k[i]
+
+    def neighbors(self, i):
+        return [1 - i] * self.k[i]
 
 
 # --------------------------------------------------------------------------------------
@@ -193,11 +212,19 @@ class MPBP:
         self.g, self.w, self.T = g, w, int(T)
         self.q = np.ascontiguousarray(np.asarray(q, dtype=np.int32))
         self.N = g.N
-        self.infinite = isinstance(g, InfiniteRegularGraph)
+        self.bipartite = isinstance(g, InfiniteBipartiteRegularGraph)
+        self.infinite = isinstance(g, InfiniteRegularGraph) or self.bipartite
         assert len(w) == self.N and all(len(wi) == T + 1 for wi in w), "w must hold T+1 factors per node"
         self.dmax = int(dmax) if dmax is not None else 16
         self._h = C.c_void_p()
-        if self.infinite:
+        # _emap: reference edge index -> engine edge index (identity except for the bipartite infinite graph, whose
+        # reference slot e = "message into node e" is the engine's edge 1 - e = (1-e -> e))
+        if self.bipartite:
+            _lib.check(L.mpbp_create_infinite_bipartite(g.k[0], g.k[1], self.T, int(self.q[0]), int(self.q[1]), self.dmax, device, C.byref(self._h)))
+            self._src = np.array([0, 1], dtype=np.int64)
+            self._dst = np.array([1, 0], dtype=np.int64)
+            self._emap = [1, 0]
+        elif self.infinite:
             _lib.check(L.mpbp_create_infinite(g.k, self.T, int(self.q[0]), self.dmax, device, C.byref(self._h)))
             self._src = np.zeros(1, dtype=np.int64)
             self._dst = np.zeros(1, dtype=np.int64)
@@ -206,8 +233,11 @@ class MPBP:
                                      _p(g.rev, _lib.c_i64p), self.dmax, device, C.byref(self._h)))
             self._src, self._dst = g.src, g.dst
         self.E2 = len(self._src)
+        if not self.bipartite:
+            self._emap = list(range(self.E2))
         self.phi = [[np.ones(self.q[i]) for _ in range(T + 1)] for i in range(self.N)] if phi is None else phi
-        self.psi = [[np.ones((self.q[self._src[e]], self.q[self._dst[e]])) for _ in range(T + 1)] for e in range(self.E2)] if psi is None else psi
+        # psi[e] (reference index) is indexed [x_src, x_dst] of the ENGINE edge _emap[e]
+        self.psi = [[np.ones((self.q[self._src[self._emap[e]]], self.q[self._dst[self._emap[e]]])) for _ in range(T + 1)] for e in range(self.E2)] if psi is None else psi
         self._classes_dirty = True
         self.sync_reweightings()
 
@@ -226,7 +256,8 @@ class MPBP:
         phi = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).ravel() for ph in self.phi for p in ph]))
         assert len(phi) == int(np.sum(self.q)) * (self.T + 1), "phi must be [N][T+1][q_i]"
         _lib.check(L.mpbp_set_phi(self._h, _p(phi, _lib.c_dp)))
-        psi = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).ravel(order="F") for ps in self.psi for p in ps]))
+        inv = np.argsort(self._emap)  # engine edge -> reference index
+        psi = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).ravel(order="F") for ee in range(self.E2) for p in self.psi[int(inv[ee])]]))
         _lib.check(L.mpbp_set_psi(self._h, _p(psi, _lib.c_dp)))
 
     def upload_phi(self, flat):
@@ -246,7 +277,7 @@ class MPBP:
             if active is not None and not active[i]:
                 cls[i] = -1
                 continue
-            qn = np.array([self.q[0]] * z if self.infinite else [self.q[j] for j in self.g.neighbors(i)], dtype=np.int32)
+            qn = np.array([self.q[0]] * z if (self.infinite and not self.bipartite) else [self.q[j] for j in self.g.neighbors(i)], dtype=np.int32)
             wi = self.w[i]
             keys = [w.key() for w in wi]
             if not isinstance(wi[0], RecursiveBPFactor):
@@ -298,6 +329,7 @@ class MPBP:
     # ---- device <-> host messages (checkpoint / resume, parity) ----
     def get_message(self, e):
         L = _lib.lib()
+        e = self._emap[e]
         bonds = np.zeros(self.T + 2, dtype=np.int32)
         need = C.c_int64()
         _lib.check(L.mpbp_get_message(self._h, e, _p(bonds, _lib.c_i32p), None, 0, C.byref(need)))
@@ -313,6 +345,7 @@ class MPBP:
 
     def set_message(self, e, tensors):
         L = _lib.lib()
+        e = self._emap[e]
         bonds = np.array([t.shape[0] for t in tensors] + [tensors[-1].shape[1]], dtype=np.int32)
         data = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64).ravel(order="F") for t in tensors]))
         _lib.check(L.mpbp_set_message(self._h, e, _p(bonds, _lib.c_i32p), _p(data, _lib.c_dp)))
@@ -373,6 +406,13 @@ def mpbp(*args, **kw):
         raise TypeError(f"no mpbp method for {type(m)}")
     g, w, q, T = args
     return MPBP(g, w, q, T, **kw)
+
+
+def mpbp_infinite_bipartite_graph(k, w, q, phi=None, psi=None, **kw):
+    """mpbp_infinite_bipartite_graph((kA, kB), [wA, wB], (qA, qB), [phiA, phiB]; psi) -- src/infinite_graph.jl:87-105"""
+    T = len(w[0]) - 1
+    assert len(w[1]) == T + 1
+    return MPBP(InfiniteBipartiteRegularGraph(k), [list(w[0]), list(w[1])], [int(q[0]), int(q[1])], T, phi=phi, psi=psi, **kw)
 
 
 def mpbp_infinite_graph(k, w, q, phi=None, psi=None, **kw):
@@ -499,7 +539,7 @@ def pair_beliefs(bp: MPBP):
         n = qs * qd * (bp.T + 1)
         res.append(np.stack([out[off + t * qs * qd: off + (t + 1) * qs * qd].reshape(qs, qd, order="F") for t in range(bp.T + 1)]))
         off += n
-    return res, logz
+    return [res[bp._emap[e]] for e in range(bp.E2)], logz
 
 
 def pair_correlations(f, bp: MPBP):
@@ -522,7 +562,7 @@ def alternate_marginals(bp: MPBP):
         qs, qd = int(bp.q[bp._src[e]]), int(bp.q[bp._dst[e]])
         res.append([out[off + t * qs * qd: off + (t + 1) * qs * qd].reshape(qs, qd, order="F").copy() for t in range(bp.T)])
         off += qs * qd * (bp.T + 1)
-    return res
+    return [res[bp._emap[e]] for e in range(bp.E2)]
 
 
 def alternate_correlations(f, bp: MPBP):
@@ -545,7 +585,11 @@ def free_energy_contributions(bp: MPBP):
 
 
 def bethe_free_energy(bp: MPBP):
-    return float(np.sum(free_energy_contributions(bp)))
+    f = free_energy_contributions(bp)
+    if bp.bipartite:  # reweighted by the fraction of nodes in each block (src/infinite_graph.jl:120-122)
+        k = bp.g.k
+        return float((f[0] * k[1] + f[1] * k[0]) / (k[0] + k[1]))
+    return float(np.sum(f))
 
 
 def onesample(bp: MPBP, rng=None):

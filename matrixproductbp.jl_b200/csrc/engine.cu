@@ -76,7 +76,12 @@ struct mpbp_state {
   int device = 0;
   int64_t N = 0, E2 = 0;
   int T = 0, L = 1, dmax = 1, qmax = 1;
-  int inf_k = 0;  // > 0: InfiniteRegularGraph(k)
+  int inf_k = 0;  // > 0: infinite (iid) graph: every node stands for a whole class and sees inf_deg[i] copies of its single in-edge
+                  // (InfiniteRegularGraph(k): N = 1, self edge; InfiniteBipartiteRegularGraph((kA,kB)): N = 2, one edge pair)
+  std::vector<int> inf_deg;
+  std::vector<int64_t> lz_off;  // offset of node i's log z_{i->j} entries in d_logzij
+  int node_deg(int64_t i) const { return inf_k > 0 ? inf_deg[i] : (int)(colptr[i + 1] - colptr[i]); }
+  int64_t out_edge(int64_t i, int k) const { return inf_k > 0 ? colptr[i] : colptr[i] + k; }
   std::vector<int> q;
   std::vector<int64_t> colptr, dst, rev, src;
   std::vector<int64_t> phi_off, psi_off, marg_off;
@@ -232,7 +237,9 @@ int common_init(mpbp_state* h) {
   }
   if (upload(&h->d_marg, marg.data(), marg.size())) return 1;
   if (upload(&h->d_means, means.data(), means.size())) return 1;
-  const int64_t nzij = h->inf_k > 0 ? h->inf_k : h->E2;
+  h->lz_off.assign(h->N + 1, 0);
+  for (int64_t i = 0; i < h->N; ++i) h->lz_off[i + 1] = h->lz_off[i] + h->node_deg(i);
+  const int64_t nzij = h->lz_off[h->N];
   std::vector<double> zeros(std::max<int64_t>(std::max<int64_t>(h->N, nzij), 32), 0.0);
   if (upload(&h->d_logzi, zeros.data(), h->N)) return 1;
   if (upload(&h->d_logzij, zeros.data(), nzij)) return 1;
@@ -273,6 +280,8 @@ struct Plan {
   std::vector<std::vector<OpDesc>> hlevels;
   std::vector<std::vector<int>> hcapA, hcapB;
   std::vector<FinJob> fin;
+  std::vector<FinJob> gfin;    // generic path: the dummy-neighbour message of every generic node (compressed before it is
+  std::vector<MargJob> gmarg;  // marginalised into the belief, src/mpbp.jl:145-154), and the marginals read from it
   std::vector<DampJob> damp;  // one per FinJob when damp > 0 (same order)
   std::vector<BelJob> bel;
   std::vector<FJob> fj;
@@ -302,6 +311,7 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
     const size_t fin = (size_t)(L + 1) * (d * q) * (d * q) + (size_t)d * d * q * q * q * qjm + (size_t)d * d * q * q * qjm +
                        (size_t)d * d * q * qjm + 2 * (size_t)d * d * q + (L + 1) + (size_t)(d * q * qjm) * (d * q * qjm);
     b += (size_t)z * (fin * 8 + 8 * 256) + ((size_t)L * d * q + (size_t)d * d * q * q) * 8 + 2 * 256;
+    b += fin * 8 + h->slot * 8 + 4 * (L + 1) + 8 + (size_t)(L + 1) * d * 8 + 16 * 256;  // dummy-neighbour message + marginals
     if (h->inf_k > 0) b += (size_t)z * (h->slot * 8 + 4 * (L + 1) + 8 + 3 * 256);
     if (h->damp > 0.0) {
       const size_t b2 = 2 * (size_t)d, Pm = (size_t)h->qmax * h->qmax;
@@ -452,8 +462,7 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
     if (c.generic) {
       // exhaustive-trace path (src/mpbp.jl:117-154, src/bp_core.jl:18-93): Kronecker of the other neighbours' messages,
       // then the same MPEM3->MPEM2 / compress / normalize kernel with the dense factor table as W
-      const int64_t e0g = h->inf_k > 0 ? 0 : h->colptr[i];
-      const int degg = h->inf_k > 0 ? h->inf_k : (int)(h->colptr[i + 1] - h->colptr[i]);
+      const int degg = h->node_deg(i);
       if (degg != z) return fail("node %lld has degree %d but its class has z=%d", (long long)i, degg, z);
       if (q != h->q[i]) return fail("node %lld: class q mismatch", (long long)i);
       auto make_gen = [&](int skip, int ny) -> TTRef {
@@ -463,8 +472,8 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
         gj.skip = skip;
         gj.q = q;
         for (int k = 0; k < z; ++k) {
-          const int64_t eout = h->inf_k > 0 ? 0 : e0g + k;
-          const int64_t ein = h->inf_k > 0 ? 0 : h->rev[eout];
+          const int64_t eout = h->out_edge(i, k);
+          const int64_t ein = h->rev[eout];
           gj.qk[k] = c.qn[k];
           gj.msg[k] = msg_ref(h, h->msg[rb], ein, c.qn[k] * q);
           gj.psi[k] = h->d_psi + h->psi_off[eout];
@@ -474,7 +483,7 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
         return gj.out;
       };
       for (int j = 0; j < z; ++j) {
-        const int64_t eout = h->inf_k > 0 ? 0 : e0g + j;
+        const int64_t eout = h->out_edge(i, j);
         const int qj = c.qn[j];
         FinJob fj;
         memset(&fj, 0, sizeof fj);
@@ -500,7 +509,7 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
         fj.W = c.d_w + c.w_off[j];
         fj.w_tstride = (int)c.w_ts;
         fj.phi = h->d_phi + h->phi_off[i];
-        fj.logz_out = h->d_logzij + (h->inf_k > 0 ? j : eout);
+        fj.logz_out = h->d_logzij + h->lz_off[i] + j;
         const size_t dq = (size_t)d * q;
         fj.rstride = (int)(dq * dq);
         fj.Rbuf = (double*)h->arena.take(8 * (size_t)(L + 1) * fj.rstride);
@@ -534,24 +543,64 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
         ok = ok && bj.Btall && bj.fwall;
       }
       P.bel.push_back(bj);
+      {
+        // bp.b[i] = marginalize(compress!(mpem2(f_bp_dummy_neighbor))) : same kernel as an outgoing message with a
+        // one-state dummy neighbour (q_j = 1) and the full table, written to a scratch slot; log z_i = its normalisation
+        FinJob fj;
+        memset(&fj, 0, sizeof fj);
+        fj.c = bj.full;
+        fj.nyc = c.gen_ny[z];
+        fj.q = q;
+        fj.qj = 1;
+        fj.W = c.d_wd;
+        fj.w_tstride = (int)c.wd_ts;
+        fj.phi = h->d_phi + h->phi_off[i];
+        fj.logz_out = h->d_logzi + i;
+        TTRef slot;
+        slot.stride = h->sstride;
+        slot.P = q;
+        slot.data = (double*)h->arena.take(sizeof(double) * h->slot);
+        slot.bonds = (int*)h->arena.take(sizeof(int) * (L + 1));
+        slot.ls = (double*)h->arena.take(sizeof(double));
+        fj.out = slot;
+        const size_t dq = (size_t)d * q;
+        fj.rstride = (int)(dq * dq);
+        fj.Rbuf = (double*)h->arena.take(8 * (size_t)(L + 1) * fj.rstride);
+        fj.kdim = (int*)h->arena.take(4 * (L + 1));
+        fj.Bt = (double*)h->arena.take(8 * (size_t)d * d * q * q);
+        fj.S = (double*)h->arena.take(8 * (size_t)d * d * q * q * q);
+        fj.H = (double*)h->arena.take(8 * (size_t)d * d * q);
+        fj.R2 = (double*)h->arena.take(8 * (size_t)(d * q) * (d * q));
+        fj.Pr[0] = (double*)h->arena.take(8 * (size_t)d * d * q);
+        fj.Pr[1] = (double*)h->arena.take(8 * (size_t)d * d * q);
+        ok = ok && slot.data && slot.bonds && slot.ls && fj.Rbuf && fj.kdim && fj.Bt && fj.S && fj.H && fj.R2 && fj.Pr[0] && fj.Pr[1];
+        P.gfin.push_back(fj);
+        MargJob mj;
+        mj.tt = slot;
+        mj.q = q;
+        mj.qj = 1;
+        mj.marg = h->d_marg + h->marg_off[i];
+        mj.rv = (double*)h->arena.take(8 * (size_t)(L + 1) * d);
+        ok = ok && mj.rv;
+        P.gmarg.push_back(mj);
+      }
       FJob f;
       f.logzi = h->d_logzi + i;
-      f.logzij = h->d_logzij + (h->inf_k > 0 ? 0 : e0g);
+      f.logzij = h->d_logzij + h->lz_off[i];
       f.z = z;
       f.f = h->d_f + i;
       P.fj.push_back(f);
       continue;
     }
-    const int64_t e0 = h->inf_k > 0 ? 0 : h->colptr[i];
-    const int deg = h->inf_k > 0 ? h->inf_k : (int)(h->colptr[i + 1] - h->colptr[i]);
+    const int deg = h->node_deg(i);
     if (deg != z) return fail("node %lld has degree %d but its class has z=%d", (long long)i, deg, z);
     if (q != h->q[i]) return fail("node %lld: class q mismatch", (long long)i);
     // B~_k
     std::vector<TTRef> src(z);
     for (int k = 0; k < z; ++k) {
-      const int64_t eout = h->inf_k > 0 ? 0 : e0 + k;
-      const int64_t ein = h->inf_k > 0 ? 0 : h->rev[eout];
-      const int qk = h->inf_k > 0 ? q : h->q[h->dst[eout]];
+      const int64_t eout = h->out_edge(i, k);
+      const int64_t ein = h->rev[eout];
+      const int qk = h->q[h->dst[eout]];
       if (qk != c.qn[k]) return fail("node %lld neighbour %d: class qn mismatch", (long long)i, k);
       BtJob jb;
       jb.msg = msg_ref(h, h->msg[rb], ein, qk * q);
@@ -625,7 +674,7 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
     }
     // outgoing messages
     for (int j = 0; j < z; ++j) {
-      const int64_t eout = h->inf_k > 0 ? 0 : e0 + j;
+      const int64_t eout = h->out_edge(i, j);
       const int qj = c.qn[j];
       FinJob fj;
       memset(&fj, 0, sizeof fj);
@@ -653,7 +702,7 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
       fj.W = c.d_w + c.w_off[j];
       fj.w_tstride = (int)c.w_ts;
       fj.phi = h->d_phi + h->phi_off[i];
-      fj.logz_out = h->d_logzij + (h->inf_k > 0 ? j : eout);
+      fj.logz_out = h->d_logzij + h->lz_off[i] + j;
       const size_t dq = (size_t)d * q;
       fj.rstride = (int)(dq * dq);
       fj.Rbuf = (double*)h->arena.take(8 * (size_t)(L + 1) * fj.rstride);
@@ -689,7 +738,7 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
     P.bel.push_back(bj);
     FJob f;
     f.logzi = h->d_logzi + i;
-    f.logzij = h->d_logzij + (h->inf_k > 0 ? 0 : e0);
+    f.logzij = h->d_logzij + h->lz_off[i];
     f.z = z;
     f.f = h->d_f + i;
     P.fj.push_back(f);
@@ -1160,6 +1209,15 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
       k_belief<<<(unsigned)P.bel.size(), NT, bsm, st>>>(d_bel, L, d, h->d_err);
       ev_end(h, st);
     }
+    if (!P.gfin.empty()) {
+      // generic nodes: the belief comes from the COMPRESSED dummy-neighbour message (overwrites what k_belief wrote)
+      FinJob* d_gfin;
+      MargJob* d_gmarg;
+      if (upload_jobs(h, P.gfin, &d_gfin) || upload_jobs(h, P.gmarg, &d_gmarg)) return 1;
+      k_finalize<<<(unsigned)P.gfin.size(), NT, smem, st>>>(d_gfin, L, tr, d, vrows, (int)jac_doubles, h->d_err);
+      k_msg_marginals<<<(unsigned)P.gmarg.size(), NT, 2 * (size_t)d * 8, st>>>(d_gmarg, L, d);
+      h->n_launch += 2;
+    }
     if (h->twovar > 0 && !P.bel.empty()) {
       const size_t tsm = 2 * (size_t)qm * d * qm * 8;
       k_twovar<<<(unsigned)P.bel.size(), NT, tsm, st>>>(d_bel, L, d, h->twovar, qm * qm);
@@ -1266,12 +1324,40 @@ int mpbp_create_infinite(int k, int T, int q, int dmax, int device, mpbp_handle*
   h->L = T + 1;
   h->dmax = dmax;
   h->inf_k = k;
+  h->inf_deg = {k};
   h->q = {q};
   h->colptr = {0, 1};
   h->dst = {0};
   h->rev = {0};
   h->src = {0};
   h->class_of_node.assign(1, -1);
+  if (common_init(h)) { delete h; return 1; }
+  *out = h;
+  return 0;
+}
+
+// InfiniteBipartiteRegularGraph((kA, kB)) (src/infinite_graph.jl:62-122): two node classes, node 0 (degree kA, q = qA) and
+// node 1 (degree kB, q = qB), one message per direction: edge 0 = (0 -> 1), edge 1 = (1 -> 0).  Node i sees inf_deg[i]
+// copies of its single incoming message; of its recomputed outgoing messages the last one stays, as in the reference.
+int mpbp_create_infinite_bipartite(int kA, int kB, int T, int qA, int qB, int dmax, int device, mpbp_handle* out) {
+  if (!out) return fail("null out");
+  if (kA < 1 || kB < 1 || T < 0 || dmax < 1 || qA < 1 || qA > 8 || qB < 1 || qB > 8) return fail("invalid arguments");
+  if (dmax > 30) return fail("dmax=%d exceeds the supported bond capacity 30 (shared-memory tiling of the contraction kernels)", dmax);
+  mpbp_state* h = new mpbp_state();
+  h->device = device;
+  h->N = 2;
+  h->E2 = 2;
+  h->T = T;
+  h->L = T + 1;
+  h->dmax = dmax;
+  h->inf_k = std::max(kA, kB);
+  h->inf_deg = {kA, kB};
+  h->q = {qA, qB};
+  h->colptr = {0, 1, 2};
+  h->dst = {1, 0};
+  h->rev = {1, 0};
+  h->src = {0, 1};
+  h->class_of_node.assign(2, -1);
   if (common_init(h)) { delete h; return 1; }
   *out = h;
   return 0;
@@ -1553,7 +1639,7 @@ int mpbp_iterate(mpbp_handle h, int maxiter, int trunc_kind, int trunc_d, double
       for (size_t k = 0; k < ord.size(); ++k) {
         const int64_t i = ord[k];
         int lv = 0;
-        if (h->inf_k == 0)
+        // (infinite graphs: the single neighbour class is the destination of the node's one edge)
           for (int64_t e = h->colptr[i]; e < h->colptr[i + 1]; ++e) {
             const int64_t j = h->dst[e];
             if (pos[j] >= 0 && pos[j] < (int)k) lv = std::max(lv, level[j] + 1);
@@ -1654,7 +1740,8 @@ int mpbp_pair_beliefs(mpbp_handle h, double* out, double* logz) {
   // logz[j] += (1/d_j - 1/2) log z_ij   (src/mpbp.jl:230 ; infinite graph: src/infinite_graph.jl:40)
   for (int64_t i = 0; i < h->N; ++i) logz[i] = 0.0;
   if (h->inf_k > 0) {
-    logz[0] = (1.0 / (h->inf_k - 1) - 0.5) * lz[0];
+    // src/infinite_graph.jl:37-43,110-118: logz[i] = (1/(k_i - 1) - 1/2) log z of the pair built on the message INTO i
+    for (int64_t e = 0; e < h->E2; ++e) logz[h->dst[e]] = (1.0 / (h->inf_deg[h->dst[e]] - 1) - 0.5) * lz[e];
   } else {
     for (int64_t e = 0; e < h->E2; ++e) {
       const int64_t j = h->src[e];

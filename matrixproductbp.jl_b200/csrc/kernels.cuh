@@ -1524,6 +1524,88 @@ __global__ void __launch_bounds__(NT) k_belief(const BelJob* jobs, int L, int dc
 }
 
 // ------------------------------------------------------------------------------------------------
+// marginals of a (compressed) MPEM2 summed over its second variable: bp.b[i] = marginalize(mu) on the generic path, where
+// the reference compresses the dummy-neighbour message before marginalising (src/mpbp.jl:145-154, src/mpems.jl:27-29).
+// p_t[x] ~ l_{t-1} (sum_xj A_t[:,:,x,xj]) r_{t+1}.  One CTA per job; rv: global scratch (L+1)*dcap doubles.
+// ------------------------------------------------------------------------------------------------
+struct MargJob {
+  TTRef tt;      // [m,n,x,xj]
+  int q, qj;
+  double* marg;  // [t][x]
+  double* rv;
+};
+__global__ void __launch_bounds__(NT) k_msg_marginals(const MargJob* jobs, int L, int dcap) {
+  __shared__ double red[NW + 1];
+  __shared__ double pm[8];
+  extern __shared__ double smem[];  // l0, l1 : dcap each
+  const MargJob& jb = jobs[blockIdx.x];
+  const int q = jb.q, P = jb.q * jb.qj;
+  const int* bonds = jb.tt.bonds;
+  // right vectors r_t (length bonds[t]) = (sum_p A_t) r_{t+1}, rescaled
+  if (threadIdx.x == 0) jb.rv[(size_t)L * dcap] = 1.0;
+  __syncthreads();
+  for (int t = L - 1; t >= 0; --t) {
+    const int bl = bonds[t], br = bonds[t + 1];
+    const double* A = jb.tt.data + (size_t)t * jb.tt.stride;
+    const double* rn = jb.rv + (size_t)(t + 1) * dcap;
+    double* rt = jb.rv + (size_t)t * dcap;
+    double mx = 0.0;
+    for (int m = threadIdx.x; m < bl; m += NT) {
+      double acc = 0.0;
+      for (int pp = 0; pp < P; ++pp)
+        for (int n = 0; n < br; ++n) acc += A[m + (size_t)bl * (n + br * pp)] * rn[n];
+      rt[m] = acc;
+      mx = fmax(mx, fabs(acc));
+    }
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int m = threadIdx.x; m < bl; m += NT) rt[m] *= f;
+    __syncthreads();
+  }
+  double* l0 = smem;
+  double* l1 = smem + dcap;
+  if (threadIdx.x == 0) l0[0] = 1.0;
+  __syncthreads();
+  for (int t = 0; t < L; ++t) {
+    const int bl = bonds[t], br = bonds[t + 1];
+    const double* A = jb.tt.data + (size_t)t * jb.tt.stride;
+    const double* rn = jb.rv + (size_t)(t + 1) * dcap;
+    if (threadIdx.x < q) {
+      const int x = threadIdx.x;
+      double acc = 0.0;
+      for (int xj = 0; xj < jb.qj; ++xj)
+        for (int n = 0; n < br; ++n) {
+          double s = 0.0;
+          for (int m = 0; m < bl; ++m) s += l0[m] * A[m + (size_t)bl * (n + br * (x + q * xj))];
+          acc += s * rn[n];
+        }
+      pm[x] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int x = 0; x < q; ++x) s += pm[x];
+      for (int x = 0; x < q; ++x) jb.marg[(size_t)t * q + x] = pm[x] / s;
+    }
+    double mx = 0.0;
+    for (int n = threadIdx.x; n < br; n += NT) {
+      double acc = 0.0;
+      for (int pp = 0; pp < P; ++pp)
+        for (int m = 0; m < bl; ++m) acc += l0[m] * A[m + (size_t)bl * (n + br * pp)];
+      l1[n] = acc;
+      mx = fmax(mx, fabs(acc));
+    }
+    mx = block_max(mx, red);
+    const double f = (mx > 0.0 && isfinite(mx)) ? 1.0 / mx : 1.0;
+    for (int n = threadIdx.x; n < br; n += NT) l1[n] *= f;
+    __syncthreads();
+    double* tmp = l0;
+    l0 = l1;
+    l1 = tmp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // two-time marginals of the belief, b_i(x^t, x^u) for t < u <= t + maxdist: what TensorTrains.twovar_marginals
 // returns for bp.b[i] (beliefs_tu / autocorrelations / autocovariances, src/mpbp.jl:239-255,289-296).  Same transfer
 // formulation as k_belief (the belief MPEM is never built): with B_s[m,n,x,x'] the site tensors of

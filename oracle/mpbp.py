@@ -69,6 +69,35 @@ class InfiniteRegularGraph:
         return self.infinite_k
 
 
+class InfiniteBipartiteRegularGraph:
+    """two node classes of degrees k = (kA, kB); edge e (0-based) is the message INTO node e from the other class
+    (infinite_graph.jl:62-85: inedges(g, i) carry idx i, outedges idx 3-i)."""
+
+    def __init__(self, k):
+        self.N = 2
+        self.k = (int(k[0]), int(k[1]))
+        self.infinite_k = None
+        self.bipartite_k = self.k
+        self.src = [1, 0]
+        self.dst = [0, 1]
+        self.rev = [1, 0]
+        self.in_edges = [[0] * self.k[0], [1] * self.k[1]]
+        self.out_edges = [[1] * self.k[0], [0] * self.k[1]]
+
+    @property
+    def ne(self):
+        return 2
+
+    def degree(self, i):
+        return self.k[i]
+
+
+def mpbp_infinite_bipartite_graph(k, w, q, phi=None, psi=None, d=1):
+    """infinite_graph.jl:87-105"""
+    T = len(w[0]) - 1
+    return MPBP(InfiniteBipartiteRegularGraph(k), [list(w[0]), list(w[1])], list(q), T, phi=phi, psi=psi, d=d)
+
+
 class MPBP:
     def __init__(self, g, w, q, T, phi=None, psi=None, d=1):
         self.g, self.w, self.q, self.T = g, w, list(q), int(T)
@@ -396,6 +425,9 @@ def autocovariances(bp, f=lambda x, i: x, maxdist=None):
 
 
 def bethe_free_energy(bp):
+    k = getattr(bp.g, "bipartite_k", None)
+    if k is not None:  # infinite_graph.jl:120-122
+        return float((bp.f[0] * k[1] + bp.f[1] * k[0]) / (k[0] + k[1]))
     return float(np.sum(bp.f))
 
 
@@ -414,6 +446,13 @@ def pair_beliefs(bp):
     g = bp.g
     logz = np.zeros(g.N)
     b = [None] * g.ne
+    if getattr(g, "bipartite_k", None) is not None:
+        # infinite_graph.jl:110-118
+        for i in range(2):
+            P = pair_belief_tt(bp.mu[i], bp.mu[1 - i], bp.psi[i])
+            b[i] = T_.marginals(P)
+            logz[i] = (1 / (g.bipartite_k[i] - 1) - 0.5) * T_.lognormalization(P)
+        return b, logz
     if g.infinite_k is not None:
         Aij = bp.mu[0]
         P = pair_belief_tt(Aij, Aij, bp.psi[0])

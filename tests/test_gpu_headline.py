@@ -196,3 +196,69 @@ def test_hub_lane_and_engine_knobs_do_not_change_results():
                     np.concatenate([np.array(p).ravel() for p in pb]), np.asarray(lz)))
     for a, b in zip(*res):
         assert np.max(np.abs(a - b)) < 1e-11
+
+
+def test_infinite_bipartite_graph_vs_oracle_and_known_answer():
+    """InfiniteBipartiteRegularGraph (src/infinite_graph.jl:62-122) on the device: (i) the reference's own known answer
+    (test/glauber_infinite_graph.jl:48-100: equals the complete bipartite graph K_{2,3}, TruncThresh(0.0), damp 0.1), both sides
+    on the device; (ii) fixed iteration count with a binding TruncBond against the oracle (beliefs, pair beliefs, f)."""
+    from oracle import factors as OF
+    T, k, m0 = 3, (3, 2), 0.5
+    JA, JB, h, beta = 1.0, -0.2, -0.1, 1.0
+    phi = [[np.array([(1 + m0) / 2, (1 - m0) / 2]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(2)]
+    phi[0][1] = np.array([0.4, 0.6])
+    phi[1][T] = np.array([0.95, 0.05])
+    wd = [[M.HomogeneousGlauberFactor(JA, h, beta)] * (T + 1), [M.HomogeneousGlauberFactor(JB, h, beta)] * (T + 1)]
+    bp = M.mpbp_infinite_bipartite_graph(k, wd, (2, 2), phi=[[p.copy() for p in ph] for ph in phi], dmax=16)
+    it, _ = M.iterate_(bp, maxiter=150, svd_trunc=M.TruncThresh(0.0), tol=1e-14, damp=0.1, shuffle_nodes=False)
+    assert it < 150
+    N = sum(k)
+    und = [(a, b) for a in range(k[1]) for b in range(k[1], N)]
+    g = M.IndexedBiDiGraph(N, und)
+    wex = [[M.HomogeneousGlauberFactor(JA if i < k[1] else JB, h, beta)] * (T + 1) for i in range(N)]
+    phiex = [[p.copy() for p in (phi[0] if i < k[1] else phi[1])] for i in range(N)]
+    be = M.mpbp(g, wex, [2] * N, T, phi=phiex, dmax=16)
+    it2, _ = M.iterate_(be, maxiter=150, svd_trunc=M.TruncThresh(0.0), tol=1e-14, shuffle_nodes=False)
+    assert it2 < 150
+    assert abs(np.exp(-M.bethe_free_energy(bp)) - np.exp(-M.bethe_free_energy(be) / N)) < TOL
+    b, bex = M.beliefs(bp), M.beliefs(be)
+    assert np.max(np.abs(b[0] - bex[0])) < TOL and np.max(np.abs(b[1] - bex[k[1]])) < TOL
+    # (ii) truncated, fixed iterations, vs the oracle
+    wo = [[OF.HomogeneousGlauberFactor(JA, h, beta)] * (T + 1), [OF.HomogeneousGlauberFactor(JB, h, beta)] * (T + 1)]
+    for schedule, damp in (("sequential", 0.0), ("parallel", 0.0), ("sequential", 0.2)):
+        bo = O.mpbp_infinite_bipartite_graph(k, wo, (2, 2), phi=[[p.copy() for p in ph] for ph in phi])
+        bd = M.mpbp_infinite_bipartite_graph(k, wd, (2, 2), phi=[[p.copy() for p in ph] for ph in phi], dmax=4)
+        O.iterate(bo, maxiter=4, trunc=OT.TruncBond(3), tol=0.0, schedule=schedule, damp=damp)
+        M.iterate_(bd, maxiter=4, svd_trunc=M.TruncBond(3), tol=0.0, shuffle_nodes=False, schedule=schedule, damp=damp)
+        eb, ef, ep = compare(bo, bd)
+        assert eb < TOL and ef < TOL and ep < TOL, (schedule, damp, eb, ef, ep)
+        assert abs(O.bethe_free_energy(bo) - M.bethe_free_energy(bd)) < TOL
+
+
+def test_generic_path_compresses_the_dummy_neighbour_message():
+    """src/mpbp.jl:145-154: on the generic (exhaustive-trace) path the belief is marginalize(compress!(dummy-neighbour
+    message)); with a BINDING truncation the device must reproduce that compression (round 1 marginalised the un-truncated
+    train).  Loopy graph, degree-3 node, T = 4, TruncBond(2) and TruncBond(3)."""
+    from oracle import factors as OF
+    T, N = 4, 4
+    und = [(0, 1), (1, 2), (2, 0), (1, 3)]
+    rng = np.random.default_rng(11)
+    hh = rng.standard_normal(N)
+    for dd in (2, 3):
+        go = O.BiDiGraph(N, und)
+        gd = M.IndexedBiDiGraph(N, und)
+        wo = [[OF.GenericFactor(OF.HomogeneousGlauberFactor(0.8, float(hh[i]), 1.0))] * (T + 1) for i in range(N)]
+        wd = [[M.GenericFactor(M.HomogeneousGlauberFactor(0.8, float(hh[i]), 1.0))] * (T + 1) for i in range(N)]
+        phi = [[np.array([0.7, 0.3]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
+        phi[2][2] = np.array([1.0, 0.2])
+        bo = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
+        bd = M.mpbp(gd, wd, [2] * N, T, phi=phi, dmax=4)
+        O.iterate(bo, maxiter=3, trunc=OT.TruncBond(dd), tol=0.0)
+        M.iterate_(bd, maxiter=3, svd_trunc=M.TruncBond(dd), tol=0.0, shuffle_nodes=False)
+        eb, ef, ep = compare(bo, bd)
+        assert eb < TOL and ef < TOL and ep < TOL, (dd, eb, ef, ep)
+    # the truncation really binds for the belief: un-truncated beliefs differ from the truncated ones by more than TOL
+    bo2 = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
+    O.iterate(bo2, maxiter=3, trunc=OT.TruncBond(16), tol=0.0)
+    diff = max(float(np.max(np.abs(np.array(a) - np.array(b)))) for a, b in zip(O.beliefs(bo), O.beliefs(bo2)))
+    assert diff > 100 * TOL

@@ -460,3 +460,30 @@ def test_random_small_trees_are_exact(seed):
     assert np.allclose(np.array(O.alternate_marginals(bp)), np.array(exact.exact_alternate_marginals(bp, p)), atol=1e-10)
     fobs = lambda x, i: x * x - 1.5
     assert np.allclose(np.array(O.autocorrelations(bp, fobs)), np.array(exact.exact_autocorrelations(bp, p, fobs)), atol=1e-10)
+
+
+def test_glauber_infinite_bipartite_graph_known_answer():
+    """/root/reference/test/glauber_infinite_graph.jl:48-100: BP on the infinite bipartite (3,2)-regular graph equals BP on the
+    complete bipartite graph K_{2,3} (free energy per node and beliefs of the two classes); TruncThresh(0.0), damp = 0.1 on
+    the infinite side, as in the reference test."""
+    T, k, m0 = 3, (3, 2), 0.5
+    JA, JB, h, beta = 1.0, -0.2, -0.1, 1.0
+    w = [[F.HomogeneousGlauberFactor(JA, h, beta)] * (T + 1), [F.HomogeneousGlauberFactor(JB, h, beta)] * (T + 1)]
+    phi = [[np.array([(1 + m0) / 2, (1 - m0) / 2]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(2)]
+    phi[0][1] = np.array([0.4, 0.6])
+    phi[1][T] = np.array([0.95, 0.05])
+    bp = O.mpbp_infinite_bipartite_graph(k, w, (2, 2), phi=phi)
+    it, _ = O.iterate(bp, maxiter=150, trunc=tt.TruncThresh(0.0), tol=1e-15, damp=0.1)
+    assert it < 150
+    N = sum(k)
+    und = [(a, b) for a in range(k[1]) for b in range(k[1], N)]
+    g = O.BiDiGraph(N, und)
+    wex = [[F.HomogeneousGlauberFactor(JA if i < k[1] else JB, h, beta)] * (T + 1) for i in range(N)]
+    phiex = [[p.copy() for p in (phi[0] if i < k[1] else phi[1])] for i in range(N)]
+    be = O.MPBP(g, wex, [2] * N, T, phi=phiex)
+    it2, _ = O.iterate(be, maxiter=150, trunc=tt.TruncThresh(0.0), tol=1e-15)
+    assert it2 < 150
+    assert abs(np.exp(-O.bethe_free_energy(bp)) - np.exp(-O.bethe_free_energy(be) / N)) < 1e-10
+    b, bex = O.beliefs(bp), O.beliefs(be)
+    assert np.max(np.abs(np.array(b[0]) - np.array(bex[0]))) < 1e-10
+    assert np.max(np.abs(np.array(b[1]) - np.array(bex[k[1]]))) < 1e-10
