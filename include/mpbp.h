@@ -122,6 +122,13 @@ int mpbp_twovar_marginals(mpbp_handle h, double* out);
  * per edge e (T+1) blocks of q_src*q_dst doubles, out[...][t][x_i^t + q_src*x_j^{t+1}] for t < T; the block t = T is 0. */
 int mpbp_alternate_marginals(mpbp_handle h, double* out);
 
+/* forward sample of the prior dynamics on the device (reference: onesample!, src/sampling.jl:30-59, the input generator of
+ * draw_node_observations!, :191-210): x_i^0 ~ phi_i^0/sum, x_i^{t+1} ~ w_i^t(. | x_neighbours^t, x_i^t) evaluated from the
+ * uploaded factor tables (recursive classes fold the neighbours like the factor's functor, src/recursive_bp_factor.jl:34-46;
+ * generic classes index their dense table).  X: N x (T+1) int32, states 0-based, row i = node i.  Deterministic in `seed`
+ * (counter-based RNG documented in csrc/kernels.cuh: samp_uniform), finite graphs only. */
+int mpbp_sample_prior(mpbp_handle h, uint64_t seed, int32_t* X);
+
 /* ---- multi-GPU plumbing (no reference counterpart; see DESIGN.md "multi-GPU") ----
  * pack/unpack the fixed-capacity device slots of `n` messages into/from one contiguous DEVICE buffer so that
  * the host layer can exchange cut-edge messages with one collective.  Record size from mpbp_message_slot_bytes

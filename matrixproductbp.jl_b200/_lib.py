@@ -35,6 +35,7 @@ SIGNATURES = {
     "mpbp_free_energy": (C.c_int, [C.c_void_p, c_dp]),
     "mpbp_twovar_marginals": (C.c_int, [C.c_void_p, c_dp]),
     "mpbp_alternate_marginals": (C.c_int, [C.c_void_p, c_dp]),
+    "mpbp_sample_prior": (C.c_int, [C.c_void_p, C.c_uint64, c_i32p]),
     "mpbp_message_slot_bytes": (C.c_int64, [C.c_void_p]),
     "mpbp_pack_messages_dev": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, C.c_void_p]),
     "mpbp_unpack_messages_dev": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, C.c_void_p]),

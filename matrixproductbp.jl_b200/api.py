@@ -24,7 +24,7 @@ __all__ = [
     "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
     "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "InfiniteBipartiteRegularGraph", "mpbp_infinite_bipartite_graph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
     "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_correlations", "pair_beliefs", "bethe_free_energy", "means",
-    "reset_messages_", "glauber_factors", "MPBPError", "onesample", "draw_node_observations_",
+    "reset_messages_", "glauber_factors", "MPBPError", "onesample", "sample_prior", "draw_node_observations_",
 ]
 
 MPBPError = _lib.MPBPError
@@ -592,10 +592,34 @@ def bethe_free_energy(bp: MPBP):
     return float(np.sum(f))
 
 
+def sample_prior(bp: MPBP, seed):
+    """X[i, t] (0-based states, N x (T+1) int32) of one forward simulation of the prior dynamics, drawn ON THE DEVICE from the
+    uploaded factor tables (mpbp_sample_prior); deterministic in `seed`"""
+    if bp._classes_dirty:
+        bp.sync_factors()
+    X = np.zeros((bp.N, bp.T + 1), dtype=np.int32)
+    _lib.check(_lib.lib().mpbp_sample_prior(bp._h, C.c_uint64(int(seed) & ((1 << 64) - 1)), _p(X, _lib.c_i32p)))
+    return X
+
+
 def onesample(bp: MPBP, rng=None):
-    """onesample(bp) -> (X, weight): forward sample of the prior dynamics of bp (host side, src/sampling.jl:30-66)"""
-    from .sampling import onesample as _one
-    return _one(bp.g, bp.w, bp.q, bp.T, bp.phi, None if bp.infinite else bp.psi, rng)
+    """onesample(bp) -> (X, weight): forward sample of the prior dynamics of bp (src/sampling.jl:30-66), states numbered from 1
+    as in the reference.  The trajectory is drawn on the device; the likelihood weight exp(sum_{t>0} log phi + 1/2 sum_e log
+    psi) is a vectorised host reduction over it."""
+    rng = np.random.default_rng(rng)
+    X0 = sample_prior(bp, int(rng.integers(0, 2 ** 63 - 1)))
+    L = bp.T + 1
+    logl = 0.0
+    with np.errstate(divide="ignore"):
+        for i in range(bp.N):
+            ph = np.asarray([np.asarray(p, dtype=float) for p in bp.phi[i]])  # [t][x]
+            logl += float(np.sum(np.log(ph[np.arange(1, L), X0[i, 1:]])))
+        for e in range(bp.E2):
+            ee = bp._emap[e]
+            i, j = int(bp._src[ee]), int(bp._dst[ee])
+            ps = np.asarray([np.asarray(p, dtype=float) for p in bp.psi[e]])  # [t][xi, xj]
+            logl += 0.5 * float(np.sum(np.log(ps[np.arange(L), X0[i], X0[j]])))
+    return X0.astype(np.int64) + 1, float(np.exp(logl))
 
 
 def draw_node_observations_(bp: MPBP, nobs, rng=None, **kw):

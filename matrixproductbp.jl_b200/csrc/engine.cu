@@ -1796,6 +1796,74 @@ int mpbp_alternate_marginals(mpbp_handle h, double* out) {
   return 0;
 }
 
+// forward sample of the prior dynamics on the device (reference onesample!, src/sampling.jl:30-59).
+// X: N x (T+1) int32, row i = trajectory of node i, states 0-based.  Deterministic in `seed` (counter-based RNG).
+int mpbp_sample_prior(mpbp_handle h, uint64_t seed, int32_t* X) {
+  if (!h || !X) return fail("null argument");
+  if (h->inf_k > 0) return fail("sampling is defined on finite graphs (src/sampling.jl iterates the nodes of bp.g)");
+  CUDA_OK(cudaSetDevice(h->device));
+  std::vector<SampCls> sc(std::max<size_t>(h->classes.size(), 1));
+  for (size_t ci = 0; ci < h->classes.size(); ++ci) {
+    const NodeClass& c = h->classes[ci];
+    SampCls& o = sc[ci];
+    memset(&o, 0, sizeof o);
+    if (c.z > SAMP_MAXZ) return fail("sampler supports degrees up to %d", SAMP_MAXZ);
+    o.z = c.z;
+    o.q = c.q;
+    o.generic = c.generic ? 1 : 0;
+    for (int k = 0; k < c.z; ++k) o.qn[k] = c.qn[k];
+    o.wd = c.d_wd;
+    o.wd_ts = (long long)c.wd_ts;
+    if (c.generic) continue;
+    for (int l = 0; l <= c.z; ++l) {
+      if (c.ny[l] > SAMP_MAXNY) return fail("sampler supports nstates up to %d", SAMP_MAXNY);
+      o.ny[l] = c.ny[l];
+    }
+    o.pxy = c.d_pxy;
+    o.pxy_ts = (long long)c.pxy_ts;
+    for (int k = 0; k < c.z; ++k) o.pxy_off[k] = (long long)c.pxy_off[k];
+    o.pyy = c.d_pyy;
+    for (int k = 1; k <= c.z; ++k) {
+      const std::pair<int, int> key = k < c.z ? std::make_pair(k, 1) : std::make_pair(c.z, 0);
+      auto it = c.pyy.find(key);
+      if (it == c.pyy.end()) return fail("class %zu lacks the prob_yy table for (%d,%d)", ci, key.first, key.second);
+      o.pyy_off[k] = (long long)it->second.first;
+      o.pyy_ts[k] = (long long)it->second.second;
+    }
+    o.minit = c.d_minit;
+    o.minit_ts = (long long)c.minit_ts;
+  }
+  SampCls* d_sc = nullptr;
+  int* d_cls = nullptr;
+  int64_t *d_colptr = nullptr, *d_dst = nullptr;
+  int* d_X = nullptr;
+  struct Guard {
+    std::vector<void*> p;
+    ~Guard() { for (void* q : p) cudaFree(q); }
+  } guard;
+  if (upload(&d_sc, sc.data(), sc.size())) return 1;
+  guard.p.push_back(d_sc);
+  if (upload(&d_cls, h->class_of_node.data(), (size_t)h->N)) return 1;
+  guard.p.push_back(d_cls);
+  if (upload(&d_colptr, h->colptr.data(), (size_t)h->N + 1)) return 1;
+  guard.p.push_back(d_colptr);
+  if (upload(&d_dst, h->dst.data(), (size_t)h->E2)) return 1;
+  guard.p.push_back(d_dst);
+  CUDA_OK(cudaMalloc((void**)&d_X, sizeof(int) * (size_t)h->N * h->L));
+  guard.p.push_back(d_X);
+  const unsigned nb = (unsigned)((h->N + 127) / 128);
+  for (int t = -1; t < h->T; ++t) {
+    k_sample_step<<<nb, 128, 0, h->st>>>(d_sc, d_cls, d_colptr, d_dst, h->d_phi, h->d_marg_off, h->d_q, (long long)h->N, h->L, t, seed,
+                                         d_X, h->d_err);
+    h->n_launch++;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->st));
+  if (check_err(h)) return 1;
+  CUDA_OK(cudaMemcpy(X, d_X, sizeof(int) * (size_t)h->N * h->L, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int64_t mpbp_message_slot_bytes(mpbp_handle h) {
   if (!h) return 0;
   // data + bonds + ls, padded to 8 bytes

@@ -1980,6 +1980,126 @@ __global__ void __launch_bounds__(NT) k_alt_marginal(const PairJob* jobs, int L,
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward sampler of the prior dynamics (reference onesample!, src/sampling.jl:30-59): x_i^0 ~ phi_i^0 / sum,
+// x_i^{t+1} ~ w_i^t(. | x_{di}^t, x_i^t).  The transition probability of a RecursiveBPFactor is evaluated from the class
+// tables exactly as the factor's functor does (src/recursive_bp_factor.jl:34-46), folding the neighbours in cavity order:
+// P_1 = Pxy_1, P_{k+1} = Pyy(k,1)[P_k, Pxy_{k+1}], P_full = Pyy(z,0)[P_z, Minit], p(x') = sum_y Wd[x',x,y] P_full[y];
+// a generic BPFactor indexes its dense table with the joint neighbour state.  One thread per node, one launch per time
+// step.  Counter-based RNG (splitmix64 of (seed, node, time)) and no FMA contraction, so the oracle's restatement
+// reproduces the trajectory bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int SAMP_MAXZ = 32;
+constexpr int SAMP_MAXNY = 64;
+struct SampCls {
+  int z, q, generic;
+  int ny[SAMP_MAXZ + 1];
+  int qn[SAMP_MAXZ];
+  const double* pxy;
+  long long pxy_ts, pxy_off[SAMP_MAXZ];
+  const double* pyy;
+  long long pyy_off[SAMP_MAXZ + 1], pyy_ts[SAMP_MAXZ + 1];  // [k] : pair (k,1) for 1 <= k < z ; [z] : pair (z,0)
+  const double* wd;
+  long long wd_ts;
+  const double* minit;
+  long long minit_ts;
+};
+__host__ __device__ inline double samp_uniform(unsigned long long seed, long long i, int t) {
+  unsigned long long zz = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(t + 2);
+  zz = (zz ^ (zz >> 30)) * 0xBF58476D1CE4E5B9ull;
+  zz = (zz ^ (zz >> 27)) * 0x94D049BB133111EBull;
+  zz = zz ^ (zz >> 31);
+  return (double)(zz >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ inline int samp_draw(const double* p, int q, double u) {
+  double S = 0.0;
+  for (int x = 0; x < q; ++x) S = __dadd_rn(S, p[x]);
+  double c = 0.0;
+  for (int x = 0; x < q; ++x) {
+    c = __dadd_rn(c, __ddiv_rn(p[x], S));
+    if (u < c) return x;
+  }
+  return q - 1;
+}
+// t < 0: initial condition; else step t -> t+1.  X[i*L + t], states 0-based.
+__global__ void k_sample_step(const SampCls* cls, const int* class_of_node, const int64_t* colptr, const int64_t* dst, const double* phi,
+                              const int64_t* phi_off, const int* qarr, long long N, int L, int t, unsigned long long seed, int* X, int* err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int q = qarr[i];
+  double p[8];
+  if (t < 0) {
+    for (int x = 0; x < q; ++x) p[x] = phi[phi_off[i] + x];
+    X[i * L] = samp_draw(p, q, samp_uniform(seed, i, -1));
+    return;
+  }
+  const int ci = class_of_node[i];
+  if (ci < 0) { atomicOr(err, ERR_NAN); return; }
+  const SampCls& c = cls[ci];
+  const int x = X[i * L + t];
+  const int64_t e0 = colptr[i];
+  if (c.generic) {
+    long long yall = 0, mul = 1;
+    for (int k = 0; k < c.z; ++k) {
+      yall += mul * X[dst[e0 + k] * L + t];
+      mul *= c.qn[k];
+    }
+    const double* wd = c.wd + (size_t)t * c.wd_ts;
+    for (int xn = 0; xn < q; ++xn) p[xn] = wd[xn + q * (x + (size_t)q * yall)];
+  } else {
+    double P[SAMP_MAXNY], Pn[SAMP_MAXNY];
+    const double* minit = c.minit + (size_t)t * c.minit_ts;
+    const int ny0 = c.ny[0], ny1 = c.ny[1];
+    int nycur;
+    if (c.z == 0) {
+      nycur = ny0;
+      for (int y = 0; y < ny0; ++y) P[y] = minit[y + ny0 * x];
+    } else {
+      const double* pxy_t = c.pxy + (size_t)t * c.pxy_ts;
+      {
+        const int xk = X[dst[e0] * L + t];
+        const double* px = pxy_t + c.pxy_off[0];
+        for (int y = 0; y < ny1; ++y) P[y] = px[y + ny1 * (xk + c.qn[0] * x)];
+        nycur = ny1;
+      }
+      for (int k = 1; k < c.z; ++k) {
+        const int xk = X[dst[e0 + k] * L + t];
+        const double* px = pxy_t + c.pxy_off[k];
+        const double* pyy = c.pyy + c.pyy_off[k] + (size_t)t * c.pyy_ts[k];
+        const int nyn = c.ny[k + 1];
+        for (int y = 0; y < nyn; ++y) {
+          double acc = 0.0;
+          for (int y1 = 0; y1 < nycur; ++y1)
+            for (int y2 = 0; y2 < ny1; ++y2)
+              acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(pyy[y + nyn * (y1 + nycur * (y2 + ny1 * x))], P[y1]), px[y2 + ny1 * (xk + c.qn[k] * x)]));
+          Pn[y] = acc;
+        }
+        for (int y = 0; y < nyn; ++y) P[y] = Pn[y];
+        nycur = nyn;
+      }
+      // full = op(p[z-1], init): pair (z, 0)
+      const double* pyy = c.pyy + c.pyy_off[c.z] + (size_t)t * c.pyy_ts[c.z];
+      const int nyz = c.ny[c.z];
+      for (int y = 0; y < nyz; ++y) {
+        double acc = 0.0;
+        for (int y1 = 0; y1 < nycur; ++y1)
+          for (int y0 = 0; y0 < ny0; ++y0)
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(pyy[y + nyz * (y1 + nycur * (y0 + ny0 * x))], P[y1]), minit[y0 + ny0 * x]));
+        Pn[y] = acc;
+      }
+      for (int y = 0; y < nyz; ++y) P[y] = Pn[y];
+      nycur = nyz;
+    }
+    const double* wd = c.wd + (size_t)t * c.wd_ts;
+    for (int xn = 0; xn < q; ++xn) {
+      double acc = 0.0;
+      for (int y = 0; y < nycur; ++y) acc = __dadd_rn(acc, __dmul_rn(wd[xn + q * (x + q * y)], P[y]));
+      p[xn] = acc;
+    }
+  }
+  X[i * L + t + 1] = samp_draw(p, q, samp_uniform(seed, i, t));
+}
+
+// ------------------------------------------------------------------------------------------------
 // Minit TT: [1,1,y,x] = prob_y0 per t
 struct InitJob {
   TTRef out;

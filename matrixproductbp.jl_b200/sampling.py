@@ -1,6 +1,7 @@
-"""Host-side forward sampler and observation drawing (reference: src/sampling.jl:30-66,191-210).
+"""Observation drawing and a host-side forward sampler (reference: src/sampling.jl:30-66,191-210).
 
-Pure numpy, no device: these build INPUTS (reweightings phi) for an inference run, they are not on the hot path.
+The API's `onesample` / `draw_node_observations_` draw the trajectory ON THE DEVICE (mpbp_sample_prior); the numpy `onesample`
+below evaluates the factors' functors on the host and only serves the CPU-only checks of the factor definitions.
 `onesample` draws a trajectory from the prior dynamics and returns it with its likelihood weight, exactly like the
 reference's `onesample!`; `draw_node_observations_` turns entries of a trajectory into (soft) one-hot reweightings.
 States are numbered from 1, as in the reference."""

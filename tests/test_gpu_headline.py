@@ -262,3 +262,58 @@ def test_generic_path_compresses_the_dummy_neighbour_message():
     O.iterate(bo2, maxiter=3, trunc=OT.TruncBond(16), tol=0.0)
     diff = max(float(np.max(np.abs(np.array(a) - np.array(b)))) for a, b in zip(O.beliefs(bo), O.beliefs(bo2)))
     assert diff > 100 * TOL
+
+
+def test_device_forward_sampler_matches_oracle_bitwise_and_feeds_observations():
+    """mpbp_sample_prior (src/sampling.jl:30-59 on the device): trajectories equal the oracle's restatement (same
+    counter-based uniforms, same arithmetic order) entry by entry for Glauber, SIRS and a generic factor on a loopy graph
+    with mixed degrees; draw_node_observations_ turns them into hard one-hot reweightings; and the empirical one-time
+    marginals of many device samples approach the exact ones."""
+    from oracle import factors as OF, sampling as OS
+    T = 6
+    und = [(0, 1), (1, 2), (2, 0), (2, 3), (3, 4), (4, 5), (5, 3), (1, 5)]
+    N = 7  # node 6 is isolated
+    cases = [
+        ("glauber", lambda F: F.HomogeneousGlauberFactor(0.7, 0.2, 1.0), 2, [0.3, 0.7]),
+        ("sirs", lambda F: F.SIRSFactor(0.4, 0.2, 0.15), 3, [0.6, 0.4, 0.0]),
+        ("generic", lambda F: F.GenericFactor(F.HomogeneousGlauberFactor(0.5, -0.1, 1.0)), 2, [0.5, 0.5]),
+    ]
+    for name, mk, q, p0 in cases:
+        und_c = und if name != "generic" else und[:5]  # a generic BPFactor needs degree >= 1: drop the isolated node
+        Nc = N if name != "generic" else 5
+        go = O.BiDiGraph(Nc, und_c)
+        gd = M.IndexedBiDiGraph(Nc, und_c)
+        wo = [[mk(OF)] * (T + 1) for _ in range(Nc)]
+        wd = [[mk(M)] * (T + 1) for _ in range(Nc)]
+        phi = [[np.array(p0) if t == 0 else np.ones(q) for t in range(T + 1)] for _ in range(Nc)]
+        bo = O.MPBP(go, wo, [q] * Nc, T, phi=[[p.copy() for p in ph] for ph in phi])
+        bd = M.mpbp(gd, wd, [q] * Nc, T, phi=[[p.copy() for p in ph] for ph in phi], dmax=4)
+        for seed in (1, 2, 12345678901234567):
+            Xo, _ = OS.sample_prior(bo, seed)
+            Xd = M.sample_prior(bd, seed)
+            assert np.array_equal(Xo, Xd), (name, seed)
+    # observations from a device sample
+    go = O.BiDiGraph(N, und)
+    gd = M.IndexedBiDiGraph(N, und)
+    fac = M.SIRSFactor(0.4, 0.2, 0.15)
+    phi = [[np.array([0.6, 0.4, 0.0]) if t == 0 else np.ones(3) for t in range(T + 1)] for _ in range(N)]
+    bd = M.mpbp(gd, [[fac] * (T + 1)] * N, [3] * N, T, phi=phi, dmax=4)
+    X, observed = M.draw_node_observations_(bd, 5, rng=3)
+    assert X.shape == (N, T + 1) and X.min() >= 1 and X.max() <= 3 and len(observed) == 5
+    for (i, t) in observed:
+        assert np.count_nonzero(bd.phi[i][t]) <= 1 and (t == 0 or bd.phi[i][t][X[i, t] - 1] == 1.0)
+    # statistics: empirical marginals of 4000 device samples vs exact enumeration on a small tree
+    T2, N2 = 3, 4
+    und2 = [(0, 1), (1, 2), (1, 3)]
+    phi2 = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T2 + 1)] for _ in range(N2)]
+    bd2 = M.mpbp(M.IndexedBiDiGraph(N2, und2), [[M.HomogeneousGlauberFactor(0.8, 0.1, 1.0)] * (T2 + 1)] * N2, [2] * N2, T2, phi=phi2, dmax=4)
+    cnt = np.zeros((N2, T2 + 1, 2))
+    ns = 4000
+    for s_ in range(ns):
+        Xs = M.sample_prior(bd2, 1000 + s_)
+        for i in range(N2):
+            cnt[i, np.arange(T2 + 1), Xs[i]] += 1
+    emp = cnt / ns
+    M.iterate_(bd2, maxiter=5, svd_trunc=M.TruncThresh(0.0), tol=0.0, shuffle_nodes=False)  # exact on a tree: beliefs = marginals
+    b = M.beliefs(bd2)
+    assert max(float(np.max(np.abs(emp[i] - b[i]))) for i in range(N2)) < 0.04
