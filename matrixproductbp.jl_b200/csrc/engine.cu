@@ -113,6 +113,8 @@ struct mpbp_state {
   double hub_frac = 0.3;     // share of the chunk's cost the hub lane may take
   cudaStream_t hub_st = nullptr;
   cudaEvent_t ev_hub_fork = nullptr, ev_hub_join = nullptr;
+  double svd_mode = 0;       // 0: squared Jacobi block iteration when the block fits shared memory (else Householder), 1: always the
+                             // un-squared Householder variant
   double tri_merge = 1;      // 1: the TSQR merge skips the zero panels of the stacked triangular chunk factors
   double kron_mma = 1;       // 1: DMMA Kronecker-carry kernel (k_kron_carry_mma), 0: scalar FP64 kernel (k_kron_carry)
   double outlier_split = 0;  // > 0: ops costing more than this multiple of the mean of their launch group run in a
@@ -177,7 +179,13 @@ int common_init(mpbp_state* h) {
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
   }
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  CUDA_OK(cudaStreamCreateWithFlags(&h->hub_st, cudaStreamNonBlocking));
+  {
+    // highest priority: the hub lane is the critical path of a step; its (few, small) launches must get the SMs that the
+    // bulk kernels free, ahead of the bulk's own queued CTAs
+    int lo = 0, hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&h->hub_st, cudaStreamNonBlocking, hi));
+  }
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_hub_fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_hub_join, cudaEventDisableTiming));
   CUDA_OK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -817,9 +825,7 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
       return fail("bond capacity %d / nstates %d exceed the shared-memory tiling of the contraction kernels", d, g.maxNy);
     g.kc_mma_rb = 0;
     if (h->kron_mma > 0) {
-      // prefer two CTAs per SM (the A fragments come from L1/L2: latency hiding), else the widest tile that fits
-      for (int rb : {16, 8, 4})
-        if (!g.kc_mma_rb && kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS) * 8 <= (size_t)h->max_smem / 2) g.kc_mma_rb = rb;
+      // the widest tile that fits (the kernel keeps its A fragments and 4 n-tiles of accumulators in registers: one CTA per SM)
       for (int rb : {16, 8, 4})
         if (!g.kc_mma_rb && kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS) * 8 <= (size_t)h->max_smem) g.kc_mma_rb = rb;
     }
@@ -889,7 +895,7 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
         else k_qr_small<16><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
         ev_end(h, g.st);
         ev_begin(h, F_JAC, g.st);
-        k_jacobi_project<<<g.nops, NT, jac_smem, g.st>>>(g.d_ops, t, tr, d, (int)jac_doubles, h->d_err, h->d_flops + 1);
+        k_jacobi_project<<<g.nops, NT, jac_smem, g.st>>>(g.d_ops, t, tr, d, (int)jac_doubles, h->d_err, h->d_flops + 1, (int)h->svd_mode);
         ev_end(h, g.st);
         h->n_launch += 3;
       } else {
@@ -2042,6 +2048,7 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "kron_mma") h->kron_mma = value;
   else if (n == "hub_lane") h->hub_lane = value;
   else if (n == "tri_merge") h->tri_merge = value;
+  else if (n == "svd_mode") h->svd_mode = value;
   else if (n == "hub_frac") h->hub_frac = value;
   else if (n == "twovar") {
     // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
@@ -2131,7 +2138,7 @@ int mpbp_test_qr_ft(const double* A, int batch, int m, int n, int H, double* R, 
   return 0;
 }
 __global__ void __launch_bounds__(NT) k_test_svd(const double* M, int p, int n, Trunc tr, int jac_doubles, double* scratch,
-                                                 size_t scratch_per, double* U, double* S, int* err, double* stats) {
+                                                 size_t scratch_per, double* U, double* S, int* err, double* stats, int mode) {
   extern __shared__ double smem_tsvd[];
   double* smem = smem_tsvd;
   __shared__ int flag, s_done;
@@ -2146,7 +2153,7 @@ __global__ void __launch_bounds__(NT) k_test_svd(const double* M, int p, int n, 
     __syncthreads();
     qr_ft_cta<16>(Mcopy, n, p, p, R2, p, false, smem);  // M^T (n x p row-major == M col-major) -> R (p x p)
   }
-  const SvdLeft sv = svd_left_cta(Mb, R2, svdscr, p, n, tr, tr.d, jac_doubles, smem, &flag, &s_done, red, err, stats);
+  const SvdLeft sv = svd_left_cta(Mb, R2, svdscr, p, n, tr, tr.d, jac_doubles, smem, &flag, &s_done, red, err, stats, mode);
   const double* sig = smem;
   const int* order = reinterpret_cast<const int*>(smem + SUB_BMAX);
   const int keep = min(tr.d, sv.ceff);
@@ -2184,7 +2191,8 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
   for (int rep = 0; rep < 3; ++rep) {
     CUDA_OK(cudaMemset(dst, 0, sizeof(double) * 16));
     cudaEventRecord(e0);
-    k_test_svd<<<batch, NT, (size_t)maxs>>>(dM, p, n, tr, (int)jac_doubles, dscr, per, dU, dS, derr, dst);
+    k_test_svd<<<batch, NT, (size_t)maxs>>>(dM, p, n, tr, (int)jac_doubles, dscr, per, dU, dS, derr, dst,
+                                            getenv("MPBP_SVD_MODE") ? atoi(getenv("MPBP_SVD_MODE")) : 0);
     cudaEventRecord(e1);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventSynchronize(e1));

@@ -15,6 +15,7 @@
 #include "qr.cuh"
 #include "qr_ft.cuh"
 #include "svd_block.cuh"
+#include "svd_squared.cuh"
 
 namespace mpbp {
 
@@ -301,10 +302,20 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
   }
   __syncthreads();
   // ---------------- stage 1 ----------------
+  // A fragments (the operand site, a few KB in L1/L2) are hoisted into registers per auxiliary state: the inner loops
+  // then issue one shared-memory B-fragment load per m-tile group of DMMAs.
   const int mtS = (blS + 7) >> 3, ksS = (brS + 3) >> 2;
   const int ncol1 = brF * RB, nt1 = (ncol1 + 7) >> 3;
   for (int yS = 0; yS < nyS; ++yS) {
     const double* Sy = Sd + (size_t)blS * brS * (yS + nyS * x);
+    double af[4][8];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int mr = 8 * mt + g, kB = 4 * ks + q4;
+        af[mt][ks] = (mr < blS && kB < brS) ? Sy[mr + blS * kB] : 0.0;
+      }
     for (int nt = warp; nt < nt1; nt += NW) {
       const int cB = 8 * nt + g;                       // B-fragment column of this lane
       const bool cBok = cB < ncol1;
@@ -312,16 +323,14 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
       double acc[4][2];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
-      for (int ks = 0; ks < ksS; ++ks) {
-        const int kB = 4 * ks + q4;
-        const double bf = (cBok && kB < brS) ? Lc[boff + kB * sLS] : 0.0;
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          if (mt < mtS) {
-            const int mr = 8 * mt + g;
-            const double af = (mr < blS && kB < brS) ? Sy[mr + blS * kB] : 0.0;
-            dmma884(acc[mt][0], acc[mt][1], af, bf);
-          }
+      for (int ks = 0; ks < 8; ++ks) {
+        if (ks < ksS) {
+          const int kB = 4 * ks + q4;
+          const double bf = (cBok && kB < brS) ? Lc[boff + kB * sLS] : 0.0;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+            if (mt < mtS) dmma884(acc[mt][0], acc[mt][1], af[mt][ks], bf);
         }
       }
       // C tile: rows mS = 8mt+g, columns c0, c0+1
@@ -349,46 +358,71 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
   const int mtF = (blF + 7) >> 3, ksF = (brF + 3) >> 2;
   const int ncol2 = blS * RB, nt2 = (ncol2 + 7) >> 3;
   const size_t pyx = (size_t)nyo * ny1 * ny2 * x;
+  constexpr int TG = 4;  // n-tiles a warp carries at once (their accumulators persist across the (y_S, y_F) pairs)
   for (int y = 0; y < nyo; ++y) {
-    for (int nt = warp; nt < nt2; nt += NW) {
-      const int cB = 8 * nt + g;
-      const bool cBok = cB < ncol2;
-      const int uB = cBok ? cB / blS : 0, mSB = cBok ? cB % blS : 0;  // column (mS, u), mS fastest
-      double acc[4][2];
+    for (int ntb = warp; ntb < nt2; ntb += NW * TG) {
+      int zoff[TG];
+      bool cok[TG];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+      for (int j = 0; j < TG; ++j) {
+        const int cB = 8 * (ntb + NW * j) + g;
+        cok[j] = (ntb + NW * j < nt2) && cB < ncol2;
+        zoff[j] = cok[j] ? ((cB / blS) * brF) * ZP + (cB % blS) : 0;  // column (mS, u), mS fastest; + (yS*RB*brF + kB)*ZP
+      }
+      double acc[TG][4][2];
+#pragma unroll
+      for (int j = 0; j < TG; ++j)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) acc[j][mt][0] = acc[j][mt][1] = 0.0;
       for (int yS = 0; yS < nyS; ++yS) {
-        const double* zb = Z + ((size_t)(yS * RB + uB) * brF) * ZP + mSB;
+        const double* zy = Z + (size_t)yS * RB * brF * ZP;
         for (int yF = 0; yF < nyF; ++yF) {
           const double pv = pyy[y + yF * pF + yS * pS + pyx];
           if (pv == 0.0) continue;
           const double* Fy = Fd + (size_t)blF * brF * (yF + nyF * x);
-          for (int ks = 0; ks < ksF; ++ks) {
-            const int kB = 4 * ks + q4;
-            const double bf = (cBok && kB < brF) ? zb[(size_t)kB * ZP] : 0.0;
+          double af[4][8];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-              if (mt < mtF) {
-                const int mr = 8 * mt + g;
-                const double af = (mr < blF && kB < brF) ? pv * Fy[mr + blF * kB] : 0.0;
-                dmma884(acc[mt][0], acc[mt][1], af, bf);
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const int mr = 8 * mt + g, kB = 4 * ks + q4;
+              af[mt][ks] = (mr < blF && kB < brF) ? pv * Fy[mr + blF * kB] : 0.0;
+            }
+#pragma unroll
+          for (int j = 0; j < TG; ++j) {
+            if (ntb + NW * j < nt2) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                if (ks < ksF) {
+                  const int kB = 4 * ks + q4;
+                  const double bf = (cok[j] && kB < brF) ? zy[zoff[j] + (size_t)kB * ZP] : 0.0;
+#pragma unroll
+                  for (int mt = 0; mt < 4; ++mt)
+                    if (mt < mtF) dmma884(acc[j][mt][0], acc[j][mt][1], af[mt][ks], bf);
+                }
               }
             }
           }
         }
       }
-      const int c0 = 8 * nt + 2 * q4;
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        if (mt < mtF) {
-          const int mF = 8 * mt + g;
-          if (mF < blF) {
+      for (int j = 0; j < TG; ++j) {
+        const int nt = ntb + NW * j;
+        if (nt < nt2) {
+          const int c0 = 8 * nt + 2 * q4;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = c0 + e;
-              if (c < ncol2) {
-                const int u = c / blS, mS = c % blS;
-                if (u < nb) op.M[(size_t)(mF * sOF + mS * sOS) + (size_t)Dl * (rr0 + u + (size_t)rn * (y + nyo * x))] = acc[mt][e];
+          for (int mt = 0; mt < 4; ++mt) {
+            if (mt < mtF) {
+              const int mF = 8 * mt + g;
+              if (mF < blF) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int c = c0 + e;
+                  if (c < ncol2) {
+                    const int u = c / blS, mS = c % blS;
+                    if (u < nb) op.M[(size_t)(mF * sOF + mS * sOS) + (size_t)Dl * (rr0 + u + (size_t)rn * (y + nyo * x))] = acc[j][mt][e];
+                  }
+                }
               }
             }
           }
@@ -582,9 +616,6 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_small(const OpDesc
 //                    Z = orth(M^T Q),  Y = M Z = Q R,  Ritz values = singular values of the b x b factor R
 //                  with b <= 64 columns: DMMA GEMMs, Householder orthonormalisation of the blocks, Jacobi only on R.
 //                  Converges like (sigma_{b+1}/sigma_k)^2 per iteration; validated against exact SVDs in the tests.
-constexpr int SUB_BMAX = 64;   // storage bound of the block
-constexpr int SUB_BLOCK = 48;  // block width used (>= 2d+8 at d = 20): convergence ~ (sigma_{b+1}/sigma_k)^2
-constexpr int SUB_MAXIT = 60;
 __host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles) {
   const int c = p < n ? p : n;
   return c <= SUB_BMAX && (long long)p * c <= jac_doubles;
@@ -616,7 +647,7 @@ struct SvdLeft {
 };
 __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, double* scratch, const int p, const int rn, const Trunc tr,
                                        const int dcap, const int jac_doubles, double* smem, int* flagp, int* s_donep, double* red,
-                                       int* err, double* stats) {
+                                       int* err, double* stats, const int mode = 0) {
   int& flag = *flagp;
   int& s_done = *s_donep;
   const int c = min(p, rn);
@@ -637,6 +668,14 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
     if (sweeps >= JACOBI_MAX_SWEEPS && threadIdx.x == 0) atomicOr(err, ERR_JACOBI_NOCONV);
     jacobi_sort(A, p, ceff, p, sig, order);
     normalize_cols(A, p, ceff, p, sig);
+  } else if (mode == 0 && (long long)max(p, rn) * (min(min(max(SUB_BLOCK, min(SUB_BMAX, 2 * (tr.kind == 1 ? dcap : tr.d) + 8)), c), SUB_BMAX) & ~7) <= jac_doubles) {
+    // the full-width block fits shared memory: squared iteration with Jacobi orthonormalisation (svd_squared.cuh)
+    const size_t mx8 = (size_t)max(p, rn) + 8;
+    int b = 0;
+    nrm2_all = svd_subspace_squared(Mcm, scratch + SUB_BMAX * mx8, scratch, scratch + 3 * SUB_BMAX * mx8, p, rn, tr, dcap, jac_doubles, sig,
+                                    order, sprev, W, flagp, s_donep, red, err, stats, &b);
+    A = W;
+    ceff = b;
   } else {
     const int n = rn;
     const double* M = Mcm;  // column-major p x n
@@ -816,7 +855,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
 // truncated SVD (left vectors) of M2 (dX x r), output site, new carry Pc_t = U^T G_t (rescaled).
 // dyn smem: [sig 64][order 64 ints][sprev 64][W : jac_doubles]
 __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t, Trunc tr, int dcap, int jac_doubles,
-                                                       int* err, double* stats) {
+                                                       int* err, double* stats, int svd_mode) {
   extern __shared__ double smem[];
   __shared__ int flag;
   __shared__ int s_keep;
@@ -834,7 +873,7 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
   int* order = reinterpret_cast<int*>(smem + SUB_BMAX);
   // global scratch of the subspace path: the tall sweep-1 matrix op.M is dead during sweep 2 (D^2 X doubles >= what is needed
   // whenever the subspace path can occur, i.e. min(p, n) > 64)
-  const SvdLeft sv = svd_left_cta(op.M2T, op.R2, op.M, p, rn, tr, dcap, jac_doubles, smem, &flag, &s_done, red, err, stats);
+  const SvdLeft sv = svd_left_cta(op.M2T, op.R2, op.M, p, rn, tr, dcap, jac_doubles, smem, &flag, &s_done, red, err, stats, svd_mode);
   double* A = sv.A;
   const int ceff = sv.ceff;
   const double nrm2_all = sv.nrm2_all;

@@ -40,14 +40,29 @@ __host__ __device__ inline int ft_ld(int n) {
 __device__ __forceinline__ int ft_sw(int row) { return ((row >> 1) & 1) << 2; }
 template <int H>
 __host__ __device__ inline size_t ft_smem_doubles(int n) {
-  return (size_t)H * ft_ld(n) + 2 * (FT_B * (H + 4) + FT_B * FT_B) + NW * 72 + 16;
+  return (size_t)H * ft_ld(n) + 2 * (FT_B * (H + 4) + FT_B * FT_B) + NW * 72 + 16 + (H == 64 ? 2 * 128 : 0);
+}
+
+// H = 64: the otherwise idle partner warp of the panel warp stages, one panel ahead, the two 8x8 blocks of R the panel
+// warp needs first in its serial chain -- R_{j,j+1} (look-ahead slab update) and R_{j+1,j+1} (panel factorisation) --
+// from global/L2 into shared memory, so that their load latency leaves the critical path.
+// dst[0..63] = R[8 jpt + r, 8 (jpt+1) + c], dst[64..127] = R[8 (jpt+1) + r, 8 (jpt+1) + c], zero outside the matrix.
+__device__ __forceinline__ void ft_prefetch_R(const double* __restrict__ R, const int ldr, const int n, const int jpt, double* dst) {
+  const int lane = threadIdx.x & 31;
+  const int j0 = jpt * FT_B, c0 = j0 + FT_B;
+#pragma unroll
+  for (int e = lane; e < 128; e += 32) {
+    const int r = (e >> 3) & 7, c = e & 7;
+    const int row = ((e >> 6) ? c0 : j0) + r, col = c0 + c;
+    dst[e] = (row < n && col < n) ? R[(size_t)row * ldr + col] : 0.0;
+  }
 }
 
 // Householder factorisation of [R_jj ; Ablk[:, j0..j0+8)] by ONE warp.  Writes V^T (A part) to Vt (8 x LDV), the
 // compact-WY T (8x8) to Tm, the new R_jj block to global R.
 template <int H>
 __device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const int j0, const int n, double* __restrict__ R,
-                                         const int ldr, double* Vt, double* Tm) {
+                                         const int ldr, double* Vt, double* Tm, const double* rjj_s = nullptr) {
   constexpr int LDV = H + 4;
   constexpr int RPL = (H + 31) / 32;  // rows of the block per lane
   const int lane = threadIdx.x & 31;
@@ -61,8 +76,10 @@ __device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const
   // R_jj (8x8 upper) preloaded once: lane k holds row j0+k; rows are broadcast with shuffles
   double rrow[FT_B];
 #pragma unroll
-  for (int c = 0; c < FT_B; ++c)
-    rrow[c] = (lane < FT_B && j0 + lane < n && j0 + c < n && c >= lane) ? R[(size_t)(j0 + lane) * ldr + j0 + c] : 0.0;
+  for (int c = 0; c < FT_B; ++c) {
+    if (rjj_s) rrow[c] = (lane < FT_B && c >= lane) ? rjj_s[lane * FT_B + c] : 0.0;  // staged by ft_prefetch_R (zero padded)
+    else rrow[c] = (lane < FT_B && j0 + lane < n && j0 + c < n && c >= lane) ? R[(size_t)(j0 + lane) * ldr + j0 + c] : 0.0;
+  }
   double T[FT_B][FT_B];
 #pragma unroll
   for (int x = 0; x < FT_B; ++x)
@@ -253,6 +270,8 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
   double* Ablk = smem;                       // H x ld
   double* VT0 = Ablk + (size_t)H * ld;       // 2 x (V^T 8 x LDV, T 8x8)
   double* Ws = VT0 + 2 * VT_SZ + warp * 72;  // per-warp 8x8 scratch (ld 9)
+  constexpr bool PREF = (H == 64);             // warp 4 stages the panel warp's R blocks one panel ahead
+  double* Rst = VT0 + 2 * VT_SZ + NW * 72 + 16;  // 2 x 128 doubles (H = 64 only)
   if (tri_n > 0) {
     for (int idx = tid; idx < n * n; idx += NT) {
       const int i = idx / n, c = idx % n;
@@ -315,6 +334,7 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
     }
     __syncthreads();
     if (warp == 0) ft_panel<H>(Ablk, ld, jp0 * FT_B, n, R, ldr, VT0 + (jp0 & 1) * VT_SZ, VT0 + (jp0 & 1) * VT_SZ + FT_B * LDV);
+    if (PREF && warp == 4 && jp0 + 1 < npanel) ft_prefetch_R(R, ldr, n, jp0, Rst + (jp0 & 1) * 128);
     for (int jp = jp0; jp < npanel; ++jp) {
       const int j0 = jp * FT_B;
       double* Vt = VT0 + (jp & 1) * VT_SZ;
@@ -331,17 +351,22 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
         const int c0 = j0 + FT_B, cc = c0 + 2 * q4;
         const bool ok0 = (rr < n) && (cc < n), ok1 = (rr < n) && (cc + 1 < n);
         double* rp = R + (size_t)rr * ldr + cc;
-        const double r0 = ok0 ? rp[0] : 0.0, r1 = ok1 ? rp[1] : 0.0;
+        const double* rs = Rst + (jp & 1) * 128;
+        const double r0 = PREF ? rs[g * FT_B + 2 * q4] : (ok0 ? rp[0] : 0.0);
+        const double r1 = PREF ? rs[g * FT_B + 2 * q4 + 1] : (ok1 ? rp[1] : 0.0);
         ft_update_slab<H>(Ablk, ld, c0, f, Ws, rp, ok0, ok1, r0, r1);
         __syncwarp();
-        ft_panel<H>(Ablk, ld, c0, n, R, ldr, Vtn, Vtn + FT_B * LDV);
+        ft_panel<H>(Ablk, ld, c0, n, R, ldr, Vtn, Vtn + FT_B * LDV, PREF ? rs + 64 : nullptr);
       } else {
         // slabs 1 .. nslab-1 over the updating warps.  With H = 64 (one CTA per SM) warp 4, which shares the SM
         // sub-partition and its FP64 pipe with the panel warp, sits out: the step is bound by the panel's dependent
         // FP64 chain, which must not queue behind DMMAs (measured +7 % on isolated 1600..4000 x 400 batches).
         constexpr bool IDLE = (H == 64);
         constexpr int NUPD = IDLE ? NW - 2 : NW - 1;
-        if (IDLE && warp == 4) continue;
+        if (IDLE && warp == 4) {
+          if (PREF && jp + 2 < npanel) ft_prefetch_R(R, ldr, n, jp + 1, Rst + ((jp + 1) & 1) * 128);
+          continue;
+        }
         int sl = (!IDLE || warp < 4) ? warp : warp - 1;
         double nr0 = 0.0, nr1 = 0.0;
         if (sl < nslab && rr < n) {

@@ -15,6 +15,10 @@
 
 namespace mpbp {
 
+constexpr int SUB_BMAX = 64;   // storage bound of the block of the subspace iterations
+constexpr int SUB_BLOCK = 48;  // block width used (>= 2d+8 at d = 20): convergence ~ (sigma_{b+1}/sigma_k)^2
+constexpr int SUB_MAXIT = 60;
+
 // leading dimension == 4 (mod 8): the DMMA B-fragment loads (lane (g,q4) reads B[q4 + ld*g]) then hit 16 distinct
 // 8-byte bank pairs per half-warp (2 wavefronts for 256 bytes = the minimum)
 __host__ __device__ inline int blk_ld(int rows) { return rows + ((12 - (rows & 7)) & 7); }
@@ -220,6 +224,178 @@ __device__ inline void hh_orth(double* W, const int rows, const int b, const int
     for (int i = threadIdx.x; i < rows; i += NT) ck[i] = i < k ? 0.0 : (i == k ? 1.0 - tau : -ts * ck[i]);
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cholesky-QR2 orthonormalisation of the rows x b block W (column-major, ld) in shared memory, with the Householder
+// routine above as the unconditional fallback:
+//   1. scale every column to unit norm (D);  2. G = W^T W (DMMA, both operands from the block);  3. G = R^T R (Cholesky,
+//   one warp, b x b in shared memory);  4. W <- W R^-1 (one thread per row, forward substitution);  repeat 2-4 once.
+// Q is orthonormal to machine precision when cond(W D^-1) < ~1e6: true for the blocks of a subspace iteration once it has
+// started to converge (columns ~ sigma_j v_j: orthogonal up to their scale).  A pivot below 1e-13 (or a zero column) means
+// the block is too ill-conditioned for this route: the caller falls back to hh_orth on the ORIGINAL block, which is why
+// the input is preserved in `backup` (global scratch, rows x b with ld) until the first factorisation succeeded.
+// On success returns true; Rout (b x b column-major, optional) = R2 R1 D, the triangular factor of the input block.
+// G1, G2: shared scratch of b*b doubles each; dsc: b doubles.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ inline void blk_gram_dmma(const double* W, const int rows, const int b, const int ld, double* G) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q4 = lane & 3;
+  const int nt = b >> 3;
+  const int ntile = nt * (nt + 1) / 2;  // upper triangle of tiles (i <= j)
+  for (int tix = warp; tix < ntile; tix += NW) {
+    int ti = 0, rem = tix;
+    while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+    const int tj = ti + rem;
+    const double* ap = W + (size_t)(8 * ti + g) * ld + q4;  // A(i, k) = W[k + ld*i]
+    const double* bp = W + (size_t)(8 * tj + g) * ld + q4;  // B(k, j) = W[k + ld*j]
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    int k = 0;
+    for (; k + 8 <= rows; k += 8) {
+      dmma884(c0, c1, ap[k], bp[k]);
+      dmma884(e0, e1, ap[k + 4], bp[k + 4]);
+    }
+    for (; k < rows; k += 4) {
+      const bool ok = k + q4 < rows;
+      dmma884(c0, c1, ok ? ap[k] : 0.0, ok ? bp[k] : 0.0);
+    }
+    c0 += e0;
+    c1 += e1;
+    const int i = 8 * ti + g, j = 8 * tj + 2 * q4;
+    G[i + (size_t)b * j] = c0;
+    G[i + (size_t)b * (j + 1)] = c1;
+    G[j + (size_t)b * i] = c0;  // mirror (the Cholesky below reads the upper triangle only; kept symmetric for clarity)
+    G[j + 1 + (size_t)b * i] = c1;
+  }
+}
+// in-place upper Cholesky G = R^T R by warp 0 (column-major b x b, upper triangle in/out); *ok_flag = 0 on a pivot <= tol
+__device__ inline void blk_chol_warp(double* G, const int b, const double tol, int* ok_flag) {
+  const int lane = threadIdx.x & 31;
+  if ((threadIdx.x >> 5) != 0) return;
+  for (int k = 0; k < b; ++k) {
+    const double piv = G[k + (size_t)b * k];
+    if (!(piv > tol)) {
+      if (lane == 0) *ok_flag = 0;
+      return;
+    }
+    const double rkk = sqrt(piv), inv = 1.0 / rkk;
+    __syncwarp();
+    if (lane == 0) G[k + (size_t)b * k] = rkk;
+    for (int j = k + 1 + lane; j < b; j += 32) G[k + (size_t)b * j] *= inv;  // row k of R
+    __syncwarp();
+    // trailing update: G[i,j] -= R[k,i] R[k,j] for k < i <= j
+    for (int j = k + 1 + lane; j < b; j += 32) {
+      const double rkj = G[k + (size_t)b * j];
+      for (int i = k + 1; i <= j; ++i) G[i + (size_t)b * j] -= G[k + (size_t)b * i] * rkj;
+    }
+    __syncwarp();
+  }
+}
+// X = R^-1 (upper triangular b x b, column-major, ld b): thread j solves R x = e_j by back substitution
+__device__ inline void blk_tri_inverse(const double* R, const int b, double* X) {
+  for (int j = threadIdx.x; j < b; j += NT) {
+    double* xj = X + (size_t)b * j;
+    for (int i = j + 1; i < b; ++i) xj[i] = 0.0;
+    xj[j] = 1.0 / R[j + (size_t)b * j];
+    for (int i = j - 1; i >= 0; --i) {
+      double acc = 0.0;
+      for (int k = i + 1; k <= j; ++k) acc += R[i + (size_t)b * k] * xj[k];
+      xj[i] = -acc / R[i + (size_t)b * i];
+    }
+  }
+}
+// W <- W X in place (X upper triangular b x b): each warp owns 8-row tiles, reads the whole tile row (b/4 A fragments) into
+// registers before it writes; k-steps above the diagonal of X are skipped.  b <= 64, multiple of 8.
+__device__ inline void blk_trmm_dmma(double* W, const int rows, const int b, const int ld, const double* X) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q4 = lane & 3;
+  const int nt = b >> 3, nks = b >> 2;
+  for (int mt = warp; mt < (rows + 7) / 8; mt += NW) {
+    const int i = 8 * mt + g;
+    const bool ok = i < rows;
+    double af[SUB_BMAX / 4];
+#pragma unroll
+    for (int ks = 0; ks < SUB_BMAX / 4; ++ks) af[ks] = (ok && ks < nks) ? W[i + (size_t)ld * (4 * ks + q4)] : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < SUB_BMAX / 8; ++t) {
+      if (t < nt) {
+        double c0 = 0.0, c1 = 0.0;
+        const double* xp = X + q4 + (size_t)b * (8 * t + g);  // B(k, n) = X[k + b*n]
+#pragma unroll
+        for (int ks = 0; ks < SUB_BMAX / 4; ++ks)
+          if (ks <= 2 * t + 1) dmma884(c0, c1, af[ks], xp[4 * ks]);  // X[k, n] = 0 for k > n: k-steps beyond the tile's columns vanish
+        if (ok) {
+          W[i + (size_t)ld * (8 * t + 2 * q4)] = c0;
+          W[i + (size_t)ld * (8 * t + 2 * q4 + 1)] = c1;
+        }
+      }
+    }
+  }
+}
+// G: shared b*b; Xg: b*b (global scratch is fine); Racc: shared b*b (only touched when want_R); dsc: b doubles
+__device__ inline bool cholqr2_orth(double* W, const int rows, const int b, const int ld, const bool want_R, double* Racc, double* G,
+                                    double* Xg, double* dsc, double* backup, int* s_flag) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  // backup + column norms
+  for (int j = warp; j < b; j += NW) {
+    double s = 0.0;
+    for (int i = lane; i < rows; i += 32) {
+      const double x = W[i + (size_t)ld * j];
+      backup[i + (size_t)ld * j] = x;
+      s += x * x;
+    }
+    s = warp_sum(s);
+    if (lane == 0) dsc[j] = sqrt(s);
+  }
+  if (threadIdx.x == 0) *s_flag = 1;
+  __syncthreads();
+  double dmax = 0.0;
+  for (int j = 0; j < b; ++j) dmax = fmax(dmax, dsc[j]);
+  bool good = dmax > 0.0;
+  for (int j = 0; j < b; ++j) good = good && (dsc[j] > 1e-150 * dmax);
+  if (!good) return false;  // (numerically) zero column: the Householder route handles it; the block is untouched so far
+  for (int j = warp; j < b; j += NW) {
+    const double f = 1.0 / dsc[j];
+    for (int i = lane; i < rows; i += 32) W[i + (size_t)ld * j] *= f;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    blk_gram_dmma(W, rows, b, ld, G);
+    __syncthreads();
+    blk_chol_warp(G, b, pass == 0 ? 1e-13 : 0.5, s_flag);
+    __syncthreads();
+    if (*s_flag == 0) {
+      // too ill-conditioned for the Gram route: restore the input, the caller runs the Householder route
+      for (int j = warp; j < b; j += NW)
+        for (int i = lane; i < rows; i += 32) W[i + (size_t)ld * j] = backup[i + (size_t)ld * j];
+      __syncthreads();
+      return false;
+    }
+    blk_tri_inverse(G, b, Xg);
+    __syncthreads();
+    blk_trmm_dmma(W, rows, b, ld, Xg);
+    __syncthreads();
+    if (want_R) {
+      if (pass == 0) {
+        for (int idx = threadIdx.x; idx < b * b; idx += NT) {
+          const int i = idx % b, j = idx / b;
+          Racc[idx] = i <= j ? G[idx] * dsc[j] : 0.0;  // R1 D
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < b * b; idx += NT) {
+          const int i = idx % b, j = idx / b;
+          double acc = 0.0;
+          if (i <= j)
+            for (int k = i; k <= j; ++k) acc += G[i + (size_t)b * k] * Racc[k + (size_t)b * j];
+          Xg[idx] = acc;  // R2 (R1 D), X is free again
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < b * b; idx += NT) Racc[idx] = Xg[idx];
+      }
+      __syncthreads();
+    }
+  }
+  return true;
 }
 
 }  // namespace mpbp
