@@ -109,7 +109,10 @@ struct mpbp_state {
   double nstreams = 4;
   int twovar = 0;            // > 0: maxdist of the two-time marginals computed with every belief (option "twovar")
   double* d_tv = nullptr;    // [N][L][L][qmax*qmax]
-  double hub_lane = 1;       // 1: high-degree nodes of a chunk run on their own stream (2: also for tiny chunks, tests)
+  double hub_lane = 0;       // 1: high-degree nodes of a chunk run on their own (high-priority) stream (2: also for tiny chunks, tests).
+                             // OFF by default: measured slower (N=256 bench 22.8 s vs 19.0 s per step) -- a hub kernel can only start
+                             // when a bulk CTA retires, and the bulk QR CTAs run for 6-30 ms each, so the ~4500 sequential hub
+                             // launches of a step queue behind them; kept as an option for graphs whose bulk CTAs are short.
   double hub_frac = 0.3;     // share of the chunk's cost the hub lane may take
   cudaStream_t hub_st = nullptr;
   cudaEvent_t ev_hub_fork = nullptr, ev_hub_join = nullptr;
@@ -346,10 +349,15 @@ size_t node_bytes(const mpbp_state* h, int64_t i) {
   return b;
 }
 
+// doubles of the tall sweep-1 matrix M of an op; sweep 2 reuses it as the global scratch of the truncating SVD, so it is at
+// least svd_scratch_doubles(p <= dX, n <= D)
+size_t op_M_doubles(const mpbp_state* h, size_t D, int X) {
+  const size_t d = h->dmax;
+  return std::max(D * X * D, svd_scratch_doubles((int)(d * X), (int)D));
+}
 size_t op_scratch_bytes(const mpbp_state* h, int capA, int capB, int X) {
   const size_t D = (size_t)capA * capB, d = h->dmax, L = h->L;
-  const size_t mrows = D * X;
-  size_t dbl = L * D * D + mrows * D + QR_NSPLIT_MAX * D * D + d * D * X + D * d * X + (d * X) * (d * X) + 2 * d * D;
+  size_t dbl = L * D * D + op_M_doubles(h, D, X) + QR_NSPLIT_MAX * D * D + d * D * X + D * d * X + (d * X) * (d * X) + 2 * d * D;
   return dbl * 8 + 4 * (L + 1) + 10 * 256;
 }
 
@@ -914,11 +922,10 @@ bool alloc_op_scratch(mpbp_state* h, OpDesc& op, int ca, int cb) {
   const int X = op.nyo * op.q;
   if (h->arena.used + op_scratch_bytes(h, ca, cb, X) > h->arena.cap) return false;
   const size_t D = (size_t)ca * cb;
-  const size_t mrows = D * X;
   op.r = (int*)h->arena.take(4 * (L + 1));
   op.Lstride = (long long)(D * D);
   op.Lbuf = (double*)h->arena.take(8 * (size_t)L * D * D);
-  op.M = (double*)h->arena.take(8 * mrows * D);
+  op.M = (double*)h->arena.take(8 * op_M_doubles(h, D, X));
   op.Ms = (double*)h->arena.take(8 * (size_t)QR_NSPLIT_MAX * D * D);
   op.G = (double*)h->arena.take(8 * (size_t)d * D * X);
   op.M2T = (double*)h->arena.take(8 * D * (size_t)d * X);

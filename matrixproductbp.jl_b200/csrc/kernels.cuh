@@ -623,7 +623,7 @@ __host__ __device__ inline bool svd_direct(int p, int n, int jac_doubles) {
 // doubles of global scratch svd_left_cta needs for a p x n matrix (subspace path + exact fallback)
 __host__ __device__ inline size_t svd_scratch_doubles(int p, int n) {
   const size_t mx = (size_t)(p > n ? p : n) + 8;
-  return 3 * SUB_BMAX * mx + (size_t)p * n;
+  return 3 * SUB_BMAX * mx + (size_t)p * n + SUB_BMAX * SUB_BMAX;
 }
 __device__ inline void normalize_cols(double* W, int rows, int b, int ld, const double* sig) {
   double smax = 0.0;
@@ -698,12 +698,22 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
     double* Qg = scratch + SUB_BMAX * mx8;        // GEMM output p x b (ld = ldq)
     double* Gblk = scratch + 2 * SUB_BMAX * mx8;  // the block itself when shared memory cannot hold it
     double* Mwork = scratch + 3 * SUB_BMAX * mx8;  // p x n work copy of the exact fallback
-    // shared-memory carve-up of W: [block : cap][S : b*b][scal : 3*b]
-    const int fixed = SUB_BMAX * SUB_BMAX + 3 * SUB_BMAX;
+    double* Xg = Mwork + (size_t)p * n;            // b x b (inverse triangular factor of the Cholesky-QR route)
+    // shared-memory carve-up of W: [block : cap][S : 64*64][scal : 3*64][dsc : 64][Gs : b*b (mode 2)]
+    const int fixed = SUB_BMAX * SUB_BMAX + 4 * SUB_BMAX + (mode == 2 ? b * b : 0);
     const int cap = jac_doubles - fixed;
     double* S = W + cap;
     double* scal = S + SUB_BMAX * SUB_BMAX;
+    double* dsc = scal + 3 * SUB_BMAX;
+    double* Gs = dsc + SUB_BMAX;
     double* blk = ((long long)max(ldq, ldz) * b <= cap) ? W : Gblk;
+    // orthonormalise the block: Cholesky-QR2 (mode 2, block in shared memory) with the Householder route as fallback
+    auto orth = [&](const int rows, const int ld, const bool want_R) {
+      bool done = false;
+      if (mode == 2 && blk == W) done = cholqr2_orth(blk, rows, b, ld, want_R, S, Gs, Xg, dsc, Gblk, &flag);
+      if (!done) hh_orth(blk, rows, b, ld, want_R ? S : nullptr, scal);
+      if (stats && threadIdx.x == 0 && !done) atomicAdd(stats + 5, 1.0);
+    };
     // ---- start block: the b largest-norm columns of M ----
     double* nrm = (n + n / 2 + 2 <= SUB_BMAX * SUB_BMAX) ? S : Zg;  // n column norms + n ints
     int* sel = reinterpret_cast<int*>(nrm + n);
@@ -730,7 +740,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
     for (int j = threadIdx.x; j < SUB_BMAX; j += NT) sprev[j] = 0.0;
     __syncthreads();
     phase(1);
-    hh_orth(blk, p, b, ldq, nullptr, scal);
+    orth(p, ldq, false);
     phase(2);
     int sw = 0;
     int extra = -1;
@@ -743,13 +753,13 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       __syncthreads();
       for (int idx = threadIdx.x; idx < n * b; idx += NT) { const size_t o = (idx % n) + (size_t)ldz * (idx / n); blk[o] = Zg[o]; }
       phase(3);
-      hh_orth(blk, n, b, ldz, nullptr, scal);
+      orth(n, ldz, false);
       phase(4);
       blk_gemm_dmma(M, 1LL, (long long)p, p, n, blk, ldz, b, Qg, ldq);  // Y = M Z   (p x b)
       __syncthreads();
       for (int idx = threadIdx.x; idx < p * b; idx += NT) { const size_t o = (idx % p) + (size_t)ldq * (idx / p); blk[o] = Qg[o]; }
       phase(3);
-      hh_orth(blk, p, b, ldq, S, scal);  // Y = Q R, R -> S (b x b)
+      orth(p, ldq, true);  // Y = Q R, R -> S (b x b)
       phase(4);
       ++nit;
       if (extra > 1) {
