@@ -43,6 +43,36 @@ function CuMPBP(bp::MPBP{G,F}; dmax::Int=16, device::Int=0) where {G<:IndexedBiD
     return cu
 end
 
+"""
+`CuMPBP(bp)` for `InfiniteRegularGraph` / `InfiniteBipartiteRegularGraph` states (src/infinite_graph.jl:8-122): one node per
+class.  Bipartite: the reference's slot `e` ("message into node e") is the engine's edge `3 - e` (edge 1 = A→B, edge 2 = B→A),
+so ψ is uploaded in that order; `bethe_free_energy` re-weights the two blocks on the host.
+"""
+function CuMPBP(bp::MPBP{G,F}; dmax::Int=16, device::Int=0) where {G<:Union{InfiniteRegularGraph,InfiniteBipartiteRegularGraph},F}
+    g = bp.g; T = getT(bp); q = Int32[nstates(bp, i) for i in 1:nv(g)]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    if g isa InfiniteRegularGraph
+        check(ccall((:mpbp_create_infinite, LIB), Cint, (Cint, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}), g.k, T, q[1], dmax, device, h))
+        ψ = bp.ψ
+    else
+        check(ccall((:mpbp_create_infinite_bipartite, LIB), Cint, (Cint, Cint, Cint, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+            g.k[1], g.k[2], T, q[1], q[2], dmax, device, h))
+        ψ = bp.ψ[[2, 1]]                                # engine edge order
+    end
+    cu = CuMPBP{G,F,eltype(bp.w)}(g, bp.w, bp.ϕ, ψ, q, T, dmax, h[], true)
+    finalizer(x -> ccall((:mpbp_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), cu)
+    sync_reweightings!(cu)
+    return cu
+end
+
+"`sample_prior(cu; seed)` -> X (N × (T+1), states from 1): forward simulation of the prior on the device (src/sampling.jl:30-59)"
+function sample_prior(cu::CuMPBP; seed::Integer=rand(UInt64))
+    cu.classes_dirty && sync_factors!(cu)
+    X = zeros(Int32, cu.T + 1, nv(cu.g))               # C layout [i][t] = Julia (t, i)
+    check(ccall((:mpbp_sample_prior, LIB), Cint, (Ptr{Cvoid}, UInt64, Ptr{Int32}), cu.h, UInt64(seed), X))
+    permutedims(X) .+ 1
+end
+
 function sync_reweightings!(cu::CuMPBP)
     ϕ = reduce(vcat, (reduce(vcat, ϕᵢ) for ϕᵢ in cu.ϕ))            # [i][t][x]
     ψ = reduce(vcat, (reduce(vcat, vec.(ψₑ)) for ψₑ in cu.ψ))      # [e][t][x_src, x_dst] column-major
@@ -201,6 +231,10 @@ end
 function bethe_free_energy(cu::CuMPBP)
     f = zeros(nv(cu.g))
     check(ccall((:mpbp_free_energy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), cu.h, f))
+    if cu.g isa InfiniteBipartiteRegularGraph          # src/infinite_graph.jl:120-122
+        k = cu.g.k
+        return (f[1] * k[2] + f[2] * k[1]) / sum(k)
+    end
     sum(f)
 end
 
@@ -220,5 +254,5 @@ function get_message(cu::CuMPBP, e::Integer)
     TensorTrain(tensors)
 end
 
-export CuMPBP, CB_CuBP, sync_factors!, sync_reweightings!, get_message
+export CuMPBP, CB_CuBP, sync_factors!, sync_reweightings!, get_message, sample_prior
 end # module
