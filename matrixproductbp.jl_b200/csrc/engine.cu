@@ -104,9 +104,14 @@ struct mpbp_state {
   Arena arena;
   cudaStream_t st = nullptr;
   bool own_stream = true;
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // extra streams: op groups of one level run concurrently
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  static constexpr int NAUX = 7;
+  cudaStream_t aux[NAUX] = {};  // extra streams: op groups of one level run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
   double nstreams = 4;
+  double bulk_split = 4;     // TSQR chunks allowed per tall matrix inside a FULL launch (1 = off)
+  double bulk_split_min = 5; // ... for matrices of at least this many times n rows (X = nstates*q >= 6 at full bonds)
+  double group_mode = 0;     // how the cost-sorted ops of a round are dealt into stream groups: 0 round-robin (every group the same
+                             // mix), 1 contiguous chunks of equal work (homogeneous launches: no intra-launch tail)
   int twovar = 0;            // > 0: maxdist of the two-time marginals computed with every belief (option "twovar")
   double* d_tv = nullptr;    // [N][L][L][qmax*qmax]
   double hub_lane = 0;       // 1: high-degree nodes of a chunk run on their own (high-priority) stream (2: also for tiny chunks, tests).
@@ -177,7 +182,7 @@ int flat_messages(mpbp_state* h, MsgStore& m) {
 int common_init(mpbp_state* h) {
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaStreamCreate(&h->st));
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < mpbp_state::NAUX; ++k) {
     CUDA_OK(cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
   }
@@ -787,7 +792,7 @@ void ev_begin(mpbp_state* h, int tag, cudaStream_t st) {
 void ev_flush(mpbp_state* h) {
   if (!h->profile || h->ev_used == 0) return;
   cudaStreamSynchronize(h->st);
-  for (int k = 0; k < 3; ++k) cudaStreamSynchronize(h->aux[k]);
+  for (int k = 0; k < mpbp_state::NAUX; ++k) cudaStreamSynchronize(h->aux[k]);
   cudaStreamSynchronize(h->hub_st);
   for (size_t k = 0; k < h->ev_used; ++k) {
     float ms = 0;
@@ -813,13 +818,19 @@ struct GroupRun {
   int kc_rb;
   int bigH, smallH;  // row-block height of the flat-tree QR: 64 (one CTA/SM, D >= 200), 32 (two CTAs/SM) or 16
   int dXcap;
+  size_t jac_doubles, jac_smem;  // shared memory of the truncating-SVD kernel: only what the group's matrices need
   int nsplit;  // TSQR chunks allowed per matrix in this group's QR launches
+  int split_min;  // ... for matrices of at least split_min * n rows (0: every matrix, the rule of an under-filled launch)
 };
 
 // run the groups of one level concurrently: the per-site launch sequences of the groups are issued interleaved on
 // their own streams, so the tail of one group's launch is filled by the other groups' kernels
-int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr) {
+int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups_in, const Trunc& tr) {
   const int L = h->L, d = h->dmax;
+  std::vector<GroupRun> groups;  // (a group can come out empty of the contiguous dealing: nothing to launch for it)
+  for (auto& g : groups_in)
+    if (g.nops > 0) groups.push_back(g);
+  if (groups.empty()) return 0;
   const size_t kp_smem = (size_t)d * d * d * 8;
   const size_t jac_fixed = 3 * SUB_BMAX;
   const size_t jac_doubles = (size_t)h->max_smem / 8 - jac_fixed;
@@ -835,9 +846,17 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
     if (h->kron_mma > 0) {
       // the widest tile that fits (the kernel keeps its A fragments and 4 n-tiles of accumulators in registers: one CTA per SM)
       for (int rb : {16, 8, 4})
-        if (!g.kc_mma_rb && kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS) * 8 <= (size_t)h->max_smem) g.kc_mma_rb = rb;
+        if (!g.kc_mma_rb && kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS, g.maxNy) * 8 <= (size_t)h->max_smem) g.kc_mma_rb = rb;
     }
     g.dXcap = d * g.maxX;
+    {
+      // small problems (every matrix of the group goes through the direct Jacobi path with a p x c block, c <= 64): ask for
+      // the block only, so that several CTAs share an SM; otherwise the whole opt-in shared memory (subspace iteration)
+      const size_t cmax = (size_t)std::min(g.dXcap, g.maxD);
+      g.jac_doubles = jac_doubles;
+      if (cmax <= (size_t)SUB_BMAX && (size_t)g.dXcap * cmax + 64 <= jac_doubles) g.jac_doubles = std::max<size_t>((size_t)g.dXcap * cmax + 64, 1024);
+      g.jac_smem = (jac_fixed + g.jac_doubles) * 8;
+    }
     auto pickH = [&](int n, size_t& bytes) -> int {
       const size_t s64 = ft_smem_doubles<64>(n) * 8, s32 = ft_smem_doubles<32>(n) * 8, s16 = ft_smem_doubles<16>(n) * 8;
       if (n >= 200 && s64 <= (size_t)h->max_smem) { bytes = s64; return 64; }
@@ -860,10 +879,10 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
       if (g.kc_mma_rb) {
         const int rb = g.kc_mma_rb;
         dim3 gm(g.nops, g.maxq, (g.maxD + rb - 1) / rb);
-        const size_t sm = kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS) * 8;
-        if (rb == 16) k_kron_carry_mma<16><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, h->d_flops + 17);
-        else if (rb == 8) k_kron_carry_mma<8><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, h->d_flops + 17);
-        else k_kron_carry_mma<4><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, h->d_flops + 17);
+        const size_t sm = kc_mma_smem_doubles(rb, g.maxD, d, g.maxNyS, g.maxNy) * 8;
+        if (rb == 16) k_kron_carry_mma<16><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, g.maxNy, h->d_flops + 17);
+        else if (rb == 8) k_kron_carry_mma<8><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, g.maxNy, h->d_flops + 17);
+        else k_kron_carry_mma<4><<<gm, NT, sm, g.st>>>(g.d_ops, t, L, g.maxNyS, g.maxNy, h->d_flops + 17);
       } else if (g.kc_rb == 4) k_kron_carry<4><<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
       else k_kron_carry<1><<<g1, NT, g.kc_smem, g.st>>>(g.d_ops, t, L);
       ev_end(h, g.st);
@@ -871,14 +890,14 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
       ev_begin(h, F_QR, g.st);
       const int nsplit = g.nsplit;
       dim3 gq(g.nops, nsplit);
-      if (g.bigH == 64) k_qr_ft<64><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
-      else if (g.bigH == 32) k_qr_ft<32><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
-      else k_qr_ft<16><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops);
+      if (g.bigH == 64) k_qr_ft<64><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, g.split_min);
+      else if (g.bigH == 32) k_qr_ft<32><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, g.split_min);
+      else k_qr_ft<16><<<gq, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, g.split_min);
       h->n_launch++;
       if (nsplit > 1) {
-        if (g.bigH == 64) k_qr_ft_merge<64><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge);
-        else if (g.bigH == 32) k_qr_ft_merge<32><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge);
-        else k_qr_ft_merge<16><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge);
+        if (g.bigH == 64) k_qr_ft_merge<64><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge, g.split_min);
+        else if (g.bigH == 32) k_qr_ft_merge<32><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge, g.split_min);
+        else k_qr_ft_merge<16><<<g.nops, NT, g.ft_big, g.st>>>(g.d_ops, t, nsplit, h->d_flops, (int)h->tri_merge, g.split_min);
         h->n_launch++;
       }
       ev_end(h, g.st);
@@ -898,12 +917,12 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups, const Trunc& tr)
         k_gemm_m2t<<<g4, NT, 0, g.st>>>(g.d_ops, t);
         ev_end(h, g.st);
         ev_begin(h, F_QRS, g.st);
-        if (g.smallH == 64) k_qr_small<64><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
-        else if (g.smallH == 32) k_qr_small<32><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
-        else k_qr_small<16><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)jac_doubles);
+        if (g.smallH == 64) k_qr_small<64><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)g.jac_doubles);
+        else if (g.smallH == 32) k_qr_small<32><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)g.jac_doubles);
+        else k_qr_small<16><<<g.nops, NT, g.ft_small, g.st>>>(g.d_ops, t, (int)g.jac_doubles);
         ev_end(h, g.st);
         ev_begin(h, F_JAC, g.st);
-        k_jacobi_project<<<g.nops, NT, jac_smem, g.st>>>(g.d_ops, t, tr, d, (int)jac_doubles, h->d_err, h->d_flops + 1, (int)h->svd_mode);
+        k_jacobi_project<<<g.nops, NT, g.jac_smem, g.st>>>(g.d_ops, t, tr, d, (int)g.jac_doubles, h->d_err, h->d_flops + 1, (int)h->svd_mode);
         ev_end(h, g.st);
         h->n_launch += 3;
       } else {
@@ -1062,6 +1081,7 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         CUDA_OK(cudaMemcpyAsync(d_ops, sorted.data(), sizeof(OpDesc) * sorted.size(), cudaMemcpyHostToDevice, hs));
         gr.d_ops = d_ops;
         gr.nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(gr.nops, 1))));
+        gr.split_min = 0;
         std::vector<GroupRun> one(1, gr);
         if (run_op_groups(h, one, tr)) {
           cudaStreamSynchronize(hs);
@@ -1131,9 +1151,22 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         while (nhead < nops && cst(i0 + nhead) >= h->outlier_split * mean) ++nhead;
         if (nhead * 4 > (int)h->qr_fill || nops - nhead < G - 1) nhead = 0;  // too many to be outliers / nothing left for the other groups
       }
+      std::vector<int> gchunk(nops, 0);
+      if (h->group_mode >= 1) {
+        // contiguous chunks of (nearly) equal work over the groups that take the non-outlier ops
+        auto cst = [&](size_t k) { return (double)P.capA[lev][k] * P.capB[lev][k] * ops[k].nyo * ops[k].q; };
+        const int g0 = nhead > 0 ? 1 : 0, ng = G - g0;
+        double tot = 0.0;
+        for (int k = nhead; k < nops; ++k) tot += cst(i0 + k);
+        double acc = 0.0;
+        for (int k = nhead; k < nops; ++k) {
+          gchunk[k] = g0 + std::min(ng - 1, (int)(acc / std::max(tot, 1e-300) * ng));
+          acc += cst(i0 + k);
+        }
+      }
       for (int k = 0; k < nops; ++k) {
         const OpDesc& op = ops[i0 + k];
-        const int gsel = nhead > 0 ? (k < nhead ? 0 : 1 + (k - nhead) % (G - 1)) : k % G;
+        const int gsel = (h->group_mode >= 1 && k >= nhead) ? gchunk[k] : (nhead > 0 ? (k < nhead ? 0 : 1 + (k - nhead) % (G - 1)) : k % G);
         GroupRun& gr = groups[gsel];
         gops[gsel].push_back(op);
         gr.nops++;
@@ -1155,11 +1188,20 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
         CUDA_OK(cudaEventRecord(h->ev_fork, st));
         for (int gi = 1; gi < G; ++gi) CUDA_OK(cudaStreamWaitEvent(h->aux[gi - 1], h->ev_fork, 0));
       }
-      const int nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(nops, 1))));
-      for (int gi = 0; gi < G; ++gi) groups[gi].nsplit = nsplit;
-      if (nhead > 0) groups[0].nsplit = std::max(nsplit, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / nhead)));
+      // under-filled launch: split every tall matrix (sqrt rule); full launch: only the matrices of >= bulk_split_min * n
+      // rows, the long poles of their launch, into at most bulk_split chunks
+      const int fill_split = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(nops, 1))));
+      const int nsplit = std::max(fill_split, std::min(QR_NSPLIT_MAX, (int)h->bulk_split));
+      for (int gi = 0; gi < G; ++gi) {
+        groups[gi].nsplit = nsplit;
+        groups[gi].split_min = fill_split >= 2 ? 0 : (int)h->bulk_split_min;
+      }
+      if (nhead > 0) {
+        groups[0].nsplit = std::max(nsplit, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / nhead)));
+        groups[0].split_min = 0;
+      }
       if (run_op_groups(h, groups, tr)) {
-        for (int k = 0; k < 3; ++k) cudaStreamSynchronize(h->aux[k]);  // do not leave forked streams running
+        for (int k = 0; k < mpbp_state::NAUX; ++k) cudaStreamSynchronize(h->aux[k]);  // do not leave forked streams running
         cudaStreamSynchronize(st);
         return 1;
       }
@@ -1389,7 +1431,7 @@ int mpbp_destroy(mpbp_handle h) {
   cudaFree(h->d_delta); cudaFree(h->d_err); cudaFree(h->d_flops); cudaFree(h->d_edge_idx); cudaFree(h->arena.base); cudaFree(h->d_tv);
   for (auto& e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (h->own_stream) cudaStreamDestroy(h->st);
-  for (int k = 0; k < 3; ++k) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
+  for (int k = 0; k < mpbp_state::NAUX; ++k) { if (h->aux[k]) cudaStreamDestroy(h->aux[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->hub_st) cudaStreamDestroy(h->hub_st);
   if (h->ev_hub_fork) cudaEventDestroy(h->ev_hub_fork);
@@ -2049,7 +2091,10 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   } else if (n == "max_group_ops") h->max_group_ops = value;
   else if (n == "profile") h->profile = (int)value;
   else if (n == "qr_fill") h->qr_fill = value;
-  else if (n == "nstreams") h->nstreams = std::max(1.0, std::min(4.0, value));
+  else if (n == "nstreams") h->nstreams = std::max(1.0, std::min(1.0 + mpbp_state::NAUX, value));
+  else if (n == "group_mode") h->group_mode = value;
+  else if (n == "bulk_split") h->bulk_split = std::max(1.0, value);
+  else if (n == "bulk_split_min") h->bulk_split_min = value;
   else if (n == "level_balance") h->level_balance = value;
   else if (n == "outlier_split") h->outlier_split = value;
   else if (n == "kron_mma") h->kron_mma = value;
@@ -2216,6 +2261,9 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
   {
     double ph[6];
     CUDA_OK(cudaMemcpy(ph, dst + 8, sizeof(double) * 6, cudaMemcpyDeviceToHost));
+    double fb = 0;
+    CUDA_OK(cudaMemcpy(&fb, dst + 5, sizeof(double), cudaMemcpyDeviceToHost));
+    if (getenv("MPBP_SVD_PHASES")) printf("householder orthonormalisations per call (mode 2: Cholesky-QR fallbacks) %.2f\n", fb / batch);
     if (getenv("MPBP_SVD_PHASES")) printf("svd phases (Mcycles/call): final %.2f  select %.2f  start-orth %.2f  iter-gemms %.2f  iter-orth %.2f  iter-ritz %.2f\n", ph[0] / batch / 1e6, ph[1] / batch / 1e6, ph[2] / batch / 1e6, ph[3] / batch / 1e6, ph[4] / batch / 1e6, ph[5] / batch / 1e6);
   }
   cudaFree(dM); cudaFree(dU); cudaFree(dS); cudaFree(dscr); cudaFree(dst); cudaFree(derr);

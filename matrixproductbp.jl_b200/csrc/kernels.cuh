@@ -82,7 +82,15 @@ __global__ void __launch_bounds__(NT) k_generic_kron(const GenJob* jobs, int L, 
     Y *= jb.qk[k];
   }
   if (Ml > dcap || Mr > dcap) {
-    if (threadIdx.x == 0) atomicOr(err, ERR_BOND_OVERFLOW);
+    // loud error; leave a VALID (bond-1) site behind so that the kernels that follow stay inside their buffers
+    if (threadIdx.x == 0) {
+      atomicOr(err, ERR_BOND_OVERFLOW);
+      jb.out.bonds[t] = 1;
+      if (t == L - 1) jb.out.bonds[L] = 1;
+      if (t == 0) *jb.out.ls = 0.0;
+    }
+    double* Oz = jb.out.data + (size_t)t * jb.out.stride;
+    for (int idx = threadIdx.x; idx < jb.out.stride; idx += NT) Oz[idx] = 0.0;
     return;
   }
   const int q = jb.q;
@@ -235,11 +243,11 @@ __global__ void __launch_bounds__(NT) k_kron_carry(const OpDesc* ops, int t, int
 // from L1/L2 (a site of an operand train is a few KB).  grid (nops, q, ceil(rcap/RB)).
 // dyn smem: RB*DrP + nySmax*RB*brFmax*ZP doubles (see kc_mma_smem_doubles).
 __host__ __device__ inline int kc_pad4(int n) { return n + ((12 - (n & 7)) & 7); }  // == 4 (mod 8): conflict-free B fragments
-__host__ __device__ inline size_t kc_mma_smem_doubles(int RB, int Dcap, int dcap, int nyS) {
-  return (size_t)RB * (Dcap + 8) + (size_t)nyS * RB * dcap * kc_pad4(dcap);
+__host__ __device__ inline size_t kc_mma_smem_doubles(int RB, int Dcap, int dcap, int nyS, int nymax) {
+  return (size_t)RB * (Dcap + 8) + (size_t)nyS * RB * dcap * kc_pad4(dcap) + (size_t)nymax * nymax * nyS;
 }
 template <int RB>
-__global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t, int L, int nyS_cap, double* flops) {
+__global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t, int L, int nyS_cap, int ny_cap, double* flops) {
   extern __shared__ double smem[];
   const OpDesc& op = ops[blockIdx.x];
   const int x = blockIdx.y;
@@ -264,12 +272,18 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
   const int sLF = swap ? br1 : 1, sLS = swap ? 1 : br1;        // L row index = nF*sLF + nS*sLS
   const int sOF = swap ? bl1 : 1, sOS = swap ? 1 : bl1;        // out row index = mF*sOF + mS*sOS
   const int pF = swap ? nyo * ny1 : nyo, pS = swap ? nyo : nyo * ny1;  // pyy index = y + yF*pF + yS*pS + nyo*ny1*ny2*x
-  if (nyS > nyS_cap) return;  // host guarantees this does not happen (falls back to the scalar kernel otherwise)
+  if (nyS > nyS_cap || nyo > ny_cap || nyF > ny_cap) return;  // host guarantees this does not happen (launch sized from the group maxima)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q4 = lane & 3;
   const int DrP = Dr + 8;
   const int ZP = kc_pad4(blS);
   double* Lc = smem;                       // [u][DrP]
   double* Z = smem + (size_t)RB * DrP;     // [(yS*RB + u)*brF + nF][ZP]  (mS fastest)
+  double* Ps = Z + (size_t)nyS_cap * RB * brF * ZP;  // Pyy[y + nyo*(yF + nyF*yS)] of this x: the (y_S, y_F) loops test it per pair,
+                                                      // from global memory every test would be an exposed L2 round trip
+  for (int i = threadIdx.x; i < nyo * nyF * nyS; i += NT) {
+    const int y = i % nyo, yF = (i / nyo) % nyF, yS = i / (nyo * nyF);
+    Ps[i] = pyy[y + yF * pF + yS * pS + (size_t)nyo * ny1 * ny2 * x];
+  }
   if (flops && blockIdx.z == 0 && threadIdx.x == 0) {
     int npairs = 0;
     for (int yS = 0; yS < nyS; ++yS)
@@ -357,7 +371,6 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
   // ---------------- stage 2 ----------------
   const int mtF = (blF + 7) >> 3, ksF = (brF + 3) >> 2;
   const int ncol2 = blS * RB, nt2 = (ncol2 + 7) >> 3;
-  const size_t pyx = (size_t)nyo * ny1 * ny2 * x;
   constexpr int TG = 4;  // n-tiles a warp carries at once (their accumulators persist across the (y_S, y_F) pairs)
   for (int y = 0; y < nyo; ++y) {
     for (int ntb = warp; ntb < nt2; ntb += NW * TG) {
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
       for (int yS = 0; yS < nyS; ++yS) {
         const double* zy = Z + (size_t)yS * RB * brF * ZP;
         for (int yF = 0; yF < nyF; ++yF) {
-          const double pv = pyy[y + yF * pF + yS * pS + pyx];
+          const double pv = Ps[y + nyo * (yF + nyF * yS)];
           if (pv == 0.0) continue;
           const double* Fy = Fd + (size_t)blF * brF * (yF + nyF * x);
           double af[4][8];
@@ -435,8 +448,11 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
 // Sweep-1 factor of site t with the flat-tree DMMA QR: L_t = R^T of M_t ((rn*X) x Dl), r[t] = min(rows, Dl).
 // When a launch holds few matrices (nsplit > 1) tall matrices are split TSQR-style over several CTAs: row chunks
 // are factored independently into op.Ms (n x n each) and k_qr_ft_merge factors the stack.
-__device__ __forceinline__ void ft_split(int m, int n, int nsplit, int& nch, int& ch_rows) {
+// split_min: matrices with fewer than split_min * n rows stay whole (in a full launch only the tall outliers are split: they
+// are the long pole of the launch, the split trades ~15 % more flops on them for a 2x shorter critical path)
+__device__ __forceinline__ void ft_split(int m, int n, int nsplit, int split_min, int& nch, int& ch_rows) {
   const int n8 = (n + 7) & ~7;
+  if (m < split_min * n8) { nch = 1; ch_rows = m; return; }
   // latency of chunk stage + merge stage ~ m/k + k*n rows  ->  k ~ sqrt(m/n)  (the merge factors a k*n-row stack)
   nch = min(nsplit, (int)(sqrt((double)m / (double)n8) + 0.5));
   if (nch < 2) { nch = 1; ch_rows = m; return; }
@@ -447,7 +463,7 @@ __device__ __forceinline__ double qr_flops(double mm, double nn) {
   return mm >= nn ? 2.0 * mm * nn * nn - (2.0 / 3.0) * nn * nn * nn : 2.0 * nn * mm * mm - (2.0 / 3.0) * mm * mm * mm;
 }
 template <int H>
-__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* ops, int t, int nsplit, double* flops) {
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* ops, int t, int nsplit, double* flops, int split_min) {
   extern __shared__ double smem[];
   const OpDesc& op = ops[blockIdx.x];
   const int Dl = op.a.bonds[t] * op.b.bonds[t];
@@ -466,7 +482,7 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* o
     return;
   }
   int nch, ch_rows;
-  ft_split(m, Dl, nsplit, nch, ch_rows);
+  ft_split(m, Dl, nsplit, split_min, nch, ch_rows);
   const int ch = blockIdx.y;
   if (ch >= nch) return;
   const int row0 = ch * ch_rows, rows = min(ch_rows, m - row0);
@@ -484,14 +500,14 @@ __global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft(const OpDesc* o
   }
 }
 template <int H>
-__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft_merge(const OpDesc* ops, int t, int nsplit, double* flops, int tri) {
+__global__ void __launch_bounds__(NT, (H == 32 ? 2 : 1)) k_qr_ft_merge(const OpDesc* ops, int t, int nsplit, double* flops, int tri, int split_min) {
   extern __shared__ double smem[];
   const OpDesc& op = ops[blockIdx.x];
   const int Dl = op.a.bonds[t] * op.b.bonds[t];
   const int m = op.r[t + 1] * op.nyo * op.q;
   if (m <= Dl) return;
   int nch, ch_rows;
-  ft_split(m, Dl, nsplit, nch, ch_rows);
+  ft_split(m, Dl, nsplit, split_min, nch, ch_rows);
   if (nch == 1) return;
   if (flops && threadIdx.x == 0) atomicAdd(flops + 16, qr_flops((double)nch * Dl, Dl));
   qr_ft_cta<H>(op.Ms, nch * Dl, Dl, Dl, op.Lbuf + (size_t)t * op.Lstride, Dl, true, smem, /*tri_n=*/tri ? Dl : 0);
@@ -774,7 +790,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
       if (threadIdx.x == 0) {
         // Ritz VALUES converge like angle^2: once they are stationary to 1e-13 sigma_1 the subspace angle is still up to
         // ~sqrt(1e-13).  The contraction of the last step (value error ratio r = rho_angle^2) says how many more
-        // iterations bring the angle to 1e-13 (1-2 for decaying spectra, many for flat ones, where it matters).
+        // iterations bring the angle to 1e-11 (1 for decaying spectra, many for flat ones, where it matters).
         const double s1 = sig[order[0]];
         double dm = 0.0;
         for (int i = 0; i < kchk; ++i) {
@@ -787,7 +803,7 @@ __device__ inline SvdLeft svd_left_cta(const double* Mcm, const double* R2, doub
         if (ex < 0 && dm <= 1e-13) {
           const double r = fmin(0.9, fmax(1e-8, dprev > 0.0 ? dm / dprev : 1e-8));
           const double ang = sqrt(fmax(dm, 1e-18));
-          ex = (int)fmin(30.0, fmax(1.0, ceil(log(1e-13 / ang) / (0.5 * log(r)))));
+          ex = (int)fmin(30.0, fmax(1.0, ceil(log(1e-11 / ang) / (0.5 * log(r)))));
         } else if (ex > 0) ex--;
         dprev = dm;
         s_extra = ex;

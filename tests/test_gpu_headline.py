@@ -255,11 +255,16 @@ def test_generic_path_compresses_the_dummy_neighbour_message():
         phi = [[np.array([0.7, 0.3]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
         phi[2][2] = np.array([1.0, 0.2])
         bo = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
-        bd = M.mpbp(gd, wd, [2] * N, T, phi=phi, dmax=4)
+        bd = M.mpbp(gd, wd, [2] * N, T, phi=phi, dmax=27)  # the generic path needs the PRODUCT of the incoming bonds (3^3) to fit
         O.iterate(bo, maxiter=3, trunc=OT.TruncBond(dd), tol=0.0)
         M.iterate_(bd, maxiter=3, svd_trunc=M.TruncBond(dd), tol=0.0, shuffle_nodes=False)
         eb, ef, ep = compare(bo, bd)
         assert eb < TOL and ef < TOL and ep < TOL, (dd, eb, ef, ep)
+    # too small a device capacity for the product of the incoming bonds: a LOUD error, and the device stays usable
+    bsmall = M.mpbp(gd, wd, [2] * N, T, phi=phi, dmax=4)
+    with pytest.raises(M.MPBPError):
+        M.iterate_(bsmall, maxiter=3, svd_trunc=M.TruncBond(3), tol=0.0, shuffle_nodes=False)
+    M.iterate_(bd, maxiter=1, svd_trunc=M.TruncBond(3), tol=0.0, shuffle_nodes=False)
     # the truncation really binds for the belief: un-truncated beliefs differ from the truncated ones by more than TOL
     bo2 = O.MPBP(go, wo, [2] * N, T, phi=[[p.copy() for p in ph] for ph in phi])
     O.iterate(bo2, maxiter=3, trunc=OT.TruncBond(16), tol=0.0)
