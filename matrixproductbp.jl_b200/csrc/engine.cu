@@ -121,8 +121,9 @@ struct mpbp_state {
   double hub_frac = 0.3;     // share of the chunk's cost the hub lane may take
   cudaStream_t hub_st = nullptr;
   cudaEvent_t ev_hub_fork = nullptr, ev_hub_join = nullptr;
-  double svd_mode = 0;       // 0: squared Jacobi block iteration when the block fits shared memory (else Householder), 1: always the
-                             // un-squared Householder variant
+  double svd_mode = 2;       // truncating SVD of large matrices: 2 (default) un-squared block iteration, blocks orthonormalised by
+                             // Cholesky-QR2 with the Householder route as fallback; 1 same with Householder only; 0 round-1
+                             // squared iteration with Jacobi orthonormalisation when the block fits shared memory
   double tri_merge = 1;      // 1: the TSQR merge skips the zero panels of the stacked triangular chunk factors
   double kron_mma = 1;       // 1: DMMA Kronecker-carry kernel (k_kron_carry_mma), 0: scalar FP64 kernel (k_kron_carry)
   double outlier_split = 0;  // > 0: ops costing more than this multiple of the mean of their launch group run in a
@@ -834,7 +835,6 @@ int run_op_groups(mpbp_state* h, std::vector<GroupRun>& groups_in, const Trunc& 
   const size_t kp_smem = (size_t)d * d * d * 8;
   const size_t jac_fixed = 3 * SUB_BMAX;
   const size_t jac_doubles = (size_t)h->max_smem / 8 - jac_fixed;
-  const size_t jac_smem = (jac_fixed + jac_doubles) * 8;
   if (kp_smem > (size_t)h->max_smem) return fail("bond capacity %d exceeds the shared-memory tiling of k_kron_proj", d);
   for (auto& g : groups) {
     g.kc_smem = ((size_t)g.maxD + (size_t)d * d * g.maxNy) * 8;
@@ -2244,7 +2244,7 @@ int mpbp_test_svd(const double* M, int batch, int p, int n, int d, double* U, do
     CUDA_OK(cudaMemset(dst, 0, sizeof(double) * 16));
     cudaEventRecord(e0);
     k_test_svd<<<batch, NT, (size_t)maxs>>>(dM, p, n, tr, (int)jac_doubles, dscr, per, dU, dS, derr, dst,
-                                            getenv("MPBP_SVD_MODE") ? atoi(getenv("MPBP_SVD_MODE")) : 0);
+                                            getenv("MPBP_SVD_MODE") ? atoi(getenv("MPBP_SVD_MODE")) : 2);
     cudaEventRecord(e1);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventSynchronize(e1));

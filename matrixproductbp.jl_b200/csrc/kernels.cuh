@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(NT) k_kron_carry(const OpDesc* ops, int t, int
 // dyn smem: RB*DrP + nySmax*RB*brFmax*ZP doubles (see kc_mma_smem_doubles).
 __host__ __device__ inline int kc_pad4(int n) { return n + ((12 - (n & 7)) & 7); }  // == 4 (mod 8): conflict-free B fragments
 __host__ __device__ inline size_t kc_mma_smem_doubles(int RB, int Dcap, int dcap, int nyS, int nymax) {
-  return (size_t)RB * (Dcap + 8) + (size_t)nyS * RB * dcap * kc_pad4(dcap) + (size_t)nymax * nymax * nyS;
+  return (size_t)RB * (Dcap + 8) + (size_t)nyS * RB * dcap * kc_pad4(dcap) + (size_t)nymax * nymax * nyS +
+         (size_t)(nymax + nyS) * dcap * dcap + 8;  // + the two operand sites (all auxiliary states of this x)
 }
 template <int RB>
 __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t, int L, int nyS_cap, int ny_cap, double* flops) {
@@ -284,6 +285,13 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
     const int y = i % nyo, yF = (i / nyo) % nyF, yS = i / (nyo * nyF);
     Ps[i] = pyy[y + yF * pF + yS * pS + (size_t)nyo * ny1 * ny2 * x];
   }
+  // the two operand sites of this x (contiguous: [bl, br, ny] blocks) also live in shared memory: the A fragments of both
+  // stages are re-read per n-tile group / per (y_S, y_F) pair, and from L2 every re-read is an exposed round trip
+  double* Fs = Ps + (((size_t)nyo * nyF * nyS + 1) & ~(size_t)1);
+  double* Ss = Fs + (((size_t)blF * brF * nyF + 1) & ~(size_t)1);
+  const double* Fg = Fd + (size_t)blF * brF * nyF * x;
+  const double* Sg = Sd + (size_t)blS * brS * nyS * x;
+  const int nFs = blF * brF * nyF, nSs = blS * brS * nyS;
   if (flops && blockIdx.z == 0 && threadIdx.x == 0) {
     int npairs = 0;
     for (int yS = 0; yS < nyS; ++yS)
@@ -294,26 +302,38 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
       }
     atomicAdd(flops, 2.0 * rn * ((double)blS * brS * brF * nyS + (double)blF * brF * blS * npairs));
   }
-  // stage the RB columns of L_{t+1}: one TMA bulk copy per column (Dr contiguous doubles) when 16-byte aligned
+  // stage the RB columns of L_{t+1} (one TMA bulk copy per column, Dr contiguous doubles) and the two operand sites (one
+  // bulk copy each) when 16-byte aligned; plain loads otherwise
   __shared__ uint64_t kc_mbar;
-  const bool bulk = Lm != nullptr && (Dr & 1) == 0 && aligned16(Lm) && aligned16(Lc);
-  if (bulk) {
+  const bool bulkL = Lm != nullptr && (Dr & 1) == 0 && aligned16(Lm) && aligned16(Lc);
+  const bool bulkF = (nFs & 1) == 0 && aligned16(Fg) && aligned16(Fs);
+  const bool bulkS = (nSs & 1) == 0 && aligned16(Sg) && aligned16(Ss);
+  if (bulkL || bulkF || bulkS) {
     if (threadIdx.x == 0) mbar_init(&kc_mbar, 1);
     __syncthreads();
     if (warp == 0) {
-      if (lane == 0) mbar_expect_tx(&kc_mbar, (uint32_t)(nb * Dr * 8));
+      if (lane == 0) mbar_expect_tx(&kc_mbar, (uint32_t)((bulkL ? nb * Dr : 0) + (bulkF ? nFs : 0) + (bulkS ? nSs : 0)) * 8u);
       __syncwarp();
-      for (int u = lane; u < nb; u += 32) bulk_g2s(Lc + (size_t)u * DrP, Lm + (size_t)Dr * (rr0 + u), (uint32_t)(Dr * 8), &kc_mbar);
+      if (bulkL)
+        for (int u = lane; u < nb; u += 32) bulk_g2s(Lc + (size_t)u * DrP, Lm + (size_t)Dr * (rr0 + u), (uint32_t)(Dr * 8), &kc_mbar);
+      if (bulkF && lane == 0) bulk_g2s(Fs, Fg, (uint32_t)(nFs * 8), &kc_mbar);
+      if (bulkS && lane == 1) bulk_g2s(Ss, Sg, (uint32_t)(nSs * 8), &kc_mbar);
     }
+  }
+  if (bulkL) {
     for (int i = threadIdx.x; i < nb * (DrP - Dr); i += NT) Lc[(size_t)(i / (DrP - Dr)) * DrP + Dr + i % (DrP - Dr)] = 0.0;
     for (int i = threadIdx.x; i < (RB - nb) * DrP; i += NT) Lc[(size_t)nb * DrP + i] = 0.0;
-    mbar_wait(&kc_mbar, 0);
   } else {
     for (int i = threadIdx.x; i < RB * DrP; i += NT) {
       const int u = i / DrP, e = i % DrP;
       Lc[i] = (u < nb && e < Dr) ? (Lm ? Lm[e + (size_t)Dr * (rr0 + u)] : 1.0) : 0.0;
     }
   }
+  if (!bulkF)
+    for (int i = threadIdx.x; i < nFs; i += NT) Fs[i] = Fg[i];
+  if (!bulkS)
+    for (int i = threadIdx.x; i < nSs; i += NT) Ss[i] = Sg[i];
+  if (bulkL || bulkF || bulkS) mbar_wait(&kc_mbar, 0);
   __syncthreads();
   // ---------------- stage 1 ----------------
   // A fragments (the operand site, a few KB in L1/L2) are hoisted into registers per auxiliary state: the inner loops
@@ -321,7 +341,7 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
   const int mtS = (blS + 7) >> 3, ksS = (brS + 3) >> 2;
   const int ncol1 = brF * RB, nt1 = (ncol1 + 7) >> 3;
   for (int yS = 0; yS < nyS; ++yS) {
-    const double* Sy = Sd + (size_t)blS * brS * (yS + nyS * x);
+    const double* Sy = Ss + (size_t)blS * brS * yS;
     double af[4][8];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
@@ -392,7 +412,7 @@ __global__ void __launch_bounds__(NT) k_kron_carry_mma(const OpDesc* ops, int t,
         for (int yF = 0; yF < nyF; ++yF) {
           const double pv = Ps[y + nyo * (yF + nyF * yS)];
           if (pv == 0.0) continue;
-          const double* Fy = Fd + (size_t)blF * brF * (yF + nyF * x);
+          const double* Fy = Fs + (size_t)blF * brF * yF;
           double af[4][8];
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt)
