@@ -267,40 +267,52 @@ __device__ inline void blk_gram_dmma(const double* W, const int rows, const int 
     G[j + 1 + (size_t)b * i] = c1;
   }
 }
-// in-place upper Cholesky G = R^T R by warp 0 (column-major b x b, upper triangle in/out); *ok_flag = 0 on a pivot <= tol
-__device__ inline void blk_chol_warp(double* G, const int b, const double tol, int* ok_flag) {
-  const int lane = threadIdx.x & 31;
-  if ((threadIdx.x >> 5) != 0) return;
+// in-place upper Cholesky G = R^T R by the whole CTA (column-major b x b, upper triangle in/out), right-looking, two
+// __syncthreads per column; *ok_flag = 0 on a pivot <= tol (all threads then return together).  All threads call.
+__device__ inline void blk_chol_cta(double* G, const int b, const double tol, int* ok_flag) {
   for (int k = 0; k < b; ++k) {
     const double piv = G[k + (size_t)b * k];
-    if (!(piv > tol)) {
-      if (lane == 0) *ok_flag = 0;
+    if (!(piv > tol)) {  // uniform: every thread reads the same value
+      if (threadIdx.x == 0) *ok_flag = 0;
+      __syncthreads();
       return;
     }
-    const double rkk = sqrt(piv), inv = 1.0 / rkk;
-    __syncwarp();
-    if (lane == 0) G[k + (size_t)b * k] = rkk;
-    for (int j = k + 1 + lane; j < b; j += 32) G[k + (size_t)b * j] *= inv;  // row k of R
-    __syncwarp();
-    // trailing update: G[i,j] -= R[k,i] R[k,j] for k < i <= j
-    for (int j = k + 1 + lane; j < b; j += 32) {
-      const double rkj = G[k + (size_t)b * j];
-      for (int i = k + 1; i <= j; ++i) G[i + (size_t)b * j] -= G[k + (size_t)b * i] * rkj;
+    const double inv = rsqrt(piv);
+    __syncthreads();  // everyone has read the pivot
+    for (int j = k + threadIdx.x; j < b; j += NT) G[k + (size_t)b * j] = j == k ? piv * inv : G[k + (size_t)b * j] * inv;  // row k of R
+    __syncthreads();
+    // trailing update G[i,j] -= R[k,i] R[k,j] for k < i <= j, one entry per thread
+    const int nr = b - k - 1;
+    for (int e = threadIdx.x; e < nr * nr; e += NT) {
+      const int i = k + 1 + e % nr, j = k + 1 + e / nr;
+      if (i <= j) G[i + (size_t)b * j] -= G[k + (size_t)b * i] * G[k + (size_t)b * j];
     }
-    __syncwarp();
+    __syncthreads();
   }
 }
-// X = R^-1 (upper triangular b x b, column-major, ld b): thread j solves R x = e_j by back substitution
-__device__ inline void blk_tri_inverse(const double* R, const int b, double* X) {
-  for (int j = threadIdx.x; j < b; j += NT) {
-    double* xj = X + (size_t)b * j;
-    for (int i = j + 1; i < b; ++i) xj[i] = 0.0;
-    xj[j] = 1.0 / R[j + (size_t)b * j];
-    for (int i = j - 1; i >= 0; --i) {
-      double acc = 0.0;
-      for (int k = i + 1; k <= j; ++k) acc += R[i + (size_t)b * k] * xj[k];
-      xj[i] = -acc / R[i + (size_t)b * i];
+// R <- R^-1 IN PLACE (upper triangular b x b, column-major, ld b, shared memory): rows from the bottom up; at row i thread j
+// (j >= i) forms X[i,j] = -(sum_{k=i+1..j} R[i,k] X[k,j]) / R[i,i] from row i of R (still intact) and the finished rows k > i of
+// its own column; the row is written after a barrier.  All threads call (b <= NT).
+__device__ inline void blk_tri_inverse_inplace(double* R, const int b) {
+  const int j = threadIdx.x;
+  for (int i = b - 1; i >= 0; --i) {
+    double v = 0.0;
+    if (j < b && j >= i) {
+      if (j == i) v = 1.0 / R[i + (size_t)b * i];
+      else {
+        double a0 = 0.0, a1 = 0.0;
+        int k = i + 1;
+        for (; k + 1 <= j; k += 2) {
+          a0 += R[i + (size_t)b * k] * R[k + (size_t)b * j];
+          a1 += R[i + (size_t)b * (k + 1)] * R[k + 1 + (size_t)b * j];
+        }
+        if (k <= j) a0 += R[i + (size_t)b * k] * R[k + (size_t)b * j];
+        v = -(a0 + a1) / R[i + (size_t)b * i];
+      }
     }
+    __syncthreads();
+    if (j < b && j >= i) R[i + (size_t)b * j] = v;
+    __syncthreads();
   }
 }
 // W <- W X in place (X upper triangular b x b): each warp owns 8-row tiles, reads the whole tile row (b/4 A fragments) into
@@ -331,7 +343,8 @@ __device__ inline void blk_trmm_dmma(double* W, const int rows, const int b, con
     }
   }
 }
-// G: shared b*b; Xg: b*b (global scratch is fine); Racc: shared b*b (only touched when want_R); dsc: b doubles
+// G: shared b*b (Gram -> Cholesky factor -> its inverse, in place); Xg: b*b global temp (product of the two triangular
+// factors); Racc: shared b*b (only touched when want_R); dsc: b doubles; backup: global, rows x b with the block's ld
 __device__ inline bool cholqr2_orth(double* W, const int rows, const int b, const int ld, const bool want_R, double* Racc, double* G,
                                     double* Xg, double* dsc, double* backup, int* s_flag) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -362,7 +375,7 @@ __device__ inline bool cholqr2_orth(double* W, const int rows, const int b, cons
   for (int pass = 0; pass < 2; ++pass) {
     blk_gram_dmma(W, rows, b, ld, G);
     __syncthreads();
-    blk_chol_warp(G, b, pass == 0 ? 1e-13 : 0.5, s_flag);
+    blk_chol_cta(G, b, pass == 0 ? 1e-13 : 0.5, s_flag);
     __syncthreads();
     if (*s_flag == 0) {
       // too ill-conditioned for the Gram route: restore the input, the caller runs the Householder route
@@ -371,10 +384,6 @@ __device__ inline bool cholqr2_orth(double* W, const int rows, const int b, cons
       __syncthreads();
       return false;
     }
-    blk_tri_inverse(G, b, Xg);
-    __syncthreads();
-    blk_trmm_dmma(W, rows, b, ld, Xg);
-    __syncthreads();
     if (want_R) {
       if (pass == 0) {
         for (int idx = threadIdx.x; idx < b * b; idx += NT) {
@@ -387,13 +396,19 @@ __device__ inline bool cholqr2_orth(double* W, const int rows, const int b, cons
           double acc = 0.0;
           if (i <= j)
             for (int k = i; k <= j; ++k) acc += G[i + (size_t)b * k] * Racc[k + (size_t)b * j];
-          Xg[idx] = acc;  // R2 (R1 D), X is free again
+          Xg[idx] = acc;  // R2 (R1 D)
         }
         __syncthreads();
         for (int idx = threadIdx.x; idx < b * b; idx += NT) Racc[idx] = Xg[idx];
       }
       __syncthreads();
     }
+    for (int idx = threadIdx.x; idx < b * b; idx += NT)
+      if (idx % b > idx / b) G[idx] = 0.0;  // strictly lower part: the in-place inverse and the DMMA product read full tiles
+    __syncthreads();
+    blk_tri_inverse_inplace(G, b);
+    blk_trmm_dmma(W, rows, b, ld, G);
+    __syncthreads();
   }
   return true;
 }
