@@ -398,6 +398,9 @@ def run_gpu(args, rank, world, local_rank):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = bool(os.environ.get("MPBP_PROFILER_RANGE"))  # ncu --profile-from-start off: only the timed steps are visible
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStart()
     with torch.cuda.stream(stream):
         e0.record()
     for _ in range(args.steps):
@@ -405,6 +408,8 @@ def run_gpu(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     ctr_timed = bp.counters(reset=True)

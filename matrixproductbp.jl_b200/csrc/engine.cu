@@ -126,8 +126,8 @@ struct mpbp_state {
                              // squared iteration with Jacobi orthonormalisation when the block fits shared memory
   double tri_merge = 1;      // 1: the TSQR merge skips the zero panels of the stacked triangular chunk factors
   double kron_mma = 1;       // 1: DMMA Kronecker-carry kernel (k_kron_carry_mma), 0: scalar FP64 kernel (k_kron_carry)
-  double outlier_split = 0;  // > 0: ops costing more than this multiple of the mean of their launch group run in a
-                             // group of their own, TSQR-split, next to the other groups (0 = off; experimental)
+  double outlier_split = 1.7;  // > 0: ops costing more than this multiple of the mean of their launch group run in a
+                             // group of their own, TSQR-split, next to the other groups (0 = off).  1.7: N=256 bench 26.5 -> 23.4 s per step
   double level_balance = 1;  // stagger the cavity levels of the nodes of a chunk so that every round carries similar work
   double damp = 0.0;  // set by mpbp_iterate for the duration of the call
   // options
