@@ -956,21 +956,57 @@ __global__ void __launch_bounds__(NT) k_jacobi_project(const OpDesc* ops, int t,
     const int mt = idx % dt, kk = (idx / dt) % keep, yx = idx / (dt * keep);
     O[idx] = kk < kuse ? A[(mt + dt * yx) + (size_t)order[kk] * p] : 0.0;
   }
-  // carry Pc_t[kk + keep*n] = sum_a U[a,kk] G[a; n]
+  // carry Pc_t[kk + keep*n] = sum_a U[a,kk] G[a; n]   (a = mt + dt*yx): a (Dr x keep) = G^T (Dr x p) U (p x keep) GEMM on the
+  // tensor pipe.  K runs over (yx, mt in steps of 4) so that no index division is needed; rows of U beyond kuse are zero.
   double* Pn = op.Pc[t & 1];
   double mx = 0.0;
-  for (int idx = threadIdx.x; idx < keep * Dr; idx += NT) {
-    const int kk = idx % keep, n = idx / keep;
-    const double* u = A + (size_t)order[kk < kuse ? kk : 0] * p;
-    double acc = 0.0;
-    for (int yx = 0; yx < (kk < kuse ? X : 0); ++yx) {
-      const double* g = op.G + (size_t)dt * (n + (size_t)Dr * yx);
-      const double* uu = u + dt * yx;
-      for (int mt = 0; mt < dt; ++mt) acc += uu[mt] * g[mt];
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q4 = lane & 3;
+    const int ntk = (keep + 7) >> 3;  // <= 4 (dcap <= 30)
+    for (int mtile = warp; mtile < (Dr + 7) / 8; mtile += NW) {
+      const int n = 8 * mtile + g;
+      const bool nok = n < Dr;
+      double acc[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
+      const double* ub[4];
+      bool uok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = 8 * j + g;
+        uok[j] = j < ntk && kk < kuse;
+        ub[j] = A + (size_t)order[uok[j] ? kk : 0] * p;
+      }
+      for (int yx = 0; yx < X; ++yx) {
+        const double* gp = op.G + (size_t)dt * (n + (size_t)Dr * yx);
+        for (int m0 = 0; m0 < dt; m0 += 4) {
+          const int mt = m0 + q4;
+          const bool kok = mt < dt;
+          const double af = (nok && kok) ? gp[mt] : 0.0;
+          const int a = mt + dt * yx;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < ntk) dmma884(acc[j][0], acc[j][1], af, (uok[j] && kok) ? ub[j][a] : 0.0);
+        }
+      }
+      if (nok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < ntk) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int kk = 8 * j + 2 * q4 + e;
+              if (kk < keep) {
+                Pn[kk + (size_t)keep * n] = acc[j][e];
+                mx = fmax(mx, fabs(acc[j][e]));
+              }
+            }
+          }
+        }
+      }
     }
-    Pn[idx] = acc;
-    mx = fmax(mx, fabs(acc));
   }
+  __syncthreads();
   mx = block_max(mx, red);
   if (mx > 0.0 && isfinite(mx)) {
     const double f = 1.0 / mx;
