@@ -118,9 +118,12 @@ class DistMPBP:
     def iterate(self, maxiter, tol=0.0):
         """returns (iters, deltas): Delta is the max over ranks (all-reduce MAX), as CB_BP would see it."""
         import torch
+        import time
         deltas = []
         for it in range(maxiter):
-            d = self.backend.iterate_owned()
+            t0 = time.perf_counter()
+            d = self.backend.iterate_owned()  # synchronous (mpbp_iterate returns after the device is done)
+            self.compute_s = getattr(self, "compute_s", 0.0) + (time.perf_counter() - t0)
             self.halo_exchange()
             if self.world > 1:
                 t = torch.tensor([d], dtype=torch.float64, device=self.device)

@@ -1,4 +1,4 @@
-// qr_chain2.cu -- PROTOTYPE (not part of the product library, never validated on a GPU yet): flat-tree DMMA Q-less QR
+// qr_chain2.cu -- PROTOTYPE (not part of the product library; measured and rejected in round 2): flat-tree DMMA Q-less QR
 // with TWO alternating panel-chain warps and look-ahead depth 2.  Written at the end of round 1 from the measured
 // per-panel budget of the product kernel (profiles/r01_qr_ft_ncu.md): on the panel warp, barrier 800 + look-ahead
 // slab update 2240 + panel load 435 + eight Householder columns 4970 cycles, i.e. the serial chain binds on every
@@ -13,6 +13,8 @@
 //                        holds slab s+1 fully up to date and becomes the producer of step s+1;
 //     warps 1,2,3,5,6,7: apply panel s-1 to the slabs >= s+2 (DMMA), exactly as the product kernel does.
 //   Expected critical path per panel: ~5000 (columns) + ~350 (last streamed reflector) instead of ~8900 cycles.
+//   MEASURED (round 2, profiles/r02_qr_chain2_result.txt): correct on the first run (error 4e-15) but SLOWER than the product
+//   kernel, 8.4 vs 10.0 TF/s at 1600x400x148: the per-column publish lengthens the producer chain by more than it saves.
 //
 // Build / run on a B200:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o tools/qr_chain2 tools/qr_chain2.cu
