@@ -118,7 +118,10 @@ struct mpbp_state {
                              // OFF by default: measured slower (N=256 bench 22.8 s vs 19.0 s per step) -- a hub kernel can only start
                              // when a bulk CTA retires, and the bulk QR CTAs run for 6-30 ms each, so the ~4500 sequential hub
                              // launches of a step queue behind them; kept as an option for graphs whose bulk CTAs are short.
-  double hub_frac = 0.3;     // share of the chunk's cost the hub lane may take
+  double hub_frac = 0.3;
+  double lanes = 0;          // >= 2: lane mode, the nodes of a chunk are dealt (cost-balanced) into that many lanes, each running
+                             // the whole cavity DAG of its nodes on its own stream with no barrier across lanes (1xx: also for
+                             // tiny chunks, tests)     // share of the chunk's cost the hub lane may take
   cudaStream_t hub_st = nullptr;
   cudaEvent_t ev_hub_fork = nullptr, ev_hub_join = nullptr;
   double svd_mode = 2;       // truncating SVD of large matrices: 2 (default) un-squared block iteration, blocks orthonormalised by
@@ -294,8 +297,11 @@ struct Plan {
   std::vector<std::vector<int>> capA, capB;  // bond capacities of the operands per op (1 or dmax)
   // hub lane: the ops of the few high-degree nodes of the chunk, whose level chains are the critical path; they run on
   // their own stream, concurrently with the rounds of the bulk
-  std::vector<std::vector<OpDesc>> hlevels;
-  std::vector<std::vector<int>> hcapA, hcapB;
+  struct Lane {
+    std::vector<std::vector<OpDesc>> levels;
+    std::vector<std::vector<int>> capA, capB;
+  };
+  std::vector<Lane> lanes;  // index = lane id - 1 (lane id 0 = the bulk rounds above)
   std::vector<FinJob> fin;
   std::vector<FinJob> gfin;    // generic path: the dummy-neighbour message of every generic node (compressed before it is
   std::vector<MargJob> gmarg;  // marginalised into the belief, src/mpbp.jl:145-154), and the marginals read from it
@@ -463,20 +469,22 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
   // level offsets are planned per lane (each lane balances its own rounds)
   std::vector<int> lev_off(nodes.size(), 0);
   {
-    std::vector<int64_t> nb, nh;
-    std::vector<size_t> ib, ih;
-    for (size_t k = 0; k < nodes.size(); ++k) {
-      if (hub[k]) { nh.push_back(nodes[k]); ih.push_back(k); }
-      else { nb.push_back(nodes[k]); ib.push_back(k); }
+    int nl = 0;
+    for (char c : hub) nl = std::max(nl, (int)c);
+    P.lanes.resize(nl);
+    for (int lane = 0; lane <= nl; ++lane) {
+      std::vector<int64_t> nn;
+      std::vector<size_t> ii;
+      for (size_t k = 0; k < nodes.size(); ++k)
+        if (hub[k] == lane) { nn.push_back(nodes[k]); ii.push_back(k); }
+      const std::vector<int> o = plan_level_offsets(h, nn);
+      for (size_t k = 0; k < ii.size(); ++k) lev_off[ii[k]] = o[k];
     }
-    const std::vector<int> ob = plan_level_offsets(h, nb), oh = plan_level_offsets(h, nh);
-    for (size_t k = 0; k < ib.size(); ++k) lev_off[ib[k]] = ob[k];
-    for (size_t k = 0; k < ih.size(); ++k) lev_off[ih[k]] = oh[k];
   }
   for (size_t inode = 0; inode < nodes.size(); ++inode) {
     const int64_t i = nodes[inode];
     const int loff = lev_off[inode];
-    const bool in_hub = hub[inode] != 0;
+    const int lane_id = hub[inode];
     const int ci = h->class_of_node[i];
     if (ci < 0 || ci >= (int)h->classes.size()) return fail("node %lld has no factor class", (long long)i);
     const NodeClass& c = h->classes[ci];
@@ -660,9 +668,9 @@ int build_plan(mpbp_state* h, const std::vector<int64_t>& nodes, const std::vect
       op.o = out;
       op.pyy = c.d_pyy + it->second.first;
       op.pyy_tstride = (int)it->second.second;
-      auto& LV = in_hub ? P.hlevels : P.levels;
-      auto& CA = in_hub ? P.hcapA : P.capA;
-      auto& CB = in_hub ? P.hcapB : P.capB;
+      auto& LV = lane_id ? P.lanes[lane_id - 1].levels : P.levels;
+      auto& CA = lane_id ? P.lanes[lane_id - 1].capA : P.capA;
+      auto& CB = lane_id ? P.lanes[lane_id - 1].capB : P.capB;
       if ((int)LV.size() <= level) {
         LV.resize(level + 1);
         CA.resize(level + 1);
@@ -959,6 +967,27 @@ bool alloc_op_scratch(mpbp_state* h, OpDesc& op, int ca, int cb) {
 // path of a step; run next to the bulk instead of inside its rounds they no longer stretch every round.
 std::vector<char> pick_hub_nodes(const mpbp_state* h, const std::vector<int64_t>& nodes) {
   std::vector<char> hub(nodes.size(), 0);
+  if (h->lanes >= 2 && !h->profile && h->inf_k == 0 && (nodes.size() >= 64 || h->lanes >= 100)) {
+    // lane mode: EVERY node goes to one of G lanes (longest-processing-time greedy on the node cost); a lane runs the whole
+    // cavity DAG of its nodes on its own stream, level after level, with no barrier across lanes
+    const int G = std::min((int)h->lanes % 100, 1 + mpbp_state::NAUX);
+    std::vector<std::pair<double, size_t>> cost(nodes.size());
+    for (size_t k = 0; k < nodes.size(); ++k) {
+      const int ci = h->class_of_node[nodes[k]];
+      double w = 1.0;
+      if (ci >= 0 && ci < (int)h->classes.size() && !h->classes[ci].generic)
+        for (double v : node_level_cost(h->classes[ci], h->dmax)) w += v;
+      cost[k] = {w, k};
+    }
+    std::stable_sort(cost.begin(), cost.end(), [](const std::pair<double, size_t>& a, const std::pair<double, size_t>& b) { return a.first > b.first; });
+    std::vector<double> load(G, 0.0);
+    for (auto& c : cost) {
+      const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      hub[c.second] = (char)(g + 1);
+      load[g] += c.first;
+    }
+    return hub;
+  }
   if (h->hub_lane <= 0 || (nodes.size() < 64 && h->hub_lane < 2) || h->inf_k > 0) return hub;
   std::map<int, double> cost_by_z;
   std::vector<int> zs(nodes.size(), -1);
@@ -1018,85 +1047,123 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     k_init_tt<<<(unsigned)P.init.size(), 64, 0, st>>>(d_init, (int)P.init.size(), L);
     h->n_launch++;
   }
-  // ---- hub lane: every level of the high-degree nodes, enqueued back to back on its own stream (no host sync: the
-  // scratch region below is reused level after level in stream order) ----
+  // ---- lanes: every level of a lane's nodes is enqueued back to back on the lane's stream (no host sync: the lane's scratch
+  // region is reused level after level in stream order); the kernels of the lanes are issued interleaved site by site ----
   size_t persistent = h->arena.used;
-  bool hub_running = false;
-  if (!P.hlevels.empty()) {
-    // scratch region = the largest level; if it would take more than 40 % of what is left, run the hubs with the bulk
-    size_t need = 0;
-    for (size_t lev = 1; lev < P.hlevels.size(); ++lev) {
-      size_t nl = sizeof(OpDesc) * P.hlevels[lev].size() + 4096;
-      for (size_t k = 0; k < P.hlevels[lev].size(); ++k)
-        nl += op_scratch_bytes(h, P.hcapA[lev][k], P.hcapB[lev][k], P.hlevels[lev][k].nyo * P.hlevels[lev][k].q) + 4096;
-      need = std::max(need, nl);
+  if (!P.lanes.empty()) {
+    const int NL = (int)P.lanes.size();
+    // scratch region of a lane = its largest level
+    std::vector<size_t> need(NL, 0);
+    size_t need_all = 0, maxlev = 0;
+    for (int g = 0; g < NL; ++g) {
+      auto& LN = P.lanes[g];
+      maxlev = std::max(maxlev, LN.levels.size());
+      for (size_t lev = 1; lev < LN.levels.size(); ++lev) {
+        size_t nl = sizeof(OpDesc) * LN.levels[lev].size() + 4096;
+        for (size_t k = 0; k < LN.levels[lev].size(); ++k)
+          nl += op_scratch_bytes(h, LN.capA[lev][k], LN.capB[lev][k], LN.levels[lev][k].nyo * LN.levels[lev][k].q) + 4096;
+        need[g] = std::max(need[g], nl);
+      }
+      need_all += need[g];
     }
-    if (need > (size_t)(0.4 * (double)(h->arena.cap - persistent))) {
-      // merge the lanes again (level by level; the result does not depend on the lane)
-      for (size_t lev = 1; lev < P.hlevels.size(); ++lev) {
-        if (P.levels.size() <= lev) { P.levels.resize(lev + 1); P.capA.resize(lev + 1); P.capB.resize(lev + 1); }
-        for (size_t k = 0; k < P.hlevels[lev].size(); ++k) {
-          P.levels[lev].push_back(P.hlevels[lev][k]);
-          P.capA[lev].push_back(P.hcapA[lev][k]);
-          P.capB[lev].push_back(P.hcapB[lev][k]);
+    const bool all_lanes = P.levels.empty();  // lane mode proper: nothing left for the bulk rounds
+    if (need_all > (size_t)((all_lanes ? 0.95 : 0.4) * (double)(h->arena.cap - persistent))) {
+      // does not fit: merge the lanes into the bulk rounds (level by level; the result does not depend on the lane)
+      for (int g = 0; g < NL; ++g) {
+        auto& LN = P.lanes[g];
+        for (size_t lev = 1; lev < LN.levels.size(); ++lev) {
+          if (P.levels.size() <= lev) { P.levels.resize(lev + 1); P.capA.resize(lev + 1); P.capB.resize(lev + 1); }
+          for (size_t k = 0; k < LN.levels[lev].size(); ++k) {
+            P.levels[lev].push_back(LN.levels[lev][k]);
+            P.capA[lev].push_back(LN.capA[lev][k]);
+            P.capB[lev].push_back(LN.capB[lev][k]);
+          }
         }
       }
-      P.hlevels.clear();
+      P.lanes.clear();
     } else {
-      // in profile mode the lane runs inline on the main stream so that per-family event times stay exclusive
-      cudaStream_t hs = h->profile ? st : h->hub_st;
-      if (hs != st) {
-        CUDA_OK(cudaEventRecord(h->ev_hub_fork, st));
-        CUDA_OK(cudaStreamWaitEvent(hs, h->ev_hub_fork, 0));
-      }
-      const size_t hub_lo = persistent;
-      for (size_t lev = 1; lev < P.hlevels.size(); ++lev) {
-        auto& ops = P.hlevels[lev];
-        if (ops.empty()) continue;
-        h->arena.used = hub_lo;
-        OpDesc* d_ops = (OpDesc*)h->arena.take(sizeof(OpDesc) * ops.size());
-        bool fit = d_ops != nullptr;
-        GroupRun gr;
-        memset(&gr, 0, sizeof gr);
-        gr.nops = (int)ops.size(); gr.maxD = 1; gr.maxX = 1; gr.maxNy = 1; gr.maxq = 1; gr.maxNyS = 1;
-        gr.st = hs;
-        // heaviest first (LPT), as in the bulk launches
-        std::vector<size_t> idx(ops.size());
-        for (size_t k = 0; k < idx.size(); ++k) idx[k] = k;
-        auto cost = [&](size_t k) { return (double)P.hcapA[lev][k] * P.hcapB[lev][k] * ops[k].nyo * ops[k].q; };
-        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
-        std::vector<OpDesc> sorted(ops.size());
-        for (size_t k = 0; k < idx.size() && fit; ++k) {
-          OpDesc op = ops[idx[k]];
-          const int ca = P.hcapA[lev][idx[k]], cb = P.hcapB[lev][idx[k]];
-          fit = alloc_op_scratch(h, op, ca, cb);
-          sorted[k] = op;
-          gr.maxD = std::max(gr.maxD, ca * cb);
-          gr.maxX = std::max(gr.maxX, op.nyo * op.q);
-          gr.maxNy = std::max(gr.maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
-          gr.maxq = std::max(gr.maxq, op.q);
-          gr.maxNyS = std::max(gr.maxNyS, std::min(op.ny1, op.ny2));
+      // streams: the hub lane (one lane next to the bulk rounds) runs on its high-priority stream; in lane mode lane g runs
+      // on the main stream (g = 0) or an auxiliary one; in profile mode everything runs inline on the main stream
+      std::vector<cudaStream_t> ls(NL);
+      for (int g = 0; g < NL; ++g) ls[g] = h->profile ? st : (all_lanes ? (g == 0 ? st : h->aux[g - 1]) : h->hub_st);
+      // scratch pointers are a pure function of the plan: build the descriptors of EVERY (lane, level) first and upload
+      // them with one copy (an async copy from pageable memory synchronises its stream, which would put a host-side barrier
+      // between the levels of a lane)
+      size_t ndesc = 0;
+      for (int g = 0; g < NL; ++g)
+        for (size_t lev = 1; lev < P.lanes[g].levels.size(); ++lev) ndesc += P.lanes[g].levels[lev].size();
+      h->arena.used = persistent;
+      OpDesc* d_all = (OpDesc*)h->arena.take(sizeof(OpDesc) * std::max<size_t>(ndesc, 1));
+      if (!d_all) return fail("arena exhausted (lane descriptors)");
+      std::vector<size_t> lo(NL);
+      size_t acc = h->arena.used;
+      for (int g = 0; g < NL; ++g) { lo[g] = acc; acc += need[g]; }
+      if (acc > h->arena.cap) return fail("arena exhausted (lane scratch)");
+      std::vector<OpDesc> all_desc;
+      all_desc.reserve(ndesc);
+      std::vector<std::vector<GroupRun>> level_groups(maxlev);
+      for (size_t lev = 1; lev < maxlev; ++lev) {
+        for (int g = 0; g < NL; ++g) {
+          auto& LN = P.lanes[g];
+          if (lev >= LN.levels.size() || LN.levels[lev].empty()) continue;
+          auto& ops = LN.levels[lev];
+          h->arena.used = lo[g];
+          bool fit = true;
+          GroupRun gr;
+          memset(&gr, 0, sizeof gr);
+          gr.nops = (int)ops.size(); gr.maxD = 1; gr.maxX = 1; gr.maxNy = 1; gr.maxq = 1; gr.maxNyS = 1;
+          gr.st = ls[g];
+          // heaviest first (LPT), as in the bulk launches
+          std::vector<size_t> idx(ops.size());
+          for (size_t k = 0; k < idx.size(); ++k) idx[k] = k;
+          auto cost = [&](size_t k) { return (double)LN.capA[lev][k] * LN.capB[lev][k] * ops[k].nyo * ops[k].q; };
+          std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+          gr.d_ops = d_all + all_desc.size();
+          for (size_t k = 0; k < idx.size() && fit; ++k) {
+            OpDesc op = ops[idx[k]];
+            const int ca = LN.capA[lev][idx[k]], cb = LN.capB[lev][idx[k]];
+            fit = alloc_op_scratch(h, op, ca, cb);
+            all_desc.push_back(op);
+            gr.maxD = std::max(gr.maxD, ca * cb);
+            gr.maxX = std::max(gr.maxX, op.nyo * op.q);
+            gr.maxNy = std::max(gr.maxNy, std::max(op.nyo, std::max(op.ny1, op.ny2)));
+            gr.maxq = std::max(gr.maxq, op.q);
+            gr.maxNyS = std::max(gr.maxNyS, std::min(op.ny1, op.ny2));
+          }
+          if (!fit || h->arena.used > lo[g] + need[g]) return fail("arena exhausted in lane %d (internal sizing error)", g);
+          const int fill_split = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(gr.nops * (all_lanes ? NL : 1), 1))));
+          gr.nsplit = std::max(fill_split, std::min(QR_NSPLIT_MAX, (int)h->bulk_split));
+          gr.split_min = fill_split >= 2 ? 0 : (int)h->bulk_split_min;
+          level_groups[lev].push_back(gr);
+          h->n_ops += gr.nops;
         }
-        if (!fit) return fail("arena exhausted in the hub lane (internal sizing error)");
-        CUDA_OK(cudaMemcpyAsync(d_ops, sorted.data(), sizeof(OpDesc) * sorted.size(), cudaMemcpyHostToDevice, hs));
-        gr.d_ops = d_ops;
-        gr.nsplit = std::max(1, std::min(QR_NSPLIT_MAX, (int)(h->qr_fill / std::max(gr.nops, 1))));
-        gr.split_min = 0;
-        std::vector<GroupRun> one(1, gr);
-        if (run_op_groups(h, one, tr)) {
-          cudaStreamSynchronize(hs);
+      }
+      CUDA_OK(cudaMemcpyAsync(d_all, all_desc.data(), sizeof(OpDesc) * all_desc.size(), cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaEventRecord(h->ev_hub_fork, st));
+      for (int g = 0; g < NL; ++g)
+        if (ls[g] != st) CUDA_OK(cudaStreamWaitEvent(ls[g], h->ev_hub_fork, 0));
+      for (size_t lev = 1; lev < maxlev; ++lev) {
+        if (level_groups[lev].empty()) continue;
+        if (run_op_groups(h, level_groups[lev], tr)) {
+          for (int k = 0; k < mpbp_state::NAUX; ++k) cudaStreamSynchronize(h->aux[k]);
+          cudaStreamSynchronize(h->hub_st);
+          cudaStreamSynchronize(st);
           return 1;
         }
-        h->n_ops += gr.nops;
       }
-      persistent = hub_lo + need;
+      persistent = acc;
       h->arena.used = persistent;
-      if (hs != st) {
-        CUDA_OK(cudaEventRecord(h->ev_hub_join, hs));
-        hub_running = true;
-      } else {
+      if (h->profile) {
         CUDA_OK(cudaStreamSynchronize(st));
         ev_flush(h);
+      } else {
+        // join: the main stream waits for every lane stream
+        for (int g = 0; g < NL; ++g)
+          if (ls[g] != st) {
+            cudaEvent_t ev = all_lanes ? h->ev_join[g - 1] : h->ev_hub_join;
+            CUDA_OK(cudaEventRecord(ev, ls[g]));
+            CUDA_OK(cudaStreamWaitEvent(st, ev, 0));
+          }
       }
     }
   }
@@ -1217,7 +1284,6 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
     }
   }
   h->arena.used = persistent;
-  if (hub_running) CUDA_OK(cudaStreamWaitEvent(st, h->ev_hub_join, 0));
   // ---- outgoing messages, beliefs, free energy ----
   {
     int qm = h->qmax;
@@ -2102,6 +2168,7 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "tri_merge") h->tri_merge = value;
   else if (n == "svd_mode") h->svd_mode = value;
   else if (n == "hub_frac") h->hub_frac = value;
+  else if (n == "lanes") h->lanes = value;
   else if (n == "twovar") {
     // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
     h->twovar = value > 0 ? (int)std::min<double>(value, h->L) : 0;

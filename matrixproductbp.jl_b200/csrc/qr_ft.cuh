@@ -40,7 +40,7 @@ __host__ __device__ inline int ft_ld(int n) {
 __device__ __forceinline__ int ft_sw(int row) { return ((row >> 1) & 1) << 2; }
 template <int H>
 __host__ __device__ inline size_t ft_smem_doubles(int n) {
-  return (size_t)H * ft_ld(n) + 2 * (FT_B * (H + 4) + FT_B * FT_B) + NW * 72 + 16 + (H == 64 ? 2 * 128 : 0);
+  return (size_t)H * ft_ld(n) + 2 * (FT_B * (H + 4) + FT_B * FT_B) + NW * 72 + 16 + (H == 64 ? 2 * 128 : 0) + 288;
 }
 
 // H = 64: the otherwise idle partner warp of the panel warp stages, one panel ahead, the two 8x8 blocks of R the panel
@@ -50,12 +50,19 @@ __host__ __device__ inline size_t ft_smem_doubles(int n) {
 __device__ __forceinline__ void ft_prefetch_R(const double* __restrict__ R, const int ldr, const int n, const int jpt, double* dst) {
   const int lane = threadIdx.x & 31;
   const int j0 = jpt * FT_B, c0 = j0 + FT_B;
+  // four independent loads in flight (clamped address + select: no branch between them), then the stores
+  double v[4];
 #pragma unroll
-  for (int e = lane; e < 128; e += 32) {
+  for (int i = 0; i < 4; ++i) {
+    const int e = lane + 32 * i;
     const int r = (e >> 3) & 7, c = e & 7;
     const int row = ((e >> 6) ? c0 : j0) + r, col = c0 + c;
-    dst[e] = (row < n && col < n) ? R[(size_t)row * ldr + col] : 0.0;
+    const bool ok = (row < n && col < n);
+    const double x = R[ok ? (size_t)row * ldr + col : (size_t)0];
+    v[i] = ok ? x : 0.0;
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = v[i];
 }
 
 // Householder factorisation of [R_jj ; Ablk[:, j0..j0+8)] by ONE warp.  Writes V^T (A part) to Vt (8 x LDV), the
@@ -184,6 +191,390 @@ __device__ __forceinline__ void ft_panel(const double* Ablk, const int ld, const
     }
 }
 
+// ft_panel with fewer instructions on the (issue-bound) panel warp: the eight reduced dots go through a 16-double warp
+// scratch (one store + four broadcast loads instead of 16 shuffles), and row k of R_jj is read from the staged copy when
+// there is one (broadcast loads instead of shuffles).  scr: >= 16 doubles of warp-private shared memory.
+template <int H>
+__device__ __forceinline__ void ft_panel_l(const double* Ablk, const int ld, const int j0, const int n, double* __restrict__ R,
+                                         const int ldr, double* Vt, double* Tm, const double* __restrict__ rjj_s, double* __restrict__ scr) {
+  constexpr int LDV = H + 4;
+  constexpr int RPL = (H + 31) / 32;  // rows of the block per lane
+  const int lane = threadIdx.x & 31;
+  double a[RPL][FT_B];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    const int row = lane + 32 * r;
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) a[r][c] = (row < H) ? Ablk[(size_t)row * ld + ((j0 + c) ^ ft_sw(row))] : 0.0;
+  }
+  // R_jj (8x8 upper) preloaded once: lane k holds row j0+k; rows are broadcast with shuffles
+  double rrow[FT_B];
+#pragma unroll
+  for (int c = 0; c < FT_B; ++c) {
+    if (rjj_s) rrow[c] = (lane < FT_B && c >= lane) ? rjj_s[lane * FT_B + c] : 0.0;  // staged by ft_prefetch_R (zero padded)
+    else rrow[c] = (lane < FT_B && j0 + lane < n && j0 + c < n && c >= lane) ? R[(size_t)(j0 + lane) * ldr + j0 + c] : 0.0;
+  }
+  // compact-WY T, ONE ROW PER LANE (lane x < 8 holds row x; T is upper triangular, so the zeros left of the diagonal make
+  // the recurrence index-free): 2k+3 instead of k(k+3)/2 + k FP64 instructions in column step k
+  double Trow[FT_B];
+#pragma unroll
+  for (int y = 0; y < FT_B; ++y) Trow[y] = 0.0;
+#pragma unroll
+  for (int k = 0; k < FT_B; ++k) {
+    // one batched reduction: red[c] = a_k . a_c (c >= k)  and  red[l] = v_l . a_k (l < k)
+    double red[FT_B];
+    {
+      // transpose-reduce: 4+2+1+1+1 shuffles leave every lane with one complete sum, 8 more broadcast them
+      double w4[4], w2[2];
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double lo = 0.0, hi = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+          lo += a[r][k] * a[r][i];
+          hi += a[r][k] * a[r][i + 4];
+        }
+        const double send = b4 ? lo : hi, keep = b4 ? hi : lo;
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double send = b3 ? w4[i] : w4[i + 2], keep = b3 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      double tsum;
+      {
+        const double send = b2 ? w2[0] : w2[1], keep = b2 ? w2[1] : w2[0];
+        tsum = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+      // lane bits 4,3,2 = column bits 2,1,0: every lane stores its sum, four broadcast loads hand all eight to every lane
+      double* rb = scr + ((k & 1) << 3);
+      rb[(((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1)] = tsum;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < FT_B; c += 2) {
+        const double2 t2 = *reinterpret_cast<const double2*>(rb + c);
+        red[c] = t2.x;
+        red[c + 1] = t2.y;
+      }
+    }
+    double rk[FT_B];
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) rk[c] = (c >= k) ? (rjj_s ? rjj_s[k * FT_B + c] : __shfl_sync(0xffffffffu, rrow[c], k)) : 0.0;
+    const double alpha = rk[k], sig2 = red[k];
+    double tau = 0.0, sc = 0.0, beta = alpha;
+    if (sig2 > 0.0) {
+      const double n2 = alpha * alpha + sig2;
+      const double rs = rsqrt(n2);          // 1/||x||
+      const double nrm = n2 * rs;
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      const double u = alpha - beta;         // |u| = |alpha| + nrm, no cancellation
+      tau = alpha >= 0.0 ? u * rs : -u * rs; // (beta - alpha)/beta = -u/beta
+      sc = 1.0 / u;
+    }
+    double v[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      v[r] = a[r][k] * sc;
+      a[r][k] = v[r];
+    }
+#pragma unroll
+    for (int c = k + 1; c < FT_B; ++c) {
+      const double s = tau * (rk[c] + sc * red[c]);
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) a[r][c] -= s * v[r];
+      rk[c] -= s;
+    }
+    if (lane == k) {
+      rrow[k] = beta;
+#pragma unroll
+      for (int c = k + 1; c < FT_B; ++c) rrow[c] = rk[c];
+    }
+    // T(0:k,k) = -tau * T(0:k,0:k) * (V_A(:,0:k)^T v_k);   V_l^T v_k = sc * red[l]
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < k; ++l) acc += Trow[l] * (sc * red[l]);
+      Trow[k] = (lane == k) ? tau : ((lane < k) ? -tau * acc : 0.0);
+    }
+  }
+  if (lane < FT_B && j0 + lane < n) {
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c)
+      if (c >= lane && j0 + c < n) R[(size_t)(j0 + lane) * ldr + j0 + c] = rrow[c];
+  }
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    const int row = lane + 32 * r;
+    if (row < H) {
+#pragma unroll
+      for (int k = 0; k < FT_B; ++k) Vt[k * LDV + row] = a[r][k];
+    }
+  }
+  if (lane < FT_B) {
+#pragma unroll
+    for (int y = 0; y < FT_B; ++y) Tm[lane * FT_B + y] = Trow[y];
+  }
+}
+
+// ft_panel_l with the cross-lane reduction of the eight dots done through shared memory: every lane stores its eight
+// partial dots (column-major 8 x 36 scratch, conflict-free), lane (c, qt) = (lane >> 2, lane & 3) adds the eight partials
+// i*4+qt of column c, two shuffle levels finish the sum -- 36 instead of 61 instructions per column step on the
+// issue-bound panel warp.  STAGED: row k of R_jj is read from / written back to the 64-double staged block rjj (shared
+// memory) and the block is copied to global memory once at the end.  pred: 288 doubles, scr: 16 doubles (warp-private).
+template <int H, bool STAGED>
+__device__ __forceinline__ void ft_panel_m(const double* Ablk, const int ld, const int j0, const int n, double* __restrict__ R,
+                                           const int ldr, double* Vt, double* Tm, double* rjj, double* scr, double* pred) {
+  constexpr int LDV = H + 4;
+  constexpr int RPL = (H + 31) / 32;
+  constexpr int LDP = 36;
+  const int lane = threadIdx.x & 31;
+  double a[RPL][FT_B];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    const int row = lane + 32 * r;
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) a[r][c] = (row < H) ? Ablk[(size_t)row * ld + ((j0 + c) ^ ft_sw(row))] : 0.0;
+  }
+  double rrow[FT_B];
+  if (!STAGED) {
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c)
+      rrow[c] = (lane < FT_B && j0 + lane < n && j0 + c < n && c >= lane) ? R[(size_t)(j0 + lane) * ldr + j0 + c] : 0.0;
+  }
+  double Trow[FT_B];
+#pragma unroll
+  for (int y = 0; y < FT_B; ++y) Trow[y] = 0.0;
+  const int pc = lane >> 2, pq = lane & 3;
+  const double* prd = pred + pc * LDP + pq;
+#pragma unroll
+  for (int k = 0; k < FT_B; ++k) {
+    double rk[FT_B];
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) {
+      if (STAGED) rk[c] = (c >= k) ? rjj[k * FT_B + c] : 0.0;
+      else rk[c] = (c >= k) ? __shfl_sync(0xffffffffu, rrow[c], k) : 0.0;
+    }
+    // red[c] = a_k . a_c (c >= k)  and  red[l] = v_l . a_k (l < k)
+    double red[FT_B];
+    {
+#pragma unroll
+      for (int i = 0; i < FT_B; ++i) {
+        double pp = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) pp += a[r][k] * a[r][i];
+        pred[i * LDP + lane] = pp;
+      }
+      __syncwarp();
+      double x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = prd[4 * i];
+      double tsum = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+      double* rb = scr + ((k & 1) << 3);
+      rb[pc] = tsum;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < FT_B; c += 2) {
+        const double2 t2 = *reinterpret_cast<const double2*>(rb + c);
+        red[c] = t2.x;
+        red[c + 1] = t2.y;
+      }
+    }
+    const double alpha = rk[k], sig2 = red[k];
+    double tau = 0.0, sc = 0.0, beta = alpha;
+    if (sig2 > 0.0) {
+      const double n2 = alpha * alpha + sig2;
+      const double rs = rsqrt(n2);
+      const double nrm = n2 * rs;
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      const double u = alpha - beta;
+      tau = alpha >= 0.0 ? u * rs : -u * rs;
+      sc = 1.0 / u;
+    }
+    double v[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      v[r] = a[r][k] * sc;
+      a[r][k] = v[r];
+    }
+#pragma unroll
+    for (int c = k + 1; c < FT_B; ++c) {
+      const double s = tau * (rk[c] + sc * red[c]);
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) a[r][c] -= s * v[r];
+      rk[c] -= s;
+    }
+    rk[k] = beta;
+    if (STAGED) {
+      if (lane == 0) {
+#pragma unroll
+        for (int c = k; c < FT_B; ++c) rjj[k * FT_B + c] = rk[c];
+      }
+    } else {
+      if (lane == k) {
+#pragma unroll
+        for (int c = k; c < FT_B; ++c) rrow[c] = rk[c];
+      }
+    }
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < k; ++l) acc += Trow[l] * (sc * red[l]);
+      Trow[k] = (lane == k) ? tau : ((lane < k) ? -tau * acc : 0.0);
+    }
+  }
+  if (STAGED) {
+    __syncwarp();
+#pragma unroll
+    for (int e = lane; e < FT_B * FT_B; e += 32) {
+      const int r = e >> 3, c = e & 7;
+      if (c >= r && j0 + r < n && j0 + c < n) R[(size_t)(j0 + r) * ldr + j0 + c] = rjj[e];
+    }
+  } else if (lane < FT_B && j0 + lane < n) {
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c)
+      if (c >= lane && j0 + c < n) R[(size_t)(j0 + lane) * ldr + j0 + c] = rrow[c];
+  }
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    const int row = lane + 32 * r;
+    if (row < H) {
+#pragma unroll
+      for (int k = 0; k < FT_B; ++k) Vt[k * LDV + row] = a[r][k];
+    }
+  }
+  if (lane < FT_B) {
+#pragma unroll
+    for (int y = 0; y < FT_B; ++y) Tm[lane * FT_B + y] = Trow[y];
+  }
+}
+
+#ifndef FT_PANEL_LEAN
+#define FT_PANEL_LEAN 2
+#endif
+#ifndef FT_PANEL_DMMA
+#define FT_PANEL_DMMA 0  // measured slower on B200 (10.5 vs 11.5 TF/s at 1600x400): the panel warp is issue-bound and this variant issues ~245 instead of ~200 instructions per column
+#endif
+
+// Same factorisation, column-per-lane-group layout: lane (g, q4) holds column j0+g at the rows 4s+q4 -- exactly the DMMA
+// A- AND B-fragment of the panel, so the dots of a column step come from the tensor pipe (G = P^T P, H/4 DMMAs whose
+// k-reduction replaces the five dependent shuffle levels of ft_panel) and the reflector update touches one column per
+// lane.  Row k of G sits in the four lanes g = k; eight broadcasts hand it to every lane, the scalar path is ft_panel's.
+template <int H>
+__device__ __forceinline__ void ft_panel_g(const double* Ablk, const int ld, const int j0, const int n, double* __restrict__ R,
+                                           const int ldr, double* Vt, double* Tm, const double* rjj_s = nullptr) {
+  constexpr int LDV = H + 4;
+  constexpr int NS = H / 4;  // rows per lane
+  const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+  double a[NS];
+  {
+    const double* bp = Ablk + (size_t)q4 * ld + ((j0 + g) ^ (((q4 >> 1) & 1) << 2));
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a[s] = bp[(size_t)(4 * s) * ld];
+  }
+  double rrow[FT_B];
+#pragma unroll
+  for (int c = 0; c < FT_B; ++c) {
+    if (rjj_s) rrow[c] = (lane < FT_B && c >= lane) ? rjj_s[lane * FT_B + c] : 0.0;
+    else rrow[c] = (lane < FT_B && j0 + lane < n && j0 + c < n && c >= lane) ? R[(size_t)(j0 + lane) * ldr + j0 + c] : 0.0;
+  }
+  double T[FT_B][FT_B];
+#pragma unroll
+  for (int x = 0; x < FT_B; ++x)
+#pragma unroll
+    for (int y = 0; y < FT_B; ++y) T[x][y] = 0.0;
+#pragma unroll
+  for (int k = 0; k < FT_B; ++k) {
+    // column k at this lane's rows (same q4 group, lane g = k); independent of the dots below
+    double ak[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) ak[s] = __shfl_sync(0xffffffffu, a[s], 4 * k + q4);
+    // G = P^T P on the tensor pipe, two accumulator chains
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int s = 0; s < NS; s += 2) {
+      dmma884(c0, c1, a[s], a[s]);
+      dmma884(e0, e1, a[s + 1], a[s + 1]);
+    }
+    c0 += e0;
+    c1 += e1;
+    // red[c] = G[k][c]: a_k . a_c (c >= k),  v_c . a_k (c < k)
+    double red[FT_B];
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) red[c] = __shfl_sync(0xffffffffu, (c & 1) ? c1 : c0, 4 * k + (c >> 1));
+    double rk[FT_B];
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c) rk[c] = (c >= k) ? __shfl_sync(0xffffffffu, rrow[c], k) : 0.0;
+    const double alpha = rk[k], sig2 = red[k];
+    double tau = 0.0, sc = 0.0, beta = alpha;
+    if (sig2 > 0.0) {
+      const double n2 = alpha * alpha + sig2;
+      const double rs = rsqrt(n2);
+      const double nrm = n2 * rs;
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      const double u = alpha - beta;
+      tau = alpha >= 0.0 ? u * rs : -u * rs;
+      sc = 1.0 / u;
+    }
+    // a_c -= s_c v (c > k), a_k <- v = a_k sc: this lane's column only
+    double coef = (g == k) ? sc : 0.0;
+#pragma unroll
+    for (int c = k + 1; c < FT_B; ++c) {
+      const double s = tau * (rk[c] + sc * red[c]);
+      rk[c] -= s;
+      if (g == c) coef = -(s * sc);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a[s] = fma(coef, ak[s], (g == k) ? 0.0 : a[s]);
+    if (lane == k) {
+      rrow[k] = beta;
+#pragma unroll
+      for (int c = k + 1; c < FT_B; ++c) rrow[c] = rk[c];
+    }
+    T[k][k] = tau;
+#pragma unroll
+    for (int x = 0; x < k; ++x) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = x; l < k; ++l) acc += T[x][l] * (sc * red[l]);
+      T[x][k] = -tau * acc;
+    }
+  }
+  if (lane < FT_B && j0 + lane < n) {
+#pragma unroll
+    for (int c = 0; c < FT_B; ++c)
+      if (c >= lane && j0 + c < n) R[(size_t)(j0 + lane) * ldr + j0 + c] = rrow[c];
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) Vt[g * LDV + 4 * s + q4] = a[s];
+#pragma unroll
+  for (int x = 0; x < FT_B; ++x)
+    if (lane == x) {
+#pragma unroll
+      for (int y = 0; y < FT_B; ++y) Tm[x * FT_B + y] = T[x][y];
+    }
+}
+
+template <int H>
+__device__ __forceinline__ void ft_panel_sel(const double* Ablk, const int ld, const int j0, const int n, double* __restrict__ R,
+                                             const int ldr, double* Vt, double* Tm, double* scr, double* pred, double* rjj_s = nullptr) {
+#if FT_PANEL_DMMA
+  ft_panel_g<H>(Ablk, ld, j0, n, R, ldr, Vt, Tm, rjj_s);
+#elif FT_PANEL_LEAN == 2
+  if (rjj_s) ft_panel_m<H, true>(Ablk, ld, j0, n, R, ldr, Vt, Tm, rjj_s, scr, pred);
+  else ft_panel_m<H, false>(Ablk, ld, j0, n, R, ldr, Vt, Tm, nullptr, scr, pred);
+#elif FT_PANEL_LEAN
+  ft_panel_l<H>(Ablk, ld, j0, n, R, ldr, Vt, Tm, rjj_s, scr);
+#else
+  ft_panel<H>(Ablk, ld, j0, n, R, ldr, Vt, Tm, rjj_s);
+#endif
+}
+
 // fragments of V^T / T of the current panel held in registers by an updating warp
 template <int H>
 struct FtFrags {
@@ -272,6 +663,7 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
   double* Ws = VT0 + 2 * VT_SZ + warp * 72;  // per-warp 8x8 scratch (ld 9)
   constexpr bool PREF = (H == 64);             // warp 4 stages the panel warp's R blocks one panel ahead
   double* Rst = VT0 + 2 * VT_SZ + NW * 72 + 16;  // 2 x 128 doubles (H = 64 only)
+  double* Pred = Rst + (H == 64 ? 2 * 128 : 0);   // 8 x 36 partial-dot scratch of the panel warp
   if (tri_n > 0) {
     for (int idx = tid; idx < n * n; idx += NT) {
       const int i = idx / n, c = idx % n;
@@ -333,7 +725,7 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
       }
     }
     __syncthreads();
-    if (warp == 0) ft_panel<H>(Ablk, ld, jp0 * FT_B, n, R, ldr, VT0 + (jp0 & 1) * VT_SZ, VT0 + (jp0 & 1) * VT_SZ + FT_B * LDV);
+    if (warp == 0) ft_panel_sel<H>(Ablk, ld, jp0 * FT_B, n, R, ldr, VT0 + (jp0 & 1) * VT_SZ, VT0 + (jp0 & 1) * VT_SZ + FT_B * LDV, Ws, Pred);
     if (PREF && warp == 4 && jp0 + 1 < npanel) ft_prefetch_R(R, ldr, n, jp0, Rst + (jp0 & 1) * 128);
     for (int jp = jp0; jp < npanel; ++jp) {
       const int j0 = jp * FT_B;
@@ -351,12 +743,12 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
         const int c0 = j0 + FT_B, cc = c0 + 2 * q4;
         const bool ok0 = (rr < n) && (cc < n), ok1 = (rr < n) && (cc + 1 < n);
         double* rp = R + (size_t)rr * ldr + cc;
-        const double* rs = Rst + (jp & 1) * 128;
+        double* rs = Rst + (jp & 1) * 128;
         const double r0 = PREF ? rs[g * FT_B + 2 * q4] : (ok0 ? rp[0] : 0.0);
         const double r1 = PREF ? rs[g * FT_B + 2 * q4 + 1] : (ok1 ? rp[1] : 0.0);
         ft_update_slab<H>(Ablk, ld, c0, f, Ws, rp, ok0, ok1, r0, r1);
         __syncwarp();
-        ft_panel<H>(Ablk, ld, c0, n, R, ldr, Vtn, Vtn + FT_B * LDV, PREF ? rs + 64 : nullptr);
+        ft_panel_sel<H>(Ablk, ld, c0, n, R, ldr, Vtn, Vtn + FT_B * LDV, Ws, Pred, PREF ? rs + 64 : nullptr);
       } else {
         // slabs 1 .. nslab-1 over the updating warps.  With H = 64 (one CTA per SM) warp 4, which shares the SM
         // sub-partition and its FP64 pipe with the panel warp, sits out: the step is bound by the panel's dependent

@@ -177,7 +177,7 @@ def test_cuda_multirank_equals_single_rank_bitwise():
 
 def test_hub_lane_and_engine_knobs_do_not_change_results():
     """the hub lane (high-degree nodes on their own stream), the triangle-aware TSQR merge, the DMMA Kronecker carry and the
-    outlier split are scheduling / kernel-variant choices: beliefs, pair beliefs and free energies agree to 1e-11 with all of
+    outlier split, and lane mode (every node dealt to one of G lanes, each lane a stream) are scheduling / kernel-variant choices: beliefs, pair beliefs and free energies agree to 1e-11 with all of
     them off, on a graph with a degree-7 hub among degree-1..3 nodes (loopy, truncation active)."""
     T, d = 6, 8
     und = [(0, k) for k in range(1, 8)] + [(1, 2), (3, 4), (5, 6), (7, 8), (8, 9), (9, 1), (2, 10), (10, 11)]
@@ -185,7 +185,8 @@ def test_hub_lane_and_engine_knobs_do_not_change_results():
     fac = M.HomogeneousGlauberFactor(0.4, 0.1, 1.0)
     phi = [[np.array([0.3, 0.7]) if t == 0 else np.ones(2) for t in range(T + 1)] for _ in range(N)]
     res = []
-    for knobs in (dict(hub_lane=0, tri_merge=0, kron_mma=0, outlier_split=0), dict(hub_lane=2, hub_frac=0.9, tri_merge=1, kron_mma=1, outlier_split=1.5)):
+    for knobs in (dict(hub_lane=0, tri_merge=0, kron_mma=0, outlier_split=0), dict(hub_lane=2, hub_frac=0.9, tri_merge=1, kron_mma=1, outlier_split=1.5),
+                  dict(lanes=103)):
         g = M.IndexedBiDiGraph(N, und)
         bp = M.mpbp(g, [[fac] * (T + 1)] * N, [2] * N, T, phi=phi, dmax=d)
         for k, v in knobs.items():
@@ -194,8 +195,9 @@ def test_hub_lane_and_engine_knobs_do_not_change_results():
         pb, lz = M.pair_beliefs(bp)
         res.append((np.concatenate([b.ravel() for b in M.beliefs(bp)]), M.api.free_energy_contributions(bp),
                     np.concatenate([np.array(p).ravel() for p in pb]), np.asarray(lz)))
-    for a, b in zip(*res):
-        assert np.max(np.abs(a - b)) < 1e-11
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert np.max(np.abs(a - b)) < 1e-11
 
 
 def test_infinite_bipartite_graph_vs_oracle_and_known_answer():
