@@ -320,6 +320,27 @@ __device__ __forceinline__ void ft_panel_l(const double* Ablk, const int ld, con
   }
 }
 
+// Branch-free reciprocal square root / reciprocal of a NORMAL double (the caller excludes zero, subnormal and non-finite
+// arguments): the hardware seed (20 mantissa bits) followed by the same Newton steps libdevice uses (one cubic step for
+// rsqrt, two quadratic steps for rcp; result within 1-2 ulp), without libdevice's special-case branches -- on the serial
+// panel chain the reconvergence bookkeeping of those branches costs ~60 cycles per column step.
+__device__ __forceinline__ double ft_rsqrt_fast(const double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y * y, 1.0);
+  const double t = fma(e, 0.375, 0.5);
+  return fma(t, y * e, y);
+}
+__device__ __forceinline__ double ft_rcp_fast(const double u) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+  double e = fma(-u, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  e = fma(-u, y, 1.0);
+  return fma(y, e, y);
+}
+
 // ft_panel_l with the cross-lane reduction of the eight dots done through shared memory: every lane stores its eight
 // partial dots (column-major 8 x 36 scratch, conflict-free), lane (c, qt) = (lane >> 2, lane & 3) adds the eight partials
 // i*4+qt of column c, two shuffle levels finish the sum -- 36 instead of 61 instructions per column step on the
@@ -386,15 +407,21 @@ __device__ __forceinline__ void ft_panel_m(const double* Ablk, const int ld, con
       }
     }
     const double alpha = rk[k], sig2 = red[k];
-    double tau = 0.0, sc = 0.0, beta = alpha;
-    if (sig2 > 0.0) {
-      const double n2 = alpha * alpha + sig2;
-      const double rs = rsqrt(n2);
-      const double nrm = n2 * rs;
-      beta = alpha >= 0.0 ? -nrm : nrm;
-      const double u = alpha - beta;
-      tau = alpha >= 0.0 ? u * rs : -u * rs;
-      sc = 1.0 / u;
+    double tau, sc, beta;
+    {
+      // branch-free: a column whose A part is exactly zero (or whose [alpha; a] norm^2 is below 1e-280) gets tau = 0
+      const double n2 = fma(alpha, alpha, sig2);
+      const bool ok = (sig2 > 0.0) && (n2 > 1e-280);  // (inf / NaN flow through and are flagged downstream)
+      const double n2s = ok ? n2 : 1.0;
+      const double rs = ft_rsqrt_fast(n2s);
+      const double nrm = n2s * rs;
+      const double bt = alpha >= 0.0 ? -nrm : nrm;
+      const double u = alpha - bt;  // |u| = |alpha| + nrm >= nrm > 0
+      const double tt = alpha >= 0.0 ? u * rs : -u * rs;
+      const double rc = ft_rcp_fast(u);
+      tau = ok ? tt : 0.0;
+      sc = ok ? rc : 0.0;
+      beta = ok ? bt : alpha;
     }
     double v[RPL];
 #pragma unroll
