@@ -118,10 +118,11 @@ struct mpbp_state {
                              // OFF by default: measured slower (N=256 bench 22.8 s vs 19.0 s per step) -- a hub kernel can only start
                              // when a bulk CTA retires, and the bulk QR CTAs run for 6-30 ms each, so the ~4500 sequential hub
                              // launches of a step queue behind them; kept as an option for graphs whose bulk CTAs are short.
-  double hub_frac = 0.3;
+  double hub_frac = 0.3;     // share of the chunk's cost the hub lane may take
   double lanes = 0;          // >= 2: lane mode, the nodes of a chunk are dealt (cost-balanced) into that many lanes, each running
                              // the whole cavity DAG of its nodes on its own stream with no barrier across lanes (1xx: also for
-                             // tiny chunks, tests)     // share of the chunk's cost the hub lane may take
+                             // tiny chunks, tests).  OFF by default: measured slower (53.7 / 52.5 edge-updates/s with 4 / 8
+                             // lanes vs 55.1, N=256 bench) -- the smaller per-stream launches lose more in their tails
   cudaStream_t hub_st = nullptr;
   cudaEvent_t ev_hub_fork = nullptr, ev_hub_join = nullptr;
   double svd_mode = 2;       // truncating SVD of large matrices: 2 (default) un-squared block iteration, blocks orthonormalised by

@@ -726,7 +726,8 @@ __device__ void qr_ft_cta(const double* __restrict__ A, const int m, const int n
           mbar_expect_tx(&ft_mbar, (uint32_t)(vrows * n * 8));
         }
         __syncwarp();
-        for (int i = lane; i < vrows; i += 32) bulk_g2s(Ablk + (size_t)i * ld, A + (size_t)(row0 + i) * lda, (uint32_t)(n * 8), &ft_mbar);
+        const uint64_t pol = l2_policy_evict_first();
+        for (int i = lane; i < vrows; i += 32) bulk_g2s_hint(Ablk + (size_t)i * ld, A + (size_t)(row0 + i) * lda, (uint32_t)(n * 8), &ft_mbar, pol);
       }
       const int npad = n8 - n;
       for (int idx = tid; idx < vrows * npad; idx += NT) Ablk[(size_t)(idx / npad) * ld + n + idx % npad] = 0.0;
