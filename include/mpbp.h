@@ -52,6 +52,16 @@ int mpbp_create_infinite(int k, int T, int q, int dmax, int device, mpbp_handle*
  * infinite graph is (f[0]*kB + f[1]*kA)/(kA+kB) (src/infinite_graph.jl:120-122, host side). */
 int mpbp_create_infinite_bipartite(int kA, int kB, int T, int qA, int qB, int dmax, int device, mpbp_handle* out);
 
+/* periodic_mpbp(g, w, q, T) (src/mpbp.jl:399-409): same arguments as mpbp_create; the messages are PeriodicMPEM2s
+ * (src/mpems.jl:96-155: the matrix product is closed by a trace, the factor of the last time maps (x^T_neigh, x^T_i) to x^0_i),
+ * starting from flat_periodic_mpem2 with d = 1.  mpbp_iterate runs onebpiter! on ring tensor trains (recursive factors only,
+ * degree <= 10, dmax <= 16; csrc/periodic.cuh); mpbp_beliefs / mpbp_free_energy / mpbp_pair_beliefs / get / set_message work as on
+ * an open handle (bonds[0] == bonds[T+1] is the closing bond); damping is the ring sum + compress! + normalize! of set_msg!.
+ * Two-time and alternate marginals and the forward sampler are not defined on this path (loud errors).  periodic_mpbp_infinite_graph = mpbp_create_infinite followed by
+ * mpbp_set_option(h, "periodic", 1) before the first iteration. */
+int mpbp_create_periodic(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* colptr, const int64_t* dst,
+                         const int64_t* rev, int dmax, int device, mpbp_handle* out);
+
 int mpbp_destroy(mpbp_handle h);
 
 /* ---- factors: the host-tabulated values of a RecursiveBPFactor (src/recursive_bp_factor.jl:6-61) ----
@@ -148,7 +158,8 @@ int mpbp_counters(mpbp_handle h, double* out8, int reset);
  * "nstreams" (1..4) concurrent streams per cavity round, "qr_fill" CTAs below which tall QRs are TSQR-split,
  * "level_balance" (default 1) stagger the cavity levels of independent nodes so that every round carries similar
  * work, "profile" (0/1) per-kernel-family CUDA-event timing, "twovar" (maxdist, 0 = off) also compute the two-time
- * marginals read by mpbp_twovar_marginals. */
+ * marginals read by mpbp_twovar_marginals, "periodic" (0/1, before the first iteration) periodic-in-time messages on this
+ * handle (see mpbp_create_periodic). */
 int mpbp_set_option(mpbp_handle h, const char* name, double value);
 /* device ms per kernel family since the last reset (option "profile" = 1): [0] sweep-1 QR, [1] kron_carry,
  * [2] kron_proj, [3] gemm_m2t, [4] qr_small, [5] jacobi_project, [6] finalize, [7] belief */

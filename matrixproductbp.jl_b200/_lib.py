@@ -17,6 +17,7 @@ SIGNATURES = {
     "mpbp_last_error": (C.c_char_p, []),
     "mpbp_version": (C.c_int, []),
     "mpbp_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mpbp_create_periodic": (C.c_int, [C.c_int64, C.c_int64, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mpbp_create_infinite": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mpbp_create_infinite_bipartite": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mpbp_destroy": (C.c_int, [C.c_void_p]),

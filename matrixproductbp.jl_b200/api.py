@@ -23,7 +23,7 @@ __all__ = [
     "BPFactor", "RecursiveBPFactor", "HomogeneousGlauberFactor", "PMJGlauberFactor", "IntegerGlauberFactor",
     "GenericGlauberFactor", "SISFactor", "SIS_heterogeneousFactor", "SIS_heterogeneous", "SIRSFactor", "DampedFactor", "TruncBond", "TruncBondMax", "TruncThresh",
     "TruncBondThresh", "GenericFactor", "IndexedBiDiGraph", "InfiniteRegularGraph", "InfiniteBipartiteRegularGraph", "mpbp_infinite_bipartite_graph", "Ising", "Glauber", "SIS", "SIRS", "MPBP", "CB_BP",
-    "mpbp", "mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_correlations", "pair_beliefs", "bethe_free_energy", "means",
+    "mpbp", "mpbp_infinite_graph", "periodic_mpbp", "periodic_mpbp_infinite_graph", "iterate_", "beliefs", "beliefs_tu", "autocorrelations", "autocovariances", "alternate_marginals", "alternate_correlations", "pair_correlations", "pair_beliefs", "bethe_free_energy", "means",
     "reset_messages_", "glauber_factors", "MPBPError", "onesample", "sample_prior", "draw_node_observations_",
 ]
 
@@ -207,15 +207,16 @@ class MPBP:
     and are mirrored to the device; mu, b, f live on the device and are read through beliefs / pair_beliefs /
     bethe_free_energy / get_message."""
 
-    def __init__(self, g, w, q, T, phi=None, psi=None, dmax=None, device=0):
+    def __init__(self, g, w, q, T, phi=None, psi=None, dmax=None, device=0, periodic=False):
         L = _lib.lib()
         self.g, self.w, self.T = g, w, int(T)
+        self.periodic = bool(periodic)  # periodic_mpbp, src/mpbp.jl:399-409: PeriodicMPEM2 messages (ring tensor trains)
         self.q = np.ascontiguousarray(np.asarray(q, dtype=np.int32))
         self.N = g.N
         self.bipartite = isinstance(g, InfiniteBipartiteRegularGraph)
         self.infinite = isinstance(g, InfiniteRegularGraph) or self.bipartite
         assert len(w) == self.N and all(len(wi) == T + 1 for wi in w), "w must hold T+1 factors per node"
-        self.dmax = int(dmax) if dmax is not None else 16
+        self.dmax = int(dmax) if dmax is not None else (8 if self.periodic else 16)
         self._h = C.c_void_p()
         # _emap: reference edge index -> engine edge index (identity except for the bipartite infinite graph, whose
         # reference slot e = "message into node e" is the engine's edge 1 - e = (1-e -> e))
@@ -229,9 +230,12 @@ class MPBP:
             self._src = np.zeros(1, dtype=np.int64)
             self._dst = np.zeros(1, dtype=np.int64)
         else:
-            _lib.check(L.mpbp_create(self.N, g.ne, self.T, _p(self.q, _lib.c_i32p), _p(g.colptr, _lib.c_i64p), _p(g.dst, _lib.c_i64p),
-                                     _p(g.rev, _lib.c_i64p), self.dmax, device, C.byref(self._h)))
+            create = L.mpbp_create_periodic if self.periodic else L.mpbp_create
+            _lib.check(create(self.N, g.ne, self.T, _p(self.q, _lib.c_i32p), _p(g.colptr, _lib.c_i64p), _p(g.dst, _lib.c_i64p),
+                              _p(g.rev, _lib.c_i64p), self.dmax, device, C.byref(self._h)))
             self._src, self._dst = g.src, g.dst
+        if self.periodic and self.infinite:
+            _lib.check(L.mpbp_set_option(self._h, b"periodic", 1.0))
         self.E2 = len(self._src)
         if not self.bipartite:
             self._emap = list(range(self.E2))
@@ -406,6 +410,17 @@ def mpbp(*args, **kw):
         raise TypeError(f"no mpbp method for {type(m)}")
     g, w, q, T = args
     return MPBP(g, w, q, T, **kw)
+
+
+def periodic_mpbp(*args, **kw):
+    """periodic_mpbp(g, w, q, T; phi, psi, dmax) or periodic_mpbp(model; dmax) -- src/mpbp.jl:399-409: the messages are
+    periodic-in-time MPEMs (the factor at the last time maps (x_neigh^T, x_i^T) to x_i^0)."""
+    return mpbp(*args, periodic=True, **kw)
+
+
+def periodic_mpbp_infinite_graph(k, w, q, phi=None, psi=None, **kw):
+    """periodic_mpbp_infinite_graph(k, w, q, phi) -- test/periodic.jl:78-93"""
+    return mpbp_infinite_graph(k, w, q, phi=phi, psi=psi, periodic=True, **kw)
 
 
 def mpbp_infinite_bipartite_graph(k, w, q, phi=None, psi=None, **kw):

@@ -11,6 +11,7 @@
 
 #include "../../include/mpbp.h"
 #include "kernels.cuh"
+#include "periodic_plan.h"
 
 using namespace mpbp;
 
@@ -79,6 +80,7 @@ struct mpbp_state {
   int inf_k = 0;  // > 0: infinite (iid) graph: every node stands for a whole class and sees inf_deg[i] copies of its single in-edge
                   // (InfiniteRegularGraph(k): N = 1, self edge; InfiniteBipartiteRegularGraph((kA,kB)): N = 2, one edge pair)
   std::vector<int> inf_deg;
+  bool periodic = false;  // periodic-in-time MPBP (periodic_mpbp, src/mpbp.jl:399-409): ring messages, csrc/periodic.cuh
   std::vector<int64_t> lz_off;  // offset of node i's log z_{i->j} entries in d_logzij
   int node_deg(int64_t i) const { return inf_k > 0 ? inf_deg[i] : (int)(colptr[i + 1] - colptr[i]); }
   int64_t out_edge(int64_t i, int k) const { return inf_k > 0 ? colptr[i] : colptr[i] + k; }
@@ -1355,8 +1357,121 @@ int run_nodes_chunk(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, in
   return 0;
 }
 
+// ---- periodic-in-time MPBP: one CTA per node runs the whole ring update (csrc/periodic.cuh) ----
+__global__ void __launch_bounds__(NT) k_periodic_nodes(const mpbp_per::PerNode* nodes) {
+  mpbp_per::per_node_update(nodes[blockIdx.x]);
+}
+
+__global__ void __launch_bounds__(NT) k_periodic_pairs(const mpbp_per::PerPair* jobs) {
+  mpbp_per::per_pair_belief(jobs[blockIdx.x]);
+}
+
+int run_nodes_periodic(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, const Trunc& tr) {
+  using namespace mpbp_per;
+  if (ensure_arena(h)) return 1;
+  const int L = h->L;
+  auto as_ptt = [](const TTRef& r) { return PTT{r.data, r.bonds, r.ls, r.stride, r.P}; };
+  auto take = [&](size_t bytes) -> void* { return h->arena.take(bytes); };
+  std::vector<PerNode> batch;
+  auto flush = [&]() -> int {
+    if (batch.empty()) return 0;
+    PerNode* d_nodes = nullptr;
+    CUDA_OK(cudaMalloc((void**)&d_nodes, sizeof(PerNode) * batch.size()));
+    cudaError_t e = cudaMemcpyAsync(d_nodes, batch.data(), sizeof(PerNode) * batch.size(), cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) {
+      k_periodic_nodes<<<(unsigned)batch.size(), NT, 0, h->st>>>(d_nodes);
+      h->n_launch++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    cudaFree(d_nodes);
+    if (e != cudaSuccess) return fail("CUDA error %s in the periodic node update", cudaGetErrorString(e));
+    for (const PerNode& nd : batch) h->n_edge_updates += nd.z;
+    batch.clear();
+    h->arena.used = 0;
+    return 0;
+  };
+  h->arena.used = 0;
+  for (size_t k = 0; k < nodes.size(); ++k) {
+    const int64_t i = nodes[k];
+    const int ci = h->class_of_node[i];
+    if (ci < 0 || ci >= (int)h->classes.size()) return fail("node %lld has no factor class", (long long)i);
+    const NodeClass& c = h->classes[ci];
+    if (c.generic) return fail("the periodic path needs RecursiveBPFactors (node %lld has a generic BPFactor)", (long long)i);
+    const int z = c.z, q = c.q;
+    if (z > PER_MAXZ) return fail("the periodic path supports degrees up to %d (node %lld has %d)", PER_MAXZ, (long long)i, z);
+    if (h->node_deg(i) != z || q != h->q[i]) return fail("node %lld does not match its class (degree / states)", (long long)i);
+    PerClassView v;
+    v.z = z;
+    v.q = q;
+    v.qn = c.qn.data();
+    v.ny = c.ny.data();
+    v.pxy = c.d_pxy;
+    v.pxy_off = c.pxy_off.data();
+    v.pxy_ts = c.pxy_ts;
+    v.pyy = [&c](int d1, int d2, const double** p, size_t* ts) {
+      auto it = c.pyy.find({d1, d2});
+      if (it == c.pyy.end()) return false;
+      *p = c.d_pyy + it->second.first;
+      *ts = it->second.second;
+      return true;
+    };
+    v.w = c.d_w;
+    v.w_off = c.w_off.data();
+    v.w_ts = c.w_ts;
+    v.wd = c.d_wd;
+    v.wd_ts = c.wd_ts;
+    v.minit = c.d_minit;
+    v.minit_ts = c.minit_ts;
+    for (int attempt = 0;; ++attempt) {
+      PerNode nd;
+      memset((void*)&nd, 0, sizeof nd);
+      const size_t mark = h->arena.used;
+      bool ok = per_plan_node(v, L, h->dmax, take, nd);
+      // the infinite graph keeps only the last recomputed message (src/infinite_graph.jl): the others go to scratch slots
+      for (int j = 0; j < z && ok; ++j) {
+        const int64_t eout = h->out_edge(i, j);
+        if (h->q[h->dst[eout]] != c.qn[j]) return fail("node %lld neighbour %d: class qn mismatch", (long long)i, j);
+        nd.msg_in[j] = as_ptt(msg_ref(h, h->msg[rb], h->rev[eout], c.qn[j] * q));
+        nd.psi[j] = h->d_psi + h->psi_off[eout];
+        if (h->inf_k > 0 && j < z - 1 && h->damp <= 0.0) {  // (damped: every recomputation is damped into the evolving bp.mu[1])
+          PTT sc;
+          sc.stride = h->sstride;
+          sc.X = q * c.qn[j];
+          sc.data = (double*)take(sizeof(double) * h->slot);
+          sc.bonds = (int*)take(sizeof(int) * (L + 1));
+          sc.ls = (double*)take(sizeof(double));
+          ok = ok && sc.data && sc.bonds && sc.ls;
+          nd.msg_out[j] = sc;
+        } else {
+          nd.msg_out[j] = as_ptt(msg_ref(h, h->msg[wb], eout, q * c.qn[j]));
+        }
+      }
+      if (!ok) {
+        // arena full: run what is planned, then retry this node on an empty arena (a node that does not fit alone is an error)
+        h->arena.used = mark;
+        if (batch.empty() || attempt > 0) return fail("arena too small for one periodic node update (dmax=%d, degree %d)", h->dmax, z);
+        if (flush()) return 1;
+        continue;
+      }
+      nd.tr = PTrunc{tr.kind, tr.d, tr.eps};
+      nd.damp = h->damp;
+      nd.phi = h->d_phi + h->phi_off[i];
+      nd.marg = h->d_marg + h->marg_off[i];
+      nd.logzi = h->d_logzi + i;
+      nd.logzij = h->d_logzij + h->lz_off[i];
+      nd.f = h->d_f + i;
+      nd.err = h->d_err;
+      batch.push_back(nd);
+      break;
+    }
+  }
+  return flush();
+}
+
 // update a set of pairwise independent-or-double-buffered nodes, chunked by arena capacity
 int run_nodes(mpbp_state* h, const std::vector<int64_t>& nodes, int rb, int wb, const Trunc& tr) {
+  if (h->periodic) return run_nodes_periodic(h, nodes, rb, wb, tr);
   if (ensure_arena(h)) return 1;
   // fraction of the arena given to persistent per-node storage; the rest is op scratch
   const size_t budget = (size_t)(h->arena.cap * 0.45);
@@ -1431,6 +1546,14 @@ int mpbp_create(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* c
   h->class_of_node.assign(N, -1);
   if (common_init(h)) { delete h; return 1; }
   *out = h;
+  return 0;
+}
+
+int mpbp_create_periodic(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* colptr, const int64_t* dst,
+                         const int64_t* rev, int dmax, int device, mpbp_handle* out) {
+  if (dmax > 16) return fail("dmax=%d exceeds the bond capacity 16 of the periodic path (its Kronecker workspace holds bond dmax^2)", dmax);
+  if (mpbp_create(N, E2, T, q, colptr, dst, rev, dmax, device, out)) return 1;
+  (*out)->periodic = true;  // flat_periodic_mpem2 with d = 1 is the flat open message: nothing else to initialise
   return 0;
 }
 
@@ -1678,7 +1801,9 @@ int mpbp_set_message(mpbp_handle h, int64_t e, const int32_t* bonds, const doubl
   if (!h || e < 0 || e >= h->E2 || !bonds || !data) return fail("bad argument");
   CUDA_OK(cudaSetDevice(h->device));
   const int L = h->L;
-  if (bonds[0] != 1 || bonds[L] != 1) return fail("first/last bond must be 1 (src/mpems.jl:41)");
+  if (h->periodic) {
+    if (bonds[0] != bonds[L]) return fail("periodic message: the first and the last bond must coincide (src/mpems.jl:100-101)");
+  } else if (bonds[0] != 1 || bonds[L] != 1) return fail("first/last bond must be 1 (src/mpems.jl:41)");
   for (int t = 0; t <= L; ++t)
     if (bonds[t] < 1 || bonds[t] > h->dmax) return fail("bond %d exceeds dmax=%d", bonds[t], h->dmax);
   MsgStore& m = h->msg[h->cur];
@@ -1815,8 +1940,73 @@ int mpbp_free_energy(mpbp_handle h, double* f) {
   return 0;
 }
 
+// pair_beliefs(bp) on periodic messages: one CTA per directed edge (csrc/periodic.cuh: per_pair_belief)
+static int pair_beliefs_periodic(mpbp_state* h, double* out, double* logz) {
+  using namespace mpbp_per;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (ensure_arena(h)) return 1;
+  const int L = h->L, D2 = h->dmax * h->dmax;
+  const MsgStore& m = h->msg[h->cur];
+  double* d_out;
+  double* d_lz;
+  CUDA_OK(cudaMalloc((void**)&d_out, sizeof(double) * std::max<int64_t>(h->psi_off[h->E2], 1)));
+  CUDA_OK(cudaMalloc((void**)&d_lz, sizeof(double) * std::max<int64_t>(h->E2, 1)));
+  struct Guard { double *a, *b; ~Guard() { cudaFree(a); cudaFree(b); } } guard{d_out, d_lz};
+  const size_t per = 8 * ((size_t)(2 * L + 3) * D2 * D2 + PER_MAXW + 8) + 1024;
+  int64_t e0 = 0;
+  while (e0 < h->E2) {
+    h->arena.used = 0;
+    const int64_t maxn = std::max<int64_t>(1, (int64_t)((h->arena.cap / 2) / (per + sizeof(PerPair))));
+    const int64_t e1 = std::min(h->E2, e0 + maxn);
+    std::vector<PerPair> jobs;
+    for (int64_t e = e0; e < e1; ++e) {
+      PerPair jb;
+      memset((void*)&jb, 0, sizeof jb);
+      const int qs = h->q[h->src[e]], qd = h->q[h->dst[e]];
+      const TTRef a = msg_ref(h, m, e, qs * qd), b = msg_ref(h, m, h->rev[e], qs * qd);
+      jb.a = PTT{a.data, a.bonds, a.ls, a.stride, a.P};
+      jb.b = PTT{b.data, b.bonds, b.ls, b.stride, b.P};
+      jb.psi = h->d_psi + h->psi_off[e];
+      jb.qi = qs;
+      jb.qj = qd;
+      jb.L = L;
+      jb.out = d_out + h->psi_off[e];
+      jb.logz = d_lz + e;
+      jb.wcap = D2;
+      jb.tm = (double*)h->arena.take(8 * (size_t)(2 * L + 3) * D2 * D2);
+      jb.red = (double*)h->arena.take(8 * (PER_MAXW + 8));
+      jb.err = h->d_err;
+      if (!jb.tm || !jb.red) return fail("arena exhausted (periodic pair beliefs)");
+      jobs.push_back(jb);
+    }
+    PerPair* d_jobs;
+    if (upload_jobs(h, jobs, &d_jobs)) return 1;
+    k_periodic_pairs<<<(unsigned)jobs.size(), NT, 0, h->st>>>(d_jobs);
+    h->n_launch++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->st));
+    e0 = e1;
+  }
+  if (check_err(h)) return 1;
+  CUDA_OK(cudaMemcpy(out, d_out, sizeof(double) * h->psi_off[h->E2], cudaMemcpyDeviceToHost));
+  std::vector<double> lz(std::max<int64_t>(h->E2, 1));
+  CUDA_OK(cudaMemcpy(lz.data(), d_lz, sizeof(double) * h->E2, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < h->N; ++i) logz[i] = 0.0;
+  if (h->inf_k > 0) {
+    for (int64_t e = 0; e < h->E2; ++e) logz[h->dst[e]] = (1.0 / (h->inf_deg[h->dst[e]] - 1) - 0.5) * lz[e];
+  } else {
+    for (int64_t e = 0; e < h->E2; ++e) {
+      const int64_t j = h->src[e];
+      const double dj = (double)(h->colptr[j + 1] - h->colptr[j]);
+      logz[j] += (1.0 / dj - 0.5) * lz[e];
+    }
+  }
+  return 0;
+}
+
 int mpbp_pair_beliefs(mpbp_handle h, double* out, double* logz) {
   if (!h || !out || !logz) return fail("null argument");
+  if (h->periodic) return pair_beliefs_periodic(h, out, logz);
   CUDA_OK(cudaSetDevice(h->device));
   if (ensure_arena(h)) return 1;
   const int L = h->L, d = h->dmax;
@@ -1876,6 +2066,7 @@ int mpbp_pair_beliefs(mpbp_handle h, double* out, double* logz) {
 
 int mpbp_alternate_marginals(mpbp_handle h, double* out) {
   if (!h || !out) return fail("null argument");
+  if (h->periodic) return fail("alternate marginals are not available on the periodic path");
   CUDA_OK(cudaSetDevice(h->device));
   if (ensure_arena(h)) return 1;
   const int L = h->L, d = h->dmax;
@@ -1923,6 +2114,7 @@ int mpbp_alternate_marginals(mpbp_handle h, double* out) {
 int mpbp_sample_prior(mpbp_handle h, uint64_t seed, int32_t* X) {
   if (!h || !X) return fail("null argument");
   if (h->inf_k > 0) return fail("sampling is defined on finite graphs (src/sampling.jl iterates the nodes of bp.g)");
+  if (h->periodic) return fail("the forward sampler needs an initial time: not defined for periodic-in-time dynamics");
   CUDA_OK(cudaSetDevice(h->device));
   std::vector<SampCls> sc(std::max<size_t>(h->classes.size(), 1));
   for (size_t ci = 0; ci < h->classes.size(); ++ci) {
@@ -2170,7 +2362,14 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
   else if (n == "svd_mode") h->svd_mode = value;
   else if (n == "hub_frac") h->hub_frac = value;
   else if (n == "lanes") h->lanes = value;
+  else if (n == "periodic") {
+    // periodic-in-time messages on any handle (periodic_mpbp_infinite_graph: mpbp_create_infinite + this option); set before
+    // the first iteration
+    if (value != 0 && h->dmax > 16) return fail("the periodic path supports dmax <= 16");
+    h->periodic = value != 0;
+  }
   else if (n == "twovar") {
+    if (h->periodic && value > 0) return fail("two-time marginals are not available on the periodic path");
     // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
     h->twovar = value > 0 ? (int)std::min<double>(value, h->L) : 0;
     if (h->twovar > 0 && !h->d_tv) {

@@ -12,7 +12,9 @@ TensorTrains.jl (PeriodicTensorTrain); their sweep order around the ring could n
 restatement below (full ring sweeps: every bond, including the one closing the ring, is visited once per sweep) is
 "parity unpinned" whenever a truncation actually binds.  With a non-binding truncation -- what test/periodic.jl uses
 (TruncBondThresh(10) on a tree) -- every valid compression is exact, and this module is pinned against brute-force
-enumeration of the periodic dynamics (tests/test_oracle_golden.py::test_periodic_*).  No device counterpart yet.
+enumeration of the periodic dynamics (tests/test_oracle_golden.py::test_periodic_*).  Device counterpart:
+matrixproductbp.jl_b200/csrc/periodic.cuh (the same full-turn sweeps), checked against this module by
+tests/test_periodic_host_emul.py (CPU emulation of the kernel source) and tests/test_gpu_periodic.py.
 """
 from __future__ import annotations
 
@@ -212,8 +214,23 @@ def mpem2(Bs, ls):
     return TT(C, ls + logc)
 
 
-def onebpiter(bp: PeriodicMPBP, i, trunc):
-    """recursive_bp_factor.jl:146-165 on periodic messages (damp = 0)"""
+def ring_sum(A: TT, B: TT, coefB: float) -> TT:
+    """A + coefB * B as a ring train: every site block-diagonal, the closing bond included (TensorTrains._compose on
+    PeriodicTensorTrains, as used by set_msg!, recursive_bp_factor.jl:172-176)"""
+    L = len(A)
+    fa, fb = np.exp(A.ls / L), np.exp(B.ls / L)
+    out = []
+    for t in range(L):
+        a, b = A[t] * fa, B[t] * fb * (coefB if t == 0 else 1.0)
+        c = np.zeros((a.shape[0] + b.shape[0], a.shape[1] + b.shape[1]) + a.shape[2:])
+        c[: a.shape[0], : a.shape[1]] = a
+        c[a.shape[0]:, a.shape[1]:] = b
+        out.append(c)
+    return TT(out, 0.0)
+
+
+def onebpiter(bp: PeriodicMPBP, i, trunc, damp=0.0):
+    """recursive_bp_factor.jl:146-165 on periodic messages; set_msg! damping :168-179"""
     g = bp.g
     ein, eout = g.in_edges[i], g.out_edges[i]
     wi, phii, di, qi = bp.w[i], bp.phi[i], len(ein), bp.q[i]
@@ -225,6 +242,10 @@ def onebpiter(bp: PeriodicMPBP, i, trunc):
         muj = compress(mpem2(Bs, ls), trunc, "left")
         T_.normalize_eachmatrix(muj)
         sumlogz += normalize(muj)
+        if damp > 0:
+            muj = ring_sum(muj, bp.mu[e], damp / (1 - damp))
+            compress(muj, trunc)
+            normalize(muj)
         bp.mu[e] = muj
     Bs, ls = f_bp_partial(full, wi, phii, di, lambda w, *a: w.prob_y_dummy(*a), 1, 1)
     bp.b[i] = marginalize(mpem2(Bs, ls))
@@ -232,12 +253,12 @@ def onebpiter(bp: PeriodicMPBP, i, trunc):
     bp.f[i] = (di / 2 - 1) * logzi - 0.5 * sumlogz
 
 
-def iterate(bp: PeriodicMPBP, maxiter=5, trunc=None, nodes=None):
+def iterate(bp: PeriodicMPBP, maxiter=5, trunc=None, nodes=None, damp=0.0):
     trunc = trunc if trunc is not None else TruncThresh(1e-6)
     nodes = list(range(bp.g.N)) if nodes is None else list(nodes)
     for _ in range(maxiter):
         for i in nodes:
-            onebpiter(bp, i, trunc)
+            onebpiter(bp, i, trunc, damp)
     return maxiter
 
 
@@ -247,6 +268,29 @@ def beliefs(bp):
 
 def bethe_free_energy(bp):
     return float(np.sum(bp.f))
+
+
+def pair_belief_tt(Aij, Aji, psi):
+    """bp_core.jl:95-101 on ring trains: the bond-d^2 product of the two messages of an edge, reweighted by psi"""
+    tens = []
+    for a, b, p in zip(Aij, Aji, psi):
+        t = np.einsum("acij,bdji,ij->abcdij", a, b, np.asarray(p))
+        s = t.shape
+        tens.append(t.reshape(s[0] * s[1], s[2] * s[3], s[4], s[5], order="F"))
+    return TT(tens, Aij.ls + Aji.ls)
+
+
+def pair_beliefs(bp):
+    """mpbp.jl:202-235 with the ring marginals / normalisation: (b[e][t][x_src, x_dst], logz[i])"""
+    g = bp.g
+    logz = np.zeros(g.N)
+    b = [None] * g.ne
+    for e in range(g.ne):
+        j = g.dst[e]
+        Pt = pair_belief_tt(bp.mu[e], bp.mu[g.rev[e]], bp.psi[e])
+        b[e] = marginals(Pt)
+        logz[j] += (1 / g.degree(j) - 0.5) * lognormalization(Pt)
+    return b, logz
 
 
 # ---------------------------------------------------------------------------------------------
