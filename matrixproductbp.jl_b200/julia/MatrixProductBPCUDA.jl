@@ -34,9 +34,17 @@ function CuMPBP(bp::MPBP{G,F}; dmax::Int=16, device::Int=0) where {G<:IndexedBiD
     dst = Int64.(rowvals(g.A) .- 1)
     rev = Int64.(nonzeros(g.X) .- 1)                   # index of the reverse edge, src/mpbp.jl:40-58
     h = Ref{Ptr{Cvoid}}(C_NULL)
+    # periodic_mpbp states (src/mpbp.jl:399-409) carry PeriodicMPEM2 messages: the ring engine of csrc/periodic.cuh
+    periodic = eltype(bp.μ) <: PeriodicMPEM2
+    if periodic
+        check(ccall((:mpbp_create_periodic, LIB), Cint,
+            (Int64, Int64, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Cint, Cint, Ref{Ptr{Cvoid}}),
+            N, ne(g), T, q, colptr, dst, rev, min(dmax, 16), device, h))
+    else
     check(ccall((:mpbp_create, LIB), Cint,
         (Int64, Int64, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Cint, Cint, Ref{Ptr{Cvoid}}),
         N, ne(g), T, q, colptr, dst, rev, dmax, device, h))
+    end
     cu = CuMPBP{G,F,eltype(bp.w)}(g, bp.w, bp.ϕ, bp.ψ, q, T, dmax, h[], true)
     finalizer(x -> ccall((:mpbp_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), cu)
     sync_reweightings!(cu)
@@ -53,6 +61,8 @@ function CuMPBP(bp::MPBP{G,F}; dmax::Int=16, device::Int=0) where {G<:Union{Infi
     h = Ref{Ptr{Cvoid}}(C_NULL)
     if g isa InfiniteRegularGraph
         check(ccall((:mpbp_create_infinite, LIB), Cint, (Cint, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}), g.k, T, q[1], dmax, device, h))
+        # periodic_mpbp_infinite_graph (test/periodic.jl:78-93): the same handle with ring messages
+        eltype(bp.μ) <: PeriodicMPEM2 && check(ccall((:mpbp_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cdouble), h[], "periodic", 1.0))
         ψ = bp.ψ
     else
         check(ccall((:mpbp_create_infinite_bipartite, LIB), Cint, (Cint, Cint, Cint, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
