@@ -413,6 +413,7 @@ def run_gpu(args, rank, world, local_rank):
     if prof_range:
         torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
+    own_s = drv.compute_s if drv is not None else ms / 1e3  # node-update time of the TIMED steps only (the profiled step follows)
     clocks = sampler.stop() if rank == 0 else None
     ctr_timed = bp.counters(reset=True)
     launches = int(ctr_timed["launches"])
@@ -440,7 +441,7 @@ def run_gpu(args, rank, world, local_rank):
     tt = torch.tensor([ms], dtype=torch.float64, device=dev)
     ee = torch.tensor([float(edges_local)], dtype=torch.float64, device=dev)
     # per-rank time of the node updates alone (the step itself ends with the exchange, which equalises the ranks)
-    own_ms = 1e3 * (drv.compute_s if drv is not None else ms / 1e3) / args.steps
+    own_ms = 1e3 * own_s / args.steps
     per_rank = [own_ms]
     if world_eff > 1:
         gath = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]

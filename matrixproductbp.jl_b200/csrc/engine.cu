@@ -1461,6 +1461,11 @@ int run_nodes_periodic(mpbp_state* h, const std::vector<int64_t>& nodes, int rb,
       nd.logzi = h->d_logzi + i;
       nd.logzij = h->d_logzij + h->lz_off[i];
       nd.f = h->d_f + i;
+      if (h->twovar > 0 && h->d_tv) {
+        nd.tv = h->d_tv + (size_t)i * L * L * h->qmax * h->qmax;
+        nd.tv_maxdist = h->twovar;
+        nd.tv_q2cap = h->qmax * h->qmax;
+      }
       nd.err = h->d_err;
       batch.push_back(nd);
       break;
@@ -2369,7 +2374,6 @@ int mpbp_set_option(mpbp_handle h, const char* name, double value) {
     h->periodic = value != 0;
   }
   else if (n == "twovar") {
-    if (h->periodic && value > 0) return fail("two-time marginals are not available on the periodic path");
     // two-time marginals of every belief computed from now on, for time distances up to `value` (0 = off)
     h->twovar = value > 0 ? (int)std::min<double>(value, h->L) : 0;
     if (h->twovar > 0 && !h->d_tv) {

@@ -103,7 +103,7 @@ struct PerWS {
   int* perm;      // wcap
   double* red;    // PER_MAXW + 8: block reductions, scalar broadcast
   int* ib;        // 8 ints: flags / broadcast
-  double* tm;     // transfer matrices of the belief: (2L+3) * (dmax*q)^2
+  double* tm;     // transfer matrices of the belief: (3L + 3 + 2q) * wcap^2
 };
 
 struct PerNode {
@@ -135,6 +135,9 @@ struct PerNode {
   int wd_ts, nyz;
   const double* phi;  // [t][x]
   double *marg, *logzi, *logzij, *f;
+  double* tv;        // two-time marginals b_i(x^t, x^u) (twovar_marginals(bp.b[i]), src/mpbp.jl:239), nullptr = off:
+  int tv_maxdist;    //   [t][u][x_t + q*x_u], (t,u) stride tv_q2cap, zero unless t < u <= t + tv_maxdist
+  int tv_q2cap;
   int* err;  // the handle's error word (OR of the PER_ERR_* bits of every node)
   PerWS ws;
 };
@@ -726,7 +729,71 @@ PER_FN double per_belief(const PerNode& nd, PerWS& ws, int* err) {
       nd.marg[(size_t)t * q + x] = s / tot;
     }
     if (t == L - 1) logz = log(tot) + lacc;  // trace(Pre_{L-1} T_{L-1}) with Pre scaled by exp(-lacc)
+    if (nd.tv) {  // keep every suffix for the two-time marginals below
+      double* Sa = ws.tm + (3 + 2 * (size_t)L + t) * msz;
+      PER_FOR(i, k * d0) Sa[i] = cur[i];
+    }
     PER_SYNC();
+  }
+  if (nd.tv) {
+    // b(x_t, x_u) ~ trace(Pre_t P_{x_t} T_t ... T_{u-1} P_{x_u} Suf_u),  P_x = projector on the rows (m, x).
+    // V_x = Pre_t P_x T_t T_{t+1} ... is carried for all x_t together (common rescaling keeps their relative weights).
+    const int q2c = nd.tv_q2cap;
+    double* Sall = ws.tm + (3 + 2 * (size_t)L) * msz;
+    double* Va = ws.tm + (3 + 3 * (size_t)L) * msz;
+    double* Vb = Va + (size_t)q * msz;
+    PER_FOR(i, L * L * q2c) nd.tv[i] = 0.0;
+    PER_SYNC();
+    for (int t = 0; t < L - 1; ++t) {
+      const int mt = per_bl(Fu, t), kt = mt * q, nt = per_br(Fu, t, L) * q;
+      // V_x (d0 x nt) = Pre_t[:, (m, x)] * T_t[(m, x), :]
+      PER_FOR(idx, q * d0 * nt) {
+        const int x = idx / (d0 * nt), a = idx % d0, c = (idx / d0) % nt;
+        double acc = 0;
+        for (int mm = 0; mm < mt; ++mm) acc += Pre[t * msz + a + (size_t)d0 * (mm + mt * x)] * Tm[t * msz + (mm + mt * x) + (size_t)kt * c];
+        Va[x * msz + a + (size_t)d0 * c] = acc;
+      }
+      PER_SYNC();
+      double* Vc = Va;
+      double* Vn = Vb;
+      for (int u = t + 1; u < L && u - t <= nd.tv_maxdist; ++u) {
+        const int mu = per_bl(Fu, u), ku = mu * q, nu = per_br(Fu, u, L) * q;  // V_x is d0 x ku here
+        const double* Su = Sall + u * msz;                                     // ku x d0
+        double* o = nd.tv + ((size_t)t * L + u) * q2c;
+        PER_FOR(xx, q * q) {
+          const int xt = xx % q, xu = xx / q;
+          double acc = 0;
+          for (int mm = 0; mm < mu; ++mm)
+            for (int a = 0; a < d0; ++a) acc += Vc[xt * msz + a + (size_t)d0 * (mm + mu * xu)] * Su[(mm + mu * xu) + (size_t)ku * a];
+          o[xx] = acc;
+        }
+        PER_SYNC();
+        double tot = 0;
+        for (int xx = 0; xx < q * q; ++xx) tot += o[xx];
+        PER_SYNC();
+        if (!(tot > 0.0) && PER_TID == 0) *err |= PER_ERR_NAN;
+        PER_FOR(xx, q * q) o[xx] /= tot;
+        if (u + 1 < L && u + 1 - t <= nd.tv_maxdist) {
+          // V_x <- V_x T_u for every x, rescaled by ONE common factor
+          PER_FOR(idx, q * d0 * nu) {
+            const int x = idx / (d0 * nu), a = idx % d0, c = (idx / d0) % nu;
+            double acc = 0;
+            for (int l = 0; l < ku; ++l) acc += Vc[x * msz + a + (size_t)d0 * l] * Tm[u * msz + l + (size_t)ku * c];
+            Vn[x * msz + a + (size_t)d0 * c] = acc;
+          }
+          PER_SYNC();
+          double mx = 0.0;
+          for (int x = 0; x < q; ++x) mx = fmax(mx, per_maxabs(Vn + x * msz, d0 * nu, ws.red, err));
+          if (mx > 0.0) {
+            const double sc = 1.0 / mx;
+            PER_FOR(idx, q * d0 * nu) Vn[(idx / (d0 * nu)) * msz + idx % (d0 * nu)] *= sc;
+          }
+          PER_SYNC();
+          double* sw = Vc; Vc = Vn; Vn = sw;
+        }
+      }
+      PER_SYNC();
+    }
   }
   return logz + *Fu.ls;
 }

@@ -145,7 +145,7 @@ bool per_plan_node(const PerClassView& c, int L, int dmax, Take&& take, PerNode&
   ws.perm = (int*)take(4 * wc);
   ws.red = (double*)take(8 * (PER_MAXW + 8));
   ws.ib = (int*)take(4 * 8);
-  ws.tm = (double*)take(8 * (size_t)(2 * L + 3) * wc * wc);
+  ws.tm = (double*)take(8 * (size_t)(3 * L + 3 + 2 * q) * wc * wc);
   ok = ok && ws.K.data && ws.K.bonds && ws.K.ls && ws.G && ws.Lf && ws.Rf && ws.Tmp && ws.Mb && ws.W && ws.sig && ws.perm &&
        ws.red && ws.ib && ws.tm;
   return ok;

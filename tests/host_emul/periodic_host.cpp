@@ -17,7 +17,7 @@ extern "C" int per_host_node_update(int z, int q, const int* qn, int T, int dmax
                                     const double* minit, const double* phi, const double* psi, int trunc_kind, int trunc_d,
                                     double trunc_eps, double damp, int sstride, const int* in_bonds, const double* in_data, const double* in_ls,
                                     int* out_bonds, double* out_data, double* out_ls, double* marg, double* logzi, double* logzij,
-                                    double* f, int* err) {
+                                    double* f, double* tv, int tv_maxdist, int tv_q2cap, int* err) {
   const int L = T + 1;
   const bool td = nt > 1;
   std::vector<size_t> pxy_off(z), w_off(z);
@@ -89,6 +89,9 @@ extern "C" int per_host_node_update(int z, int q, const int* qn, int T, int dmax
   nd.logzi = logzi;
   nd.logzij = logzij;
   nd.f = f;
+  nd.tv = tv;
+  nd.tv_maxdist = tv_maxdist;
+  nd.tv_q2cap = tv_q2cap;
   *err = 0;
   nd.err = err;
   if (rc == 0) per_node_update(nd);

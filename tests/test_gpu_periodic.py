@@ -53,6 +53,7 @@ def test_periodic_glauber_tree_vs_oracle_and_exact(schedule):
     wd = [[M.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0)] * (T + 1) for i in range(N)]
     bo, bd = _pair(go, und, N, T, 2, wo, wd, phi, psi, dmax=10)
     P.iterate(bo, maxiter=8, trunc=tt.TruncBondThresh(10))
+    bd.set_option("twovar", T)  # two-time marginals of every belief, all time pairs
     iters, cb = M.iterate_(bd, maxiter=8, svd_trunc=M.TruncBondThresh(10), tol=0.0, shuffle_nodes=False, schedule=schedule)
     assert iters == 8
     L = T + 1
@@ -65,6 +66,17 @@ def test_periodic_glauber_tree_vs_oracle_and_exact(schedule):
     if schedule == "sequential":  # same sweep as the oracle: every intermediate agrees, not only the fixed point
         assert np.allclose(np.array(P.beliefs(bo)), np.array([np.array(b) for b in b_d]), atol=TOL)
         assert np.allclose(bo.f, M.api.free_energy_contributions(bd), atol=TOL)
+    # two-time marginals / autocorrelations (test/periodic.jl:43-47, 62-63) against brute force
+    btu = M.beliefs_tu(bd)
+    spin = lambda x, i: 3 - 2 * x  # potts2spin on states numbered from 1
+    r_bp = M.autocorrelations(spin, bd)
+    for i in range(N):
+        for t in range(L):
+            for u in range(t + 1, L):
+                ex = p.sum(axis=tuple(a for a in range(N * L) if a not in (i * L + t, i * L + u)))
+                assert np.allclose(btu[i][t][u], ex, atol=TOL)
+                r_ex = sum(spin(a + 1, i) * spin(b + 1, i) * ex[a, b] for a in range(2) for b in range(2))
+                assert abs(r_bp[i][t, u] - r_ex) < TOL
     # pair beliefs and their free-energy weights (test/periodic.jl:49-60)
     pb_d, lz_d = M.pair_beliefs(bd)
     pb_o, lz_o = P.pair_beliefs(bo)

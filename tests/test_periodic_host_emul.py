@@ -81,6 +81,7 @@ class HostPeriodicBP:
                 self.data[e, t * self.ss:t * self.ss + P_] = 1.0
             self.ls[e] = -self.L * np.log(P_)
         self.marg = [np.full((self.L, q[i]), 1.0 / q[i]) for i in range(g.N)]
+        self.tv = [np.zeros((self.L, self.L, qmax * qmax)) for i in range(g.N)]
         self.f = np.zeros(g.N)
 
     def update(self, i, trunc, damp=0.0):
@@ -110,15 +111,18 @@ class HostPeriodicBP:
         lzij = np.zeros(max(z, 1))
         err = C.c_int()
         ny = np.ascontiguousarray(tab["ny"], dtype=np.int32)
+        tv = np.zeros(L * L * self.tv[i].shape[2])
         rc = self.emu.per_host_node_update(z, qi, _p(qn, ip), self.T, self.dmax, _p(ny, ip), len(ws), _p(tab["pxy"], dp), len(d1),
                                            _p(d1, ip), _p(d2, ip), _p(tab["pyy"], dp), _p(tab["w"], dp), _p(tab["wd"], dp),
                                            _p(tab["minit"], dp), _p(phi, dp), _p(psi, dp), trunc.kind, trunc.d, C.c_double(trunc.eps),
                                            C.c_double(damp), self.ss, _p(ib, ip), _p(idat, dp), _p(ils, dp), _p(ob, ip), _p(odat, dp), _p(ols, dp),
-                                           _p(marg, dp), C.byref(lzi), _p(lzij, dp), C.byref(f), C.byref(err))
+                                           _p(marg, dp), C.byref(lzi), _p(lzij, dp), C.byref(f), _p(tv, dp), L, self.tv[i].shape[2],
+                                           C.byref(err))
         assert rc == 0 and err.value == 0, (rc, err.value)
         for k, e in enumerate(eout):
             self.bonds[e], self.data[e], self.ls[e] = ob[k], odat[k], ols[k]
         self.marg[i] = marg.reshape(L, qi)
+        self.tv[i] = tv.reshape(L, L, -1)
         self.f[i] = f.value
 
     def pair_beliefs(self):
@@ -201,6 +205,12 @@ def test_periodic_glauber_tree_kernel_source_vs_oracle_and_exact(emu):
             ex = p.sum(axis=tuple(a for a in range(N * L) if a not in (i * L + t, j * L + t)))
             assert np.allclose(pb_h[e][t], ex if i < j else ex.T, atol=1e-9)
     assert np.allclose(lz_o, lz_h, atol=1e-9)
+    # two-time marginals b_i(x^t, x^u) of every belief (autocorrelations of test/periodic.jl:43-47) against brute force
+    for i in range(N):
+        for t in range(L):
+            for u in range(t + 1, L):
+                ex = p.sum(axis=tuple(a for a in range(N * L) if a not in (i * L + t, i * L + u)))
+                assert np.allclose(hb.tv[i][t, u, :4].reshape(2, 2, order="F"), ex, atol=1e-9)
     for e in range(g.ne):
         A = tt.TT(hb.message(e))
         assert abs(P.lognormalization(A)) < 1e-10
