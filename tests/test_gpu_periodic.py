@@ -98,6 +98,30 @@ def test_periodic_glauber_tree_vs_oracle_and_exact(schedule):
                 assert abs(P.evaluate(A, x) - P.evaluate(bo.mu[e], x)) < TOL
 
 
+def test_periodic_sis_tree_truncthresh0_vs_exact():
+    # T = 3, TruncThresh(0.0): the bonds are whatever the exact ranks are (dmax is only a capacity)
+    T, N = 3, 3
+    und = [(0, 1), (1, 2)]
+    go = O.BiDiGraph(N, und)
+    wo = [[OF.SISFactor(0.3, 0.25, 0.05)] * (T + 1) for _ in range(N)]
+    wd = [[M.SISFactor(0.3, 0.25, 0.05)] * (T + 1) for _ in range(N)]
+    phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(N)]
+    phi[0][1] = np.array([0.2, 1.0])
+    phi[2][3] = np.array([1.0, 0.4])
+    psi = [[np.ones((2, 2)) for _ in range(T + 1)] for _ in range(go.ne)]
+    bo, bd = _pair(go, und, N, T, 2, wo, wd, phi, psi, dmax=12)
+    P.iterate(bo, maxiter=6, trunc=tt.TruncThresh(0.0))
+    M.iterate_(bd, maxiter=6, svd_trunc=M.TruncThresh(0.0), tol=0.0, shuffle_nodes=False)
+    p, logZ = P.exact_prob(bo)
+    L = T + 1
+    be = _exact_marginals(p, N, L)
+    b_d = M.beliefs(bd)
+    for i in range(N):
+        assert np.allclose(np.array(b_d[i]), np.array(be[i]), atol=TOL)
+    assert abs(-M.bethe_free_energy(bd) - logZ) < TOL
+    assert np.allclose(bo.f, M.api.free_energy_contributions(bd), atol=TOL)
+
+
 def test_periodic_set_get_message_roundtrip_and_one_node_update():
     # random ring messages with a non-trivial closing bond go in through mpbp_set_message; ONE node update must equal the oracle's
     rng = np.random.default_rng(7)

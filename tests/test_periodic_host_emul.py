@@ -243,3 +243,27 @@ def test_periodic_sirs_binding_truncation_matches_the_oracle_sweeps(emu):
             hb.update(i, Tr(0, 3, 0.0))
     assert np.allclose(np.array(P.beliefs(bo)), np.array(hb.marg), atol=1e-8)
     assert np.allclose(bo.f, hb.f, atol=1e-8)
+
+
+def test_periodic_sis_tree_truncthresh0_vs_exact(emu):
+    # oracle twin: tests/test_oracle_golden.py::test_periodic_sis_tree_vs_exact_and_ring_invariances (T = 3, TruncThresh(0.0))
+    T, N = 3, 3
+    g = O.BiDiGraph(N, [(0, 1), (1, 2)])
+    wo = [[OF.SISFactor(0.3, 0.25, 0.05)] * (T + 1) for _ in range(N)]
+    wp = [[PF.SISFactor(0.3, 0.25, 0.05)] * (T + 1) for _ in range(N)]
+    phi = [[np.ones(2) for _ in range(T + 1)] for _ in range(N)]
+    phi[0][1] = np.array([0.2, 1.0])
+    phi[2][3] = np.array([1.0, 0.4])
+    psi = [[np.ones((2, 2)) for _ in range(T + 1)] for _ in range(g.ne)]
+    bo = P.PeriodicMPBP(g, wo, [2] * N, T, phi=phi, psi=psi)
+    P.iterate(bo, maxiter=6, trunc=tt.TruncThresh(0.0))
+    hb = HostPeriodicBP(emu, g, wp, [2] * N, T, phi, psi, dmax=12)
+    for _ in range(6):
+        for i in range(N):
+            hb.update(i, Tr(1, 0, 0.0))
+    p, logZ = P.exact_prob(bo)
+    L = T + 1
+    be = [[p.sum(axis=tuple(a for a in range(N * L) if a != i * L + t)) for t in range(L)] for i in range(N)]
+    assert np.allclose(np.array(hb.marg), np.array(be), atol=1e-9)
+    assert abs(-hb.f.sum() - logZ) < 1e-9
+    assert np.allclose(np.array(P.beliefs(bo)), np.array(hb.marg), atol=1e-9)
