@@ -492,7 +492,17 @@ def run_gpu(args, rank, world, local_rank):
                                  "concurrent streams") if prof_ms else "profiling skipped (--no-profile)",
                     heavy_ops=int(ctr["ops"]),
                     subspace_svd=dict(calls=int(ctr["svd_calls"]), iters=int(ctr["svd_iters"]), exact_fallbacks=int(ctr["svd_unconverged"])),
-                    kernel_family_ms={k: round(v, 1) for k, v in fam.items()})
+                    kernel_family_ms={k: round(v, 1) for k, v in fam.items()},
+                    # one fraction per kernel family of the profiled step (device-counted flops / event-timed family ms / DMMA peak)
+                    families={name: dict(flops=fl, ms=round(fam.get(key, 0.0), 1),
+                                         achieved=(fl / (fam[key] * 1e-3) / 1e12 if fam.get(key, 0.0) > 0 else None),
+                                         frac=(fl / (fam[key] * 1e-3) / 1e12 / float(peak[0]) if fam.get(key, 0.0) > 0 and peak[0] > 0 else None),
+                                         counts=what)
+                              for name, key, fl, what in (
+                                  ("qr_sweep1", "qr_sweep1", ctr["qr_flops"], "algorithmic 2mn^2 - 2/3 n^3 of the unsplit matrices"),
+                                  ("kron_carry", "kron_carry", ctr["kron_carry_flops"], "structured two-stage Kronecker contraction (runtime dims, non-zero prob_yy pairs)"),
+                                  ("jacobi_project", "jacobi_project", ctr["svd_subspace_flops"],
+                                   "GEMMs + block orthonormalisations of the subspace iterations run (executed; the family's ms also holds the small direct Jacobi SVDs)"))})
         line = dict(metric=wl["metric"], value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                     config=dict(workload=wl["name"] + f", {int(edges_total)} directed edges", config_id=args.config,

@@ -155,6 +155,12 @@ int mpbp_unpack_messages_dev(mpbp_handle h, int64_t n, const int64_t* edges, con
  * [3] device ms in the sweep-1 QR kernels (CUDA events, only when profiling is on), [4] heavy ops run,
  * [5] edge updates, [6] subspace-SVD iterations, [7] subspace-SVD calls resolved by the exact Jacobi fallback. */
 int mpbp_counters(mpbp_handle h, double* out8, int reset);
+/* device-counted FLOPs per kernel family since the last mpbp_counters(reset = 1): [0] sweep-1 QR, algorithmic (= counters[1]);
+ * [1] executed on top of [0] by TSQR splits (chunk triangles + merges; not credited to the roofline); [2] Kronecker carry
+ * (structured two-stage contraction, counted from the runtime dims and the non-zero prob_yy pairs); [3] blocked subspace SVDs
+ * (the two tall GEMMs and the block orthonormalisations of every iteration run; direct small Jacobi SVDs are not counted).
+ * Together with mpbp_kernel_times they give one roofline fraction per kernel family (bench.py: roofline.families). */
+int mpbp_family_flops(mpbp_handle h, double* out4);
 /* engine tuning knobs (none changes a result bit): "arena_gb" scratch arena size, "max_group_ops" ops per launch group,
  * "nstreams" (1..4) concurrent streams per cavity round, "qr_fill" CTAs below which tall QRs are TSQR-split,
  * "level_balance" (default 1) stagger the cavity levels of independent nodes so that every round carries similar

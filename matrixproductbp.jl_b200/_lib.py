@@ -41,6 +41,7 @@ SIGNATURES = {
     "mpbp_pack_messages_dev": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, C.c_void_p]),
     "mpbp_unpack_messages_dev": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, C.c_void_p]),
     "mpbp_counters": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
+    "mpbp_family_flops": (C.c_int, [C.c_void_p, c_dp]),
     "mpbp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "mpbp_kernel_times": (C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int]),
     "mpbp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -355,9 +355,12 @@ class MPBP:
         _lib.check(L.mpbp_set_message(self._h, e, _p(bonds, _lib.c_i32p), _p(data, _lib.c_dp)))
 
     def counters(self, reset=False):
+        fam = np.zeros(4)
+        _lib.check(_lib.lib().mpbp_family_flops(self._h, _p(fam, _lib.c_dp)))  # (read before the reset below clears them)
         out = np.zeros(8)
         _lib.check(_lib.lib().mpbp_counters(self._h, _p(out, _lib.c_dp), int(reset)))
-        return dict(launches=out[0], qr_flops=out[1], qr_ms=out[3], ops=out[4], edge_updates=out[5], svd_calls=out[2], svd_iters=out[6], svd_unconverged=out[7])
+        return dict(launches=out[0], qr_flops=out[1], qr_ms=out[3], ops=out[4], edge_updates=out[5], svd_calls=out[2], svd_iters=out[6], svd_unconverged=out[7],
+                    qr_split_extra_flops=fam[1], kron_carry_flops=fam[2], svd_subspace_flops=fam[3])
 
     def kernel_times(self, reset=False):
         out = np.zeros(9)

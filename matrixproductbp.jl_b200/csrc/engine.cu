@@ -2282,6 +2282,18 @@ int mpbp_counters(mpbp_handle h, double* out8, int reset) {
   return 0;
 }
 
+int mpbp_family_flops(mpbp_handle h, double* out4) {
+  if (!h || !out4) return fail("null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  double fl[24];
+  CUDA_OK(cudaMemcpy(fl, h->d_flops, 24 * sizeof(double), cudaMemcpyDeviceToHost));
+  out4[0] = fl[0];   // sweep-1 QR, algorithmic (unsplit 2mn^2 - 2/3 n^3)
+  out4[1] = fl[16];  // executed on top of that by the TSQR splits (chunk triangles + merges)
+  out4[2] = fl[17];  // Kronecker carry (k_kron_carry_mma), flops of the structured two-stage contraction
+  out4[3] = fl[7];   // blocked subspace SVDs (k_jacobi_project): GEMMs + block orthonormalisations of the iterations run
+  return 0;
+}
+
 int mpbp_set_stream(mpbp_handle h, void* cuda_stream) {
   if (!h) return fail("null handle");
   CUDA_OK(cudaSetDevice(h->device));
