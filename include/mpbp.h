@@ -57,8 +57,8 @@ int mpbp_create_infinite_bipartite(int kA, int kB, int T, int qA, int qB, int dm
  * starting from flat_periodic_mpem2 with d = 1.  mpbp_iterate runs onebpiter! on ring tensor trains (recursive factors only,
  * degree <= 10, dmax <= 16; csrc/periodic.cuh); mpbp_beliefs / mpbp_free_energy / mpbp_pair_beliefs / get / set_message work as on
  * an open handle (bonds[0] == bonds[T+1] is the closing bond); damping is the ring sum + compress! + normalize! of set_msg!.
- * Two-time marginals (option "twovar") work as on an open handle; alternate marginals and the forward sampler are not
- * defined on this path (loud errors).  periodic_mpbp_infinite_graph = mpbp_create_infinite followed by
+ * Two-time marginals (option "twovar") and the forward sampler (which, like the reference's onesample!, ignores the
+ * wrap-around factor) work as on an open handle; alternate marginals are not defined on this path (loud error).  periodic_mpbp_infinite_graph = mpbp_create_infinite followed by
  * mpbp_set_option(h, "periodic", 1) before the first iteration. */
 int mpbp_create_periodic(int64_t N, int64_t E2, int T, const int32_t* q, const int64_t* colptr, const int64_t* dst,
                          const int64_t* rev, int dmax, int device, mpbp_handle* out);

@@ -2119,7 +2119,8 @@ int mpbp_alternate_marginals(mpbp_handle h, double* out) {
 int mpbp_sample_prior(mpbp_handle h, uint64_t seed, int32_t* X) {
   if (!h || !X) return fail("null argument");
   if (h->inf_k > 0) return fail("sampling is defined on finite graphs (src/sampling.jl iterates the nodes of bp.g)");
-  if (h->periodic) return fail("the forward sampler needs an initial time: not defined for periodic-in-time dynamics");
+  // (periodic handles: like the reference's onesample!, the forward simulation starts from phi^0 and ignores the wrap-around
+  // factor w^T -- it only generates observations, test/periodic.jl:31)
   CUDA_OK(cudaSetDevice(h->device));
   std::vector<SampCls> sc(std::max<size_t>(h->classes.size(), 1));
   for (size_t ci = 0; ci < h->classes.size(); ++ci) {

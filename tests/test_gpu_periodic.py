@@ -229,8 +229,10 @@ def test_periodic_path_fails_loudly_where_it_is_not_defined():
     bp = M.periodic_mpbp(g, w, [2] * N, T, dmax=4)
     with pytest.raises(M.MPBPError):
         M.alternate_marginals(bp)
-    with pytest.raises(M.MPBPError):
-        M.sample_prior(bp, 1)
+    # the forward sampler is an input generator: like the reference's onesample! it ignores the wrap-around factor, so a
+    # periodic state draws the same trajectory as the open one (test/periodic.jl:31 draws observations from a periodic bp)
+    bo = M.mpbp(g, w, [2] * N, T, dmax=4)
+    assert np.array_equal(M.sample_prior(bp, 7), M.sample_prior(bo, 7))
     with pytest.raises(M.MPBPError):  # a truncation that lets a bond outgrow dmax is an error, never a silent cut
         M.iterate_(M.periodic_mpbp(g, [[M.SISFactor(0.3, 0.2)] * (T + 1) for _ in range(N)], [2] * N, T, phi=[[np.array([0.3, 0.7])] * (T + 1)] * N, dmax=1),
                    maxiter=2, svd_trunc=M.TruncThresh(1e-12), tol=0.0, shuffle_nodes=False)
