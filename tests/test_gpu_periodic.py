@@ -98,6 +98,63 @@ def test_periodic_glauber_tree_vs_oracle_and_exact(schedule):
                 assert abs(P.evaluate(A, x) - P.evaluate(bo.mu[e], x)) < TOL
 
 
+def test_periodic_reference_flow_glauber_model_observations_autocovariances():
+    # the whole flow of /root/reference/test/periodic.jl:1-75 through the model constructors: Ising -> Glauber(psi) ->
+    # periodic_mpbp(model) -> draw_node_observations!(bp, N) (hard one-hot phi) -> iterate!(maxiter=20, TruncBondThresh(10)) ->
+    # Z, beliefs, autocorrelations, autocovariances, pair beliefs against brute force (oracle.periodic.exact_prob)
+    rng = np.random.default_rng(111)
+    T, N = 2, 5
+    L = T + 1
+    und = [(0, 1), (1, 2), (1, 3)]
+    g = M.IndexedBiDiGraph(N, und)
+    h = rng.standard_normal(N)
+    ising = M.Ising(g, J=np.ones(len(g.undirected)), h=h, beta=1.0)
+    O_ = {(0, 1): (1, np.array([[0.1, 0.9], [0.3, 0.4]])), (1, 3): (2, np.array([[0.4, 0.6], [0.5, 0.9]])), (1, 2): (T, rng.random((2, 2)))}
+    psi_und = []
+    for (a, b) in g.undirected.tolist():
+        ps = [np.ones((2, 2)) for _ in range(L)]
+        if (a, b) in O_:
+            t, m = O_[(a, b)]
+            ps[t] = ps[t] * m
+        psi_und.append(ps)
+    gl = M.Glauber(ising, T, psi=psi_und)
+    for i in range(N):
+        gl.phi[i][0] = gl.phi[i][0] * np.array([0.75, 0.25])
+    bp = M.periodic_mpbp(gl, dmax=10)
+    X, observed = M.draw_node_observations_(bp, N, rng=5)
+    assert len(observed) == N
+    bp.set_option("twovar", T)
+    iters, cb = M.iterate_(bp, maxiter=20, svd_trunc=M.TruncBondThresh(10), tol=0.0, shuffle_nodes=False)
+    # brute force on the same inputs
+    go = O.BiDiGraph(N, und)
+    assert list(g.src) == go.src and list(g.dst) == go.dst
+    wo = [[OF.HomogeneousGlauberFactor(1.0, float(h[i]), 1.0)] * L for i in range(N)]
+    psi_dir = [[np.asarray(p) if g.src[e] < g.dst[e] else np.asarray(p).T for p in psi_und[g.und_of[e]]] for e in range(g.ne)]
+    bo = P.PeriodicMPBP(go, wo, [2] * N, T, phi=[[np.asarray(p, dtype=float).copy() for p in ph] for ph in bp.phi], psi=psi_dir)
+    p, logZ = P.exact_prob(bo)
+    assert abs(-M.bethe_free_energy(bp) - logZ) < TOL                                  # Z_exact ~ Z_bp
+    be = _exact_marginals(p, N, L)
+    b = M.beliefs(bp)
+    for i in range(N):
+        assert np.allclose(np.array(b[i]), np.array(be[i]), atol=TOL)                  # p_ex ~ p_bp
+    f = lambda x, i: 2 * x - 3                                                         # test/periodic.jl:41
+    r_bp, c_bp, mu = M.autocorrelations(f, bp), M.autocovariances(f, bp), M.means(f, bp)
+    fx = np.array([f(1, 0), f(2, 0)], dtype=float)
+    for i in range(N):
+        for t in range(L):
+            for u in range(t + 1, L):
+                ex = p.sum(axis=tuple(a for a in range(N * L) if a not in (i * L + t, i * L + u)))
+                r_ex = fx @ ex @ fx
+                assert abs(r_bp[i][t, u] - r_ex) < TOL                                 # r_bp ~ r_exact
+                assert abs(c_bp[i][t, u] - (r_ex - (fx @ be[i][t]) * (fx @ be[i][u]))) < TOL  # c_bp ~ c_exact
+    pb, _ = M.pair_beliefs(bp)
+    for e in range(g.ne):
+        i, j = int(g.src[e]), int(g.dst[e])
+        for t in range(L):
+            ex = p.sum(axis=tuple(a for a in range(N * L) if a not in (i * L + t, j * L + t)))
+            assert np.allclose(np.array(pb[e][t]), ex if i < j else ex.T, atol=TOL)
+
+
 def test_periodic_sis_tree_truncthresh0_vs_exact():
     # T = 3, TruncThresh(0.0): the bonds are whatever the exact ranks are (dmax is only a capacity)
     T, N = 3, 3
