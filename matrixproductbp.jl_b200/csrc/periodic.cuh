@@ -164,7 +164,8 @@ PER_FN double per_maxabs(const double* a, int n, double* red, int* err) {
     if (!(v <= 1.79e308)) bad = 1;  // NaN or Inf
     else m = fmax(m, v);
   }
-  if (bad) *err |= PER_ERR_NAN;  // benign race: every writer sets the same bit pattern family (OR of flags is re-read on the host)
+  if (bad) *err |= PER_ERR_NAN;  // (plain read-modify-write of the node's own error word: concurrent writers all set this same bit,
+                                 // and any non-zero word aborts the node update at the next per_failed())
   return per_block_max(m, red);
 }
 
