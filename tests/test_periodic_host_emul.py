@@ -267,3 +267,39 @@ def test_periodic_sis_tree_truncthresh0_vs_exact(emu):
     assert np.allclose(np.array(hb.marg), np.array(be), atol=1e-9)
     assert abs(-hb.f.sum() - logZ) < 1e-9
     assert np.allclose(np.array(P.beliefs(bo)), np.array(hb.marg), atol=1e-9)
+
+
+def test_periodic_sirs_tree_q3_vs_exact(emu):
+    # q = 3 (SIRS), degree-2 centre, random reweightings and pair observations: kernel source vs brute force and the oracle
+    rng = np.random.default_rng(9)
+    T, N = 2, 3
+    g = O.BiDiGraph(N, [(0, 1), (1, 2)])
+    par = (0.35, 0.2, 0.25, 0.05)
+    wo = [[OF.SIRSFactor(*par)] * (T + 1) for _ in range(N)]
+    wp = [[PF.SIRSFactor(*par)] * (T + 1) for _ in range(N)]
+    phi = [[0.2 + rng.random(3) for _ in range(T + 1)] for _ in range(N)]
+    psi = [[np.ones((3, 3)) for _ in range(T + 1)] for _ in range(g.ne)]
+    m = 0.3 + rng.random((3, 3))
+    for e in range(g.ne):
+        if (g.src[e], g.dst[e]) == (0, 1):
+            psi[e][1] = m
+        if (g.src[e], g.dst[e]) == (1, 0):
+            psi[e][1] = m.T
+    bo = P.PeriodicMPBP(g, wo, [3] * N, T, phi=phi, psi=psi)
+    P.iterate(bo, maxiter=5, trunc=tt.TruncBondThresh(12, 1e-13))
+    hb = HostPeriodicBP(emu, g, wp, [3] * N, T, phi, psi, dmax=12)
+    for _ in range(5):
+        for i in range(N):
+            hb.update(i, Tr(2, 12, 1e-13))
+    p, logZ = P.exact_prob(bo)
+    L = T + 1
+    be = [[p.sum(axis=tuple(a for a in range(N * L) if a != i * L + t)) for t in range(L)] for i in range(N)]
+    assert np.allclose(np.array(hb.marg), np.array(be), atol=1e-9)
+    assert abs(-hb.f.sum() - logZ) < 1e-9
+    assert np.allclose(np.array(P.beliefs(bo)), np.array(hb.marg), atol=1e-9)
+    pb, _ = hb.pair_beliefs()
+    for e in range(g.ne):
+        i, j = g.src[e], g.dst[e]
+        for t in range(L):
+            ex = p.sum(axis=tuple(a for a in range(N * L) if a not in (i * L + t, j * L + t)))
+            assert np.allclose(pb[e][t], ex if i < j else ex.T, atol=1e-9)
